@@ -1,0 +1,1045 @@
+// qs_device.cuh - device side of libquadsim: one thread per env (drone), the whole env step fused in registers.
+//
+// Reference semantics (amolchanov86/gym_art, paths under gym_art/quadrotor/):
+//   QuadrotorEnv._step            quadrotor.py:942-1028      -> env_step_kernel
+//   QuadrotorDynamics.step1       quadrotor.py:273-436       -> substep()
+//   controllers                   quadrotor_control.py       -> controller_cmds()
+//   compute_reward_weighted       quadrotor.py:544-638       -> compute_reward()
+//   SensorNoise.add_noise         sensor_noise.py:100-159    -> add_noise()
+//   state_<obs_repr>              get_state.py:5-260         -> build_obs()
+//   QuadrotorEnv._reset           quadrotor.py:1059-1144     -> reset_env()
+// Written for sm_100a only.  No tensor cores: the per-env maths is 3x3 / 4x4, not a dense contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qs {
+
+constexpr int BLOCK = 128;           // threads per CTA = envs per CTA
+constexpr int MAX_OBS = 25;
+constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 32;
+
+enum Ctrl { CTRL_RAW = 0, CTRL_VERTICAL, CTRL_VERTPLANE, CTRL_SHIFTED, CTRL_OMEGA_THRUST, CTRL_VELOCITY_YAW, CTRL_MELLINGER };
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel parameter block (passed by value as a __grid_constant__; lives in the constant bank)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct Params {
+  // buffers
+  R* state;                 // [rows][n][4]
+  const R* actions;         // [k][n][act_dim] or null
+  R* obs;                   // [n][obs_dim]
+  R* rew;                   // [n]
+  uint8_t* done;            // [n]
+  R* info;                  // [n][INFO_DIM] or null
+  const uint8_t* reset_mask;
+  const R* ou_z;            // injected: [n][sim_steps][4]
+  const R* obs_z;           // injected: [n][OBS_Z]
+  const R* reset_z;         // injected: [n][RESET_Z]
+  double* stats;            // [3]
+  int* status;              // sticky non-finite flag
+  long long n;              // envs on the handle = row stride of the state buffer
+  long long begin, end;     // env range [begin, end) this launch covers (chunked host pipeline)
+  long long env_id_offset;
+  unsigned long long step_count;
+  unsigned int seed_lo, seed_hi;
+  // clocks
+  double svd_timer, svd_period, dt_d;
+  // layout / config
+  int row_ou, row_act, row_gyro, row_goal;
+  int obs_dim, act_dim;
+  int k_steps, sim_steps, ep_len;
+  int controller, zero_middle, n_agents, dim_mode;
+  int obs_rel, obs_h, obs_acc, obs_act;
+  int init_random, auto_reset, sense_on, ou_on, gyro_bias_mode;
+  int dyn_controller, dyn_substeps;   // qs_dynamics_step
+  int inject, need_rare;              // variant selection (host)
+  // model
+  R dt;
+  R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
+  R inertia[3], inv_inertia[3];
+  R mass, inv_mass, lin, c_drag, c_roll, tau_up, tau_down, vel_damp, damp_omega_q;
+  R ou_theta, ou_sigma, arm, omega_max, gravity, t2w;
+  R jinv[4][4];
+  R room_lo[3], room_hi[3];
+  R goal[3], spawn_box, max_init_vel, max_init_omega, coll_dist;
+  // reward
+  R c_pos, c_effort, c_act_change, c_crash, c_orient, c_yaw, c_rot, c_attitude, c_spin, c_vel;
+  R c_pos_offset, c_pos_log_w, c_pos_lin_w, c_collision;
+  int log_pos;
+  // sensor noise
+  R sn_pos_std, sn_pos_unif, sn_vel_std, sn_vel_unif, sn_quat_std, sn_quat_unif;
+  R sn_gyro_density, sn_gyro_rw, sn_acc_static, sn_acc_dyn;
+  R gb_pi1, gb_sig1, gb_pi3, gb_sig3;   // gyro-bias walk folded over 1 (reset) / 3 (step) add_noise calls
+};
+
+// compile-time specialisation knobs; -1 = decided at run time from Params
+template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_>
+struct Traits {
+  static constexpr int CTRL = CTRL_;
+  static constexpr int OU = OU_;
+  static constexpr int SENSE = SENSE_;
+  static constexpr bool INJECT = INJECT_;
+  static constexpr bool RARE = RARE_;   // drag/roll, linearity != 1, damping, uniform/quaternion/gyro-bias noise,
+                                        // log reward, swarm, dim_mode != 3, per-env goal, info buffer
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// scalar maths
+// ---------------------------------------------------------------------------------------------------------
+template <typename R> struct Mth;
+template <> struct Mth<float> {
+  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+  static __device__ __forceinline__ float acos(float x) { return acosf(x); }
+  static __device__ __forceinline__ float log(float x) { return logf(x); }
+  static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+  static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ bool finite(float x) { return isfinite(x); }
+  // Box-Muller pair from two 32-bit words (Philox mode only; distribution parity, not bit parity)
+  static __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float* z0, float* z1) {
+    float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-08f;   // (0, 1]
+    float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;          // [0, 1)
+    float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    *z0 = r * c;
+    *z1 = r * s;
+  }
+  static __device__ __forceinline__ float unif(uint32_t a) { return (float)(int32_t)a * 4.656612873077393e-10f; }  // [-1, 1]
+};
+template <> struct Mth<double> {
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+  static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
+  static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+  static __device__ __forceinline__ double min(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ bool finite(double x) { return isfinite(x); }
+  static __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, double* z0, double* z1) {
+    double u1 = ((double)a + 1.0) * 2.3283064365386963e-10;        // (0, 1]
+    double u2 = (double)b * 2.3283064365386963e-10;                // [0, 1)
+    double r = ::sqrt(-2.0 * ::log(u1));
+    double s, c;
+    ::sincospi(2.0 * u2, &s, &c);
+    *z0 = r * c;
+    *z1 = r * s;
+  }
+  static __device__ __forceinline__ double unif(uint32_t a) { return (double)(int32_t)a * 4.656612873077393e-10; }
+};
+
+template <typename R> __device__ __forceinline__ R clampr(R x, R lo, R hi) { return Mth<R>::min(Mth<R>::max(x, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: no RNG state in HBM
+// ---------------------------------------------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    U4 n;
+    n.x = hi1 ^ c.y ^ k0;
+    n.y = lo1;
+    n.z = hi0 ^ c.w ^ k1;
+    n.w = lo0;
+    c = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// Philox slot map (8 bits): obs groups 0..9 (step) / 16..25 (reset obs), reset draws 26..38, OU substeps 64+s
+enum Slot { SLOT_OBS = 0, SLOT_RESET_OBS = 16, SLOT_RESET_POS = 26, SLOT_RESET_VEL = 27, SLOT_RESET_OM = 28,
+            SLOT_RESET_UP = 29, SLOT_RESET_FWD = 30, SLOT_OU = 64 };
+
+template <typename R>
+struct Rng {
+  uint32_t k0, k1, e0, e1, s0, s1;
+  __device__ __forceinline__ void init(const Params<R>& p, long long i, unsigned long long step) {
+    unsigned long long gid = (unsigned long long)(p.env_id_offset + i);
+    k0 = p.seed_lo; k1 = p.seed_hi;
+    e0 = (uint32_t)gid; e1 = (uint32_t)(gid >> 32);
+    s0 = (uint32_t)step; s1 = (uint32_t)(step >> 32) & 0x00FFFFFFu;
+  }
+  __device__ __forceinline__ U4 raw(int slot) const {
+    U4 c; c.x = e0; c.y = e1; c.z = s0; c.w = s1 | ((uint32_t)slot << 24);
+    return philox4x32_10(c, k0, k1);
+  }
+  __device__ __forceinline__ void normal4(int slot, R* z) const {
+    U4 u = raw(slot);
+    Mth<R>::normal2(u.x, u.y, &z[0], &z[1]);
+    Mth<R>::normal2(u.z, u.w, &z[2], &z[3]);
+  }
+  __device__ __forceinline__ void unif4(int slot, R* z) const {
+    U4 u = raw(slot);
+    z[0] = Mth<R>::unif(u.x); z[1] = Mth<R>::unif(u.y); z[2] = Mth<R>::unif(u.z); z[3] = Mth<R>::unif(u.w);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// per-env state in registers
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct St {
+  R px, py, pz, vx, vy, vz, wx, wy, wz;
+  R r[9];                 // rotation, row-major
+  R rd[4], cd[4], ou[4];  // thrust_rot_damp, thrust_cmds_damp, OU state
+  R tick, ret;
+  R pa[4];                // previous action (actions[0] of the last step)
+  R gb[3];                // gyro bias
+  R gx, gy, gz;           // goal
+  // not persisted
+  R ax, ay, az;           // world acceleration of the last substep (dynamics.acc)
+  R tqx, tqy, tqz;        // dynamics.torque
+  R odx, ody, odz;        // dynamics.omega_dot
+  bool w_is_f32;          // set_state stored omega as a float32 array (quadrotor.py:223), see substep()
+  bool fresh;             // accelerometer still holds its set_state value (0,0,GRAV) (quadrotor.py:221)
+};
+
+template <typename R> struct alignas(4 * sizeof(R)) V4 { R x, y, z, w; };
+
+template <typename R> __device__ __forceinline__ V4<R> ld4(const R* base, long long n, int row, long long i) {
+  return *reinterpret_cast<const V4<R>*>(base + ((long long)row * n + i) * 4);
+}
+template <typename R> __device__ __forceinline__ void st4(R* base, long long n, int row, long long i, R x, R y, R z, R w) {
+  V4<R> v; v.x = x; v.y = y; v.z = z; v.w = w;
+  *reinterpret_cast<V4<R>*>(base + ((long long)row * n + i) * 4) = v;
+}
+
+template <typename R, class T>
+__device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long long i, bool active) {
+  if (active) {
+    V4<R> q0 = ld4(p.state, p.n, 0, i), q1 = ld4(p.state, p.n, 1, i), q2 = ld4(p.state, p.n, 2, i);
+    V4<R> q3 = ld4(p.state, p.n, 3, i), q4 = ld4(p.state, p.n, 4, i), q5 = ld4(p.state, p.n, 5, i);
+    V4<R> q6 = ld4(p.state, p.n, 6, i);
+    s.px = q0.x; s.py = q0.y; s.pz = q0.z; s.vx = q0.w;
+    s.vy = q1.x; s.vz = q1.y; s.wx = q1.z; s.wy = q1.w;
+    s.wz = q2.x; s.r[0] = q2.y; s.r[1] = q2.z; s.r[2] = q2.w;
+    s.r[3] = q3.x; s.r[4] = q3.y; s.r[5] = q3.z; s.r[6] = q3.w;
+    s.r[7] = q4.x; s.r[8] = q4.y; s.tick = q4.z; s.ret = q4.w;
+    s.rd[0] = q5.x; s.rd[1] = q5.y; s.rd[2] = q5.z; s.rd[3] = q5.w;
+    s.cd[0] = q6.x; s.cd[1] = q6.y; s.cd[2] = q6.z; s.cd[3] = q6.w;
+  } else {
+    s.px = s.py = s.pz = s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s.r[k] = (k % 4 == 0) ? R(1) : R(0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s.rd[k] = R(0); s.cd[k] = R(0); }
+    s.tick = R(0); s.ret = R(0);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s.ou[k] = R(0); s.pa[k] = R(0); }
+  s.gb[0] = s.gb[1] = s.gb[2] = R(0);
+  s.gx = p.goal[0]; s.gy = p.goal[1]; s.gz = p.goal[2];
+  const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+  if (active) {
+    if (ou_on) { V4<R> q = ld4(p.state, p.n, p.row_ou, i); s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
+    if (p.row_act >= 0) { V4<R> q = ld4(p.state, p.n, p.row_act, i); s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+    if (T::RARE) {
+      if (p.row_gyro >= 0) { V4<R> q = ld4(p.state, p.n, p.row_gyro, i); s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; }
+      if (p.row_goal >= 0) { V4<R> q = ld4(p.state, p.n, p.row_goal, i); s.gx = q.x; s.gy = q.y; s.gz = q.z; }
+    }
+  }
+  s.ax = s.ay = s.az = R(0);
+  s.tqx = s.tqy = s.tqz = s.odx = s.ody = s.odz = R(0);
+  // straight after set_state()/reset() (tick 0, motor filter zeroed, :438-440) omega is still the float32 array of :223
+  s.w_is_f32 = (s.tick == R(0)) && (s.rd[0] == R(0)) && (s.rd[1] == R(0)) && (s.rd[2] == R(0)) && (s.rd[3] == R(0)) &&
+               (s.cd[0] == R(0)) && (s.cd[1] == R(0)) && (s.cd[2] == R(0)) && (s.cd[3] == R(0));
+  s.fresh = false;
+}
+
+template <typename R, class T>
+__device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, long long i) {
+  st4(p.state, p.n, 0, i, s.px, s.py, s.pz, s.vx);
+  st4(p.state, p.n, 1, i, s.vy, s.vz, s.wx, s.wy);
+  st4(p.state, p.n, 2, i, s.wz, s.r[0], s.r[1], s.r[2]);
+  st4(p.state, p.n, 3, i, s.r[3], s.r[4], s.r[5], s.r[6]);
+  st4(p.state, p.n, 4, i, s.r[7], s.r[8], s.tick, s.ret);
+  st4(p.state, p.n, 5, i, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
+  st4(p.state, p.n, 6, i, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
+  const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+  if (ou_on) st4(p.state, p.n, p.row_ou, i, s.ou[0], s.ou[1], s.ou[2], s.ou[3]);
+  if (p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
+  if (T::RARE) {
+    if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0));
+    // the goal row is read-only for the step path
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// polar re-orthonormalisation: replaces u,s,v = svd(R); R = u @ v (quadrotor.py:384-385).
+// R is within rounding of a rotation, so Newton's iteration X <- (X + X^-T)/2 reaches the same polar factor
+// to machine precision in one or two steps; four are run so a caller-supplied sloppy R also converges.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void polar_orthonormalize(R* r) {
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    R c00 = r[4] * r[8] - r[5] * r[7], c01 = r[5] * r[6] - r[3] * r[8], c02 = r[3] * r[7] - r[4] * r[6];
+    R c10 = r[2] * r[7] - r[1] * r[8], c11 = r[0] * r[8] - r[2] * r[6], c12 = r[1] * r[6] - r[0] * r[7];
+    R c20 = r[1] * r[5] - r[2] * r[4], c21 = r[2] * r[3] - r[0] * r[5], c22 = r[0] * r[4] - r[1] * r[3];
+    R det = r[0] * c00 + r[1] * c01 + r[2] * c02;
+    R h = R(0.5) / det;
+    r[0] = R(0.5) * r[0] + h * c00; r[1] = R(0.5) * r[1] + h * c01; r[2] = R(0.5) * r[2] + h * c02;
+    r[3] = R(0.5) * r[3] + h * c10; r[4] = R(0.5) * r[4] + h * c11; r[5] = R(0.5) * r[5] + h * c12;
+    r[6] = R(0.5) * r[6] + h * c20; r[7] = R(0.5) * r[7] + h * c21; r[8] = R(0.5) * r[8] + h * c22;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// QuadrotorDynamics.step1 (quadrotor.py:273-436).  z: 4 unit normals for the OU thrust noise.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>& p, const R* z, bool fire_svd) {
+  const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+  const R dt = p.dt;
+  R tsum = R(0), tqx = R(0), tqy = R(0), tqz = R(0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    R c = clampr(cmd[k], R(0), R(1));                                   // :279
+    R tau = (c < s.cd[k]) ? p.tau_down : p.tau_up;                      // :284-288 (tau pre-clipped to 1 on the host)
+    R rt = Mth<R>::sqrt(c);                                             // :294
+    s.rd[k] = tau * (rt - s.rd[k]) + s.rd[k];                           // :295
+    R cd = s.rd[k] * s.rd[k];                                           // :296
+    if (ou_on) {
+      s.ou[k] = s.ou[k] + (p.ou_theta * (R(0) - s.ou[k]) + p.ou_sigma * z[k]);   // quad_utils.py:197-201
+      cd = cd + c * s.ou[k];                                            // :299
+    }
+    cd = clampr(cd, R(0), R(1));                                        // :300
+    s.cd[k] = cd;
+    R t;
+    if (T::RARE) t = p.thrust_max[k] * ((R(1) - p.lin) * cd * cd + p.lin * cd);   // :302, :140
+    else t = p.thrust_max[k] * cd;                                      // linearity == 1
+    tqx += p.pcx[k] * t;                                                // :304, :310
+    tqy += p.pcy[k] * t;
+    tqz += p.tz[k] * cd;                                                // :307
+    tsum += t;                                                          // :362
+  }
+  R fdx = R(0), fdy = R(0), fdz = R(0);                                 // rotor drag force (body frame)
+  if (T::RARE) {
+    if (p.c_drag != R(0) || p.c_roll != R(0)) {                         // :318-349
+      R vbx = s.r[0] * s.vx + s.r[3] * s.vy + s.r[6] * s.vz;            // rot.T @ vel
+      R vby = s.r[1] * s.vx + s.r[4] * s.vy + s.r[7] * s.vz;
+      R vbz = s.r[2] * s.vx + s.r[5] * s.vy + s.r[8] * s.vz;
+      R dtx = R(0), dty = R(0), dtz = R(0), rtx = R(0), rty = R(0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        R vrx = vbx + (s.wy * p.ppz[k] - s.wz * p.ppy[k]);              // :323 omega x prop_pos
+        R vry = vby + (s.wz * p.ppx[k] - s.wx * p.ppz[k]);              // z component projected out (:325)
+        R sq = Mth<R>::sqrt(s.cd[k]);
+        R fx = -p.c_drag * sq * vrx, fy = -p.c_drag * sq * vry;         // :328
+        fdx += fx; fdy += fy;
+        dtx += fy * p.ppz[k];                                           // :331 f x prop_pos (f.z = 0)
+        dty += -fx * p.ppz[k];
+        dtz += fx * p.ppy[k] - fy * p.ppx[k];
+        rtx += -p.c_roll * p.ccw[k] * sq * vrx;                         // :334
+        rty += -p.c_roll * p.ccw[k] * sq * vry;
+      }
+      R vtx = dtx + rtx, vty = dty + rty, vtz = dtz;                    // :336
+      R vel_norm = Mth<R>::sqrt(vbx * vbx + vby * vby + vbz * vbz);     // :339
+      R rdf = Mth<R>::sqrt(fdx * fdx + fdy * fdy);                      // :340
+      R rdf_clip = clampr(rdf, R(0), vel_norm * p.mass / (R(2) * dt));  // :341
+      if (rdf > R(1e-6)) { R sc = rdf_clip; fdx = (fdx / rdf) * sc; fdy = (fdy / rdf) * sc; }   // :342-343
+      R rvt = Mth<R>::sqrt(vtx * vtx + vty * vty + vtz * vtz);          // :346
+      R iwx = s.wx * p.inertia[0], iwy = s.wy * p.inertia[1], iwz = s.wz * p.inertia[2];
+      R rvt_clip = clampr(rvt, R(0), Mth<R>::sqrt(iwx * iwx + iwy * iwy + iwz * iwz) / (R(2) * dt));   // :347
+      if (rvt > R(1e-6)) { vtx = (vtx / rvt) * rvt_clip; vty = (vty / rvt) * rvt_clip; vtz = (vtz / rvt) * rvt_clip; }
+      tqx += vtx; tqy += vty; tqz += vtz;                               // :361
+    }
+  }
+  s.tqx = tqx; s.tqy = tqy; s.tqz = tqz;
+  // ---- attitude: Rodrigues with the world-frame rate, left-multiplied (:370-378) ----
+  {
+    R ox = s.r[0] * s.wx + s.r[1] * s.wy + s.r[2] * s.wz;
+    R oy = s.r[3] * s.wx + s.r[4] * s.wy + s.r[5] * s.wz;
+    R oz = s.r[6] * s.wx + s.r[7] * s.wy + s.r[8] * s.wz;
+    R on = Mth<R>::sqrt(ox * ox + oy * oy + oz * oz);
+    if (on != R(0)) {
+      R inv = R(1) / on;
+      R kx = ox * inv, ky = oy * inv, kz = oz * inv;
+      // sin(a) and 1 - cos(a) from the half angle: no cancellation for the small per-substep angles
+      R sh, ch;
+      Mth<R>::sincos(R(0.5) * (on * dt), &sh, &ch);
+      R sa = R(2) * sh * ch, cm = R(2) * sh * sh;
+      R kxx = kx * kx, kyy = ky * ky, kzz = kz * kz, kxy = kx * ky, kxz = kx * kz, kyz = ky * kz;
+      R d00 = R(1) - cm * (kyy + kzz), d01 = cm * kxy - sa * kz, d02 = cm * kxz + sa * ky;
+      R d10 = cm * kxy + sa * kz, d11 = R(1) - cm * (kxx + kzz), d12 = cm * kyz - sa * kx;
+      R d20 = cm * kxz - sa * ky, d21 = cm * kyz + sa * kx, d22 = R(1) - cm * (kxx + kyy);
+      R n0 = d00 * s.r[0] + d01 * s.r[3] + d02 * s.r[6], n1 = d00 * s.r[1] + d01 * s.r[4] + d02 * s.r[7];
+      R n2 = d00 * s.r[2] + d01 * s.r[5] + d02 * s.r[8];
+      R n3 = d10 * s.r[0] + d11 * s.r[3] + d12 * s.r[6], n4 = d10 * s.r[1] + d11 * s.r[4] + d12 * s.r[7];
+      R n5 = d10 * s.r[2] + d11 * s.r[5] + d12 * s.r[8];
+      R n6 = d20 * s.r[0] + d21 * s.r[3] + d22 * s.r[6], n7 = d20 * s.r[1] + d21 * s.r[4] + d22 * s.r[7];
+      R n8 = d20 * s.r[2] + d21 * s.r[5] + d22 * s.r[8];
+      s.r[0] = n0; s.r[1] = n1; s.r[2] = n2; s.r[3] = n3; s.r[4] = n4; s.r[5] = n5; s.r[6] = n6; s.r[7] = n7; s.r[8] = n8;
+    }
+  }
+  if (fire_svd) polar_orthonormalize(s.r);                              // :381-386 (uniform across the grid)
+  // ---- body rates (:398-405): old omega in the gyroscopic term ----
+  {
+    R iwx = p.inertia[0] * s.wx, iwy = p.inertia[1] * s.wy, iwz = p.inertia[2] * s.wz;
+    R gx = (-s.wy) * iwz - (-s.wz) * iwy;                               // cross(-omega, I omega)
+    R gy = (-s.wz) * iwx - (-s.wx) * iwz;
+    R gz = (-s.wx) * iwy - (-s.wy) * iwx;
+    s.odx = p.inv_inertia[0] * (gx + tqx);
+    s.ody = p.inv_inertia[1] * (gy + tqy);
+    s.odz = p.inv_inertia[2] * (gz + tqz);
+    R fx = dt, fy = dt, fz = dt;
+    if (T::RARE) {
+      R w2x = s.wx * s.wx, w2y = s.wy * s.wy, w2z = s.wz * s.wz;
+      if (sizeof(R) == 8 && s.w_is_f32) {   // omega ** 2 on the float32 array set_state left behind (:223, :403)
+        w2x = (R)((float)s.wx * (float)s.wx); w2y = (R)((float)s.wy * (float)s.wy); w2z = (R)((float)s.wz * (float)s.wz);
+      }
+      fx = (R(1) - clampr(p.damp_omega_q * w2x, R(0), R(1))) * dt;      // :403-404
+      fy = (R(1) - clampr(p.damp_omega_q * w2y, R(0), R(1))) * dt;
+      fz = (R(1) - clampr(p.damp_omega_q * w2z, R(0), R(1))) * dt;
+    }
+    s.wx = clampr(s.wx + fx * s.odx, -p.omega_max, p.omega_max);        // :404-405
+    s.wy = clampr(s.wy + fy * s.ody, -p.omega_max, p.omega_max);
+    s.wz = clampr(s.wz + fz * s.odz, -p.omega_max, p.omega_max);
+    s.w_is_f32 = false;
+  }
+  // ---- translation (:418-436): position with the old velocity, acceleration with the new R ----
+  s.px = clampr(s.px + dt * s.vx, p.room_lo[0], p.room_hi[0]);
+  s.py = clampr(s.py + dt * s.vy, p.room_lo[1], p.room_hi[1]);
+  s.pz = clampr(s.pz + dt * s.vz, p.room_lo[2], p.room_hi[2]);
+  R bx = fdx, by = fdy, bz = tsum + fdz;                                // thrust + rotor_drag_force (body)
+  R ax, ay, az;
+  if (T::RARE) {
+    ax = p.inv_mass * (s.r[0] * bx + s.r[1] * by + s.r[2] * bz);
+    ay = p.inv_mass * (s.r[3] * bx + s.r[4] * by + s.r[5] * bz);
+    az = p.inv_mass * (s.r[6] * bx + s.r[7] * by + s.r[8] * bz) - R(9.81);
+  } else {
+    ax = p.inv_mass * (s.r[2] * bz);
+    ay = p.inv_mass * (s.r[5] * bz);
+    az = p.inv_mass * (s.r[8] * bz) - R(9.81);                          // GRAV constant, not self.gravity (:426)
+  }
+  s.ax = ax; s.ay = ay; s.az = az;
+  if (T::RARE) {
+    R vd = R(1) - p.vel_damp;
+    s.vx = vd * s.vx + dt * ax; s.vy = vd * s.vy + dt * ay; s.vz = vd * s.vz + dt * az;   // :431
+  } else {
+    s.vx = s.vx + dt * ax; s.vy = s.vy + dt * ay; s.vz = s.vz + dt * az;
+  }
+  s.fresh = false;
+}
+
+// accelerometer = R^T (acc + (0,0,gravity)) (:436); (0,0,GRAV) straight after set_state (:221)
+template <typename R>
+__device__ __forceinline__ void accelerometer(const St<R>& s, const Params<R>& p, R* a) {
+  if (s.fresh) { a[0] = R(0); a[1] = R(0); a[2] = R(9.81); return; }
+  R x = s.ax, y = s.ay, z = s.az + p.gravity;
+  a[0] = s.r[0] * x + s.r[3] * y + s.r[6] * z;
+  a[1] = s.r[1] * x + s.r[4] * y + s.r[7] * z;
+  a[2] = s.r[2] * x + s.r[5] * y + s.r[8] * z;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// controllers: policy action -> 4 normalized motor commands (quadrotor_control.py)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ void normalize3(R& x, R& y, R& z) {   // quad_utils.py:35-41
+  R n = Mth<R>::sqrt(x * x + y * y + z * z);
+  if (!(n < R(0.00001))) { x = x / n; y = y / n; z = z / n; }
+}
+
+template <typename R>
+__device__ __forceinline__ void jinv_mix(const Params<R>& p, R d0, R d1, R d2, R d3, R* cmd) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    cmd[k] = clampr(p.jinv[k][0] * d0 + p.jinv[k][1] * d1 + p.jinv[k][2] * d2 + p.jinv[k][3] * d3, R(0), R(1));
+}
+
+template <typename R>
+__device__ __forceinline__ void attitude_controller(const St<R>& s, const Params<R>& p, bool mellinger, const R* a, R* cmd) {
+  R adx, ady, adz, xcx, xcy, xcz, ewx, ewy, ewz, kp_a, kd_a, yaw_scale;
+  if (mellinger) {                                                      // :315-362
+    R tx = s.gx - s.px, ty = s.gy - s.py, tz = s.gz - s.pz;
+    R n = Mth<R>::sqrt(tx * tx + ty * ty + tz * tz);
+    if (!(n <= R(4))) { R f = R(4) / n; tx = f * tx; ty = f * ty; tz = f * tz; }   // clamp_norm, quad_utils.py:63-67
+    R epx = -tx, epy = -ty, epz = -tz;                                  // :320
+    adx = R(-4.5) * epx - R(3.5) * s.vx;                                // :323
+    ady = R(-4.5) * epy - R(3.5) * s.vy;
+    adz = R(-4.5) * epz - R(3.5) * s.vz + R(9.81);
+    xcx = R(1); xcy = R(0); xcz = R(0);                                 // :333
+    ewx = s.wx; ewy = s.wy; ewz = s.wz;
+    kp_a = R(200); kd_a = R(50); yaw_scale = R(0.2);
+  } else {                                                              // VelocityYawControl :250-281 (thrust_mag per :275)
+    adx = R(-5) * (s.vx - a[0]); ady = R(-5) * (s.vy - a[1]); adz = R(-5) * (s.vz - a[2]) + R(9.81);
+    xcx = s.r[0]; xcy = s.r[3]; xcz = s.r[6];
+    ewx = s.wx - R(0); ewy = s.wy - R(0); ewz = s.wz - a[3];
+    kp_a = R(100); kd_a = R(50); yaw_scale = R(1);
+  }
+  R zx = adx, zy = ady, zz = adz;
+  normalize3(zx, zy, zz);                                               // :338
+  R yx = zy * xcz - zz * xcy, yy = zz * xcx - zx * xcz, yz = zx * xcy - zy * xcx;   // cross(zb, xc)
+  normalize3(yx, yy, yz);                                               // :339
+  R xx = yy * zz - yz * zy, xy = yz * zx - yx * zz, xz = yx * zy - yy * zx;          // cross(yb, zb) :340
+  // A = R_des^T R ; e_R = 0.5 * vee(A - A^T) (:344-346)
+  R a21 = zx * s.r[1] + zy * s.r[4] + zz * s.r[7], a12 = yx * s.r[2] + yy * s.r[5] + yz * s.r[8];
+  R a02 = xx * s.r[2] + xy * s.r[5] + xz * s.r[8], a20 = zx * s.r[0] + zy * s.r[3] + zz * s.r[6];
+  R a10 = yx * s.r[0] + yy * s.r[3] + yz * s.r[6], a01 = xx * s.r[1] + xy * s.r[4] + xz * s.r[7];
+  R erx = R(0.5) * (a21 - a12), ery = R(0.5) * (a02 - a20), erz = R(0.5) * (a10 - a01);
+  erz *= yaw_scale;                                                     // :347
+  R kwx = kd_a * ewx, kwy = kd_a * ewy, kwz = kd_a * ewz;
+  if (sizeof(R) == 8 && mellinger && s.w_is_f32) {                      // float32 product on the f32 omega array (:350)
+    kwx = (R)(50.0f * (float)ewx); kwy = (R)(50.0f * (float)ewy); kwz = (R)(50.0f * (float)ewz);
+  }
+  R dwx = -kp_a * erx - kwx, dwy = -kp_a * ery - kwy, dwz = -kp_a * erz - kwz;       // :350
+  R thrust_mag = adx * s.r[2] + ady * s.r[5] + adz * s.r[8];            // :352
+  jinv_mix(p, thrust_mag, dwx, dwy, dwz, cmd);                          // :357-359
+}
+
+template <typename R, class T>
+__device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>& p, int ctrl, const R* a, R* cmd) {
+  if (ctrl == CTRL_RAW || ctrl == CTRL_VERTICAL || ctrl == CTRL_VERTPLANE) {   // :72-99, :116-136, :159-179
+    R lo = p.zero_middle ? R(-1) : R(0);
+    R b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      R v = p.zero_middle ? R(0.5) * (a[k] + R(1)) : R(1) * (a[k] + R(0));
+      b[k] = clampr(v, lo, R(1));
+    }
+    if (ctrl == CTRL_RAW) { cmd[0] = b[0]; cmd[1] = b[1]; cmd[2] = b[2]; cmd[3] = b[3]; }
+    else if (ctrl == CTRL_VERTICAL) { cmd[0] = cmd[1] = cmd[2] = cmd[3] = b[0]; }
+    else { cmd[0] = cmd[1] = b[0]; cmd[2] = cmd[3] = b[1]; }
+  } else if (ctrl == CTRL_SHIFTED) {                                    // :23-27
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cmd[k] = clampr((a[k] + R(1)) / p.t2w, R(0), R(1));
+  } else if (ctrl == CTRL_OMEGA_THRUST) {                               // :225-234
+    R dwx = R(-5) * (s.wx - a[1]), dwy = R(-5) * (s.wy - a[2]), dwz = R(-5) * (s.wz - a[3]);
+    R acc_des = R(9.81) * (a[0] + R(1));
+    jinv_mix(p, acc_des, dwx, dwy, dwz, cmd);
+  } else {
+    attitude_controller(s, p, ctrl == CTRL_MELLINGER, a, cmd);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// reward (quadrotor.py:544-638; log variant quadrotor_multi.py:554)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, const R* a, const R* a_prev,
+                                            bool crashed, bool collided, R* costs) {
+  R dx = s.gx - s.px, dy = s.gy - s.py, dz = s.gz - s.pz;
+  R dist = Mth<R>::sqrt(dx * dx + dy * dy + dz * dz);
+  R c_pos;
+  if (T::RARE && p.log_pos) c_pos = p.c_pos * (p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist);
+  else c_pos = p.c_pos * dist;                                          // :547-549
+  R c_eff = p.c_effort * Mth<R>::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
+  R c_ac = R(0);
+  if (p.c_act_change != R(0)) {                                         // :556-558
+    R e0 = a[0] - a_prev[0], e1 = a[1] - a_prev[1], e2 = a[2] - a_prev[2], e3 = a[3] - a_prev[3];
+    c_ac = p.c_act_change * Mth<R>::sqrt(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+  }
+  R c_vel = R(0);
+  if (p.c_vel != R(0)) c_vel = p.c_vel * Mth<R>::sqrt(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);   // :562-563
+  R c_or = p.c_orient * (-s.r[8]);                                      // :567-568
+  R c_yaw = p.c_yaw * (-s.r[0]);                                        // :570-571
+  R c_rot = R(0), c_att = R(0);
+  if (p.c_rot != R(0)) c_rot = p.c_rot * Mth<R>::acos(clampr(((s.r[0] + s.r[4] + s.r[8]) - R(1)) / R(2), R(-1), R(1)));
+  if (p.c_attitude != R(0)) c_att = p.c_attitude * Mth<R>::acos(clampr(s.r[8], R(-1), R(1)));      // :580-581
+  R c_spin = p.c_spin * Mth<R>::sqrt(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);                     // :585-586
+  R c_crash = crashed ? p.c_crash : R(0);                               // :590-591
+  R sum = ((c_pos + c_eff) + (c_crash + c_or)) + ((c_yaw + c_rot) + (c_att + c_spin));            // np.sum pairwise
+  sum = (sum + c_ac) + c_vel;                                           // :593-604
+  if (T::RARE) { if (collided) sum += p.c_collision; }
+  if (costs) {
+    costs[0] = c_pos; costs[1] = c_eff; costs[2] = c_crash; costs[3] = c_or; costs[4] = c_yaw;
+    costs[5] = c_rot; costs[6] = c_att; costs[7] = c_spin; costs[8] = c_ac; costs[9] = c_vel;
+  }
+  return -p.dt * sum;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// noise sources: injected (host-supplied unit draws) or Philox
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+struct NoiseSrc {
+  const Params<R>& p;
+  long long i;
+  Rng<R> rng;
+  __device__ __forceinline__ NoiseSrc(const Params<R>& p_, long long i_) : p(p_), i(i_) {}
+  __device__ __forceinline__ void begin_step(unsigned long long step) { if (!T::INJECT) rng.init(p, i, step); }
+
+  __device__ __forceinline__ void ou(int sub, R* z) const {
+    if (T::INJECT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) z[k] = p.ou_z ? p.ou_z[(i * p.sim_steps + sub) * 4 + k] : R(0);
+    } else {
+      rng.normal4(SLOT_OU + sub, z);
+    }
+  }
+  // one 3-vector group of an add_noise call: g = slot/3 in the QS_Z_* layout
+  __device__ __forceinline__ void obs3(bool reset_obs, int g, bool is_unif, R* z) const {
+    if (T::INJECT) {
+      const R* src = reset_obs ? p.reset_z : p.obs_z;
+      long long base = reset_obs ? i * RESET_Z + 18 : i * OBS_Z;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) z[k] = src ? src[base + g * 3 + k] : R(0);
+    } else {
+      R t[4];
+      int slot = (reset_obs ? SLOT_RESET_OBS : SLOT_OBS) + g;
+      if (is_unif) rng.unif4(slot, t); else rng.normal4(slot, t);
+      z[0] = t[0]; z[1] = t[1]; z[2] = t[2];
+    }
+  }
+  __device__ __forceinline__ R reset_at(int k) const { return p.reset_z ? p.reset_z[i * RESET_Z + k] : R(0); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// SensorNoise.add_noise (sensor_noise.py:100-159) + observation assembly (get_state.py)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void rot2quat(const R* r, R* q) {            // sensor_noise.py:26-55
+  R tr = r[0] + r[4] + r[8];
+  if (tr > R(0)) {
+    R S = Mth<R>::sqrt(tr + R(1)) * R(2);
+    q[0] = R(0.25) * S; q[1] = (r[7] - r[5]) / S; q[2] = (r[2] - r[6]) / S; q[3] = (r[3] - r[1]) / S;
+  } else if (r[0] > r[4] && r[0] > r[8]) {
+    R S = Mth<R>::sqrt(R(1) + r[0] - r[4] - r[8]) * R(2);
+    q[0] = (r[7] - r[5]) / S; q[1] = R(0.25) * S; q[2] = (r[1] + r[3]) / S; q[3] = (r[2] + r[6]) / S;
+  } else if (r[4] > r[8]) {
+    R S = Mth<R>::sqrt(R(1) + r[4] - r[0] - r[8]) * R(2);
+    q[0] = (r[2] - r[6]) / S; q[1] = (r[1] + r[3]) / S; q[2] = R(0.25) * S; q[3] = (r[5] + r[7]) / S;
+  } else {
+    R S = Mth<R>::sqrt(R(1) + r[8] - r[0] - r[4]) * R(2);
+    q[0] = (r[3] - r[1]) / S; q[1] = (r[2] + r[6]) / S; q[2] = (r[5] + r[7]) / S; q[3] = R(0.25) * S;
+  }
+}
+
+template <typename R, class T>
+__device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const NoiseSrc<R, T>& ns, bool reset_obs,
+                                          const R* act_prev, R* o) {
+  const bool sense = T::SENSE >= 0 ? (T::SENSE != 0) : (p.sense_on != 0);
+  R px = s.px, py = s.py, pz = s.pz, vx = s.vx, vy = s.vy, vz = s.vz, wx = s.wx, wy = s.wy, wz = s.wz;
+  R rr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rr[k] = s.r[k];
+  R acc[3] = {R(0), R(0), R(0)};
+  if (p.obs_acc) accelerometer(s, p, acc);
+  if (sense) {
+    R z[3];
+    ns.obs3(reset_obs, 0, false, z);                                    // :116-118
+    px += p.sn_pos_std * z[0]; py += p.sn_pos_std * z[1]; pz += p.sn_pos_std * z[2];
+    if (T::RARE && p.sn_pos_unif != R(0)) {
+      ns.obs3(reset_obs, 1, true, z);
+      px += p.sn_pos_unif * z[0]; py += p.sn_pos_unif * z[1]; pz += p.sn_pos_unif * z[2];
+    }
+    ns.obs3(reset_obs, 2, false, z);                                    // :122-124
+    vx += p.sn_vel_std * z[0]; vy += p.sn_vel_std * z[1]; vz += p.sn_vel_std * z[2];
+    if (T::RARE && p.sn_vel_unif != R(0)) {
+      ns.obs3(reset_obs, 3, true, z);
+      vx += p.sn_vel_unif * z[0]; vy += p.sn_vel_unif * z[1]; vz += p.sn_vel_unif * z[2];
+    }
+    ns.obs3(reset_obs, 4, false, z);
+    if (T::RARE && p.gyro_bias_mode) {                                  // :127-128, :162-170 (walk folded over the calls)
+      R pi_ = reset_obs ? p.gb_pi1 : p.gb_pi3, sg = reset_obs ? p.gb_sig1 : p.gb_sig3;
+      s.gb[0] = pi_ * s.gb[0] + sg * z[0]; s.gb[1] = pi_ * s.gb[1] + sg * z[1]; s.gb[2] = pi_ * s.gb[2] + sg * z[2];
+      R z2[3];
+      ns.obs3(reset_obs, 5, false, z2);
+      wx = wx + s.gb[0] + p.sn_gyro_rw * z2[0]; wy = wy + s.gb[1] + p.sn_gyro_rw * z2[1]; wz = wz + s.gb[2] + p.sn_gyro_rw * z2[2];
+    } else {
+      wx += p.sn_gyro_density * z[0]; wy += p.sn_gyro_density * z[1]; wz += p.sn_gyro_density * z[2];   // :130-131
+    }
+    // rotation: R -> quaternion -> (x small-angle quaternion) -> R (:134-147); a pure round trip by default
+    R q[4];
+    rot2quat(s.r, q);
+    if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) {
+      R zn[3], zu[3];
+      ns.obs3(reset_obs, 6, false, zn);
+      ns.obs3(reset_obs, 7, true, zu);
+      R tx = p.sn_quat_std * zn[0] + p.sn_quat_unif * zu[0], ty = p.sn_quat_std * zn[1] + p.sn_quat_unif * zu[1];
+      R tz = p.sn_quat_std * zn[2] + p.sn_quat_unif * zu[2];
+      R qs = (tx * tx + ty * ty + tz * tz) / R(4);                      // sensor_noise.py:9-21
+      R t0, f;
+      if (qs < R(1)) { t0 = Mth<R>::sqrt(R(1) - qs); f = R(0.5); }
+      else { t0 = R(1) / Mth<R>::sqrt(R(1) + qs); f = R(0.5) * t0; }
+      R t1 = tx * f, t2 = ty * f, t3 = tz * f;
+      R tn = Mth<R>::sqrt(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3);
+      t0 /= tn; t1 /= tn; t2 /= tn; t3 /= tn;
+      R n0 = q[0] * t0 - q[1] * t1 - q[2] * t2 - q[3] * t3;             // quad_utils.py:92-99
+      R n1 = q[0] * t1 + q[1] * t0 - q[2] * t3 + q[3] * t2;
+      R n2 = q[0] * t2 + q[1] * t3 + q[2] * t0 - q[3] * t1;
+      R n3 = q[0] * t3 - q[1] * t2 + q[2] * t1 + q[3] * t0;
+      q[0] = n0; q[1] = n1; q[2] = n2; q[3] = n3;
+    }
+    R qw = q[0], qx = q[1], qy = q[2], qz = q[3];                       // quad_utils.py:82-87
+    rr[0] = R(1) - R(2) * qy * qy - R(2) * qz * qz; rr[1] = R(2) * qx * qy - R(2) * qz * qw; rr[2] = R(2) * qx * qz + R(2) * qy * qw;
+    rr[3] = R(2) * qx * qy + R(2) * qz * qw; rr[4] = R(1) - R(2) * qx * qx - R(2) * qz * qz; rr[5] = R(2) * qy * qz - R(2) * qx * qw;
+    rr[6] = R(2) * qx * qz - R(2) * qy * qw; rr[7] = R(2) * qy * qz + R(2) * qx * qw; rr[8] = R(1) - R(2) * qx * qx - R(2) * qy * qy;
+    if (p.obs_acc) {                                                    // :156-157
+      R zs[3], zd[3];
+      ns.obs3(reset_obs, 8, false, zs);
+      ns.obs3(reset_obs, 9, false, zd);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[k] = acc[k] + p.sn_acc_static * zs[k] + acc[k] * (p.sn_acc_dyn * zd[k]);
+    }
+  }
+  R ex = px - s.gx, ey = py - s.gy, ez = pz - s.gz;                     // get_state.py:15
+  if (p.obs_rel) {                                                      // get_state.py:159-160 (true R)
+    R tx = s.r[0] * ex + s.r[3] * ey + s.r[6] * ez, ty = s.r[1] * ex + s.r[4] * ey + s.r[7] * ez;
+    R tz = s.r[2] * ex + s.r[5] * ey + s.r[8] * ez;
+    ex = tx; ey = ty; ez = tz;
+    tx = s.r[0] * vx + s.r[3] * vy + s.r[6] * vz; ty = s.r[1] * vx + s.r[4] * vy + s.r[7] * vz;
+    tz = s.r[2] * vx + s.r[5] * vy + s.r[8] * vz;
+    vx = tx; vy = ty; vz = tz;
+  }
+  o[0] = ex; o[1] = ey; o[2] = ez; o[3] = vx; o[4] = vy; o[5] = vz;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) o[6 + k] = rr[k];
+  o[15] = wx; o[16] = wy; o[17] = wz;
+  // tail (h | acc+act | act) is written by the caller from these scratch slots
+  o[18] = pz;
+  o[19] = acc[0]; o[20] = acc[1]; o[21] = acc[2];
+  o[22] = act_prev[0]; o[23] = act_prev[1]; o[24] = act_prev[2]; o[25] = act_prev[3];
+}
+
+// writes one env's observation row into the CTA's shared tile in final [obs_dim] order
+template <typename R>
+__device__ __forceinline__ void obs_to_tile(const Params<R>& p, const R* o, R* row) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) row[k] = o[k];
+  int n = 18;
+  if (p.obs_h) row[n++] = o[18];
+  if (p.obs_acc) { row[n] = o[19]; row[n + 1] = o[20]; row[n + 2] = o[21]; n += 3; }
+  if (p.obs_act) { row[n] = o[22]; row[n + 1] = o[23]; row[n + 2] = o[24]; row[n + 3] = o[25]; }
+}
+
+// coalesced copy of the CTA's [BLOCK][obs_dim] tile to global memory
+template <typename R>
+__device__ __forceinline__ void flush_tile(const Params<R>& p, const R* tile, long long block_first, const uint8_t* row_valid) {
+  long long rows = p.end - block_first;
+  if (rows > BLOCK) rows = BLOCK;
+  int total = (int)rows * p.obs_dim;
+  R* dst = p.obs + block_first * p.obs_dim;
+  if (row_valid == nullptr && (total & 3) == 0 && ((p.obs_dim * BLOCK) & 3) == 0) {
+    const V4<R>* t4 = reinterpret_cast<const V4<R>*>(tile);
+    V4<R>* d4 = reinterpret_cast<V4<R>*>(dst);
+    for (int k = threadIdx.x; k < (total >> 2); k += BLOCK) d4[k] = t4[k];
+  } else {
+    for (int k = threadIdx.x; k < total; k += BLOCK) {
+      if (row_valid == nullptr || row_valid[k / p.obs_dim]) dst[k] = tile[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// QuadrotorEnv._reset (quadrotor.py:1059-1144) for one env
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const NoiseSrc<R, T>& ns) {
+  const R PI = R(3.14159265358979323846);
+  R u[4];
+  if (T::INJECT) { u[0] = ns.reset_at(0); u[1] = ns.reset_at(1); u[2] = ns.reset_at(2); u[3] = ns.reset_at(3); }
+  else ns.rng.unif4(SLOT_RESET_POS, u);
+  R x = p.spawn_box * u[0] + s.gx, y = p.spawn_box * u[1] + s.gy, z = p.spawn_box * u[2] + s.gz;   // :1087
+  if (T::RARE) {
+    if (p.dim_mode == 1) { x = s.gx; y = s.gy; }                        // :1089-1092
+    else if (p.dim_mode == 2) { y = s.gy; }
+  }
+  if (z < R(0.25)) z = R(0.25);                                         // :1094
+  s.px = x; s.py = y; s.pz = z;
+  if (p.init_random) {                                                  // :1113-1115 -> :227-239
+    R a[4], b[4], up[4], fw[4];
+    if (T::INJECT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = ns.reset_at(4 + k); b[k] = ns.reset_at(8 + k); }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { up[k] = ns.reset_at(12 + k); fw[k] = ns.reset_at(15 + k); }
+    } else {
+      ns.rng.unif4(SLOT_RESET_VEL, a);
+      ns.rng.unif4(SLOT_RESET_OM, b);
+      ns.rng.normal4(SLOT_RESET_UP, up);
+    }
+    R vm = p.max_init_vel, om = p.max_init_omega;
+    R vx = vm * a[0], vy = vm * a[1], vz = vm * a[2];                   // :230
+    R vmag = vm * (R(0.5) + R(0.5) * a[3]);                             // :231
+    R f = vmag / (Mth<R>::sqrt(vx * vx + vy * vy + vz * vz) + R(1e-6)); // :232
+    s.vx = f * vx; s.vy = f * vy; s.vz = f * vz;
+    R wx = om * b[0], wy = om * b[1], wz = om * b[2];                   // :234
+    R wmag = om * (R(0.5) + R(0.5) * b[3]);                             // :235
+    f = wmag / (Mth<R>::sqrt(wx * wx + wy * wy + wz * wz) + R(1e-6));   // :236
+    s.wx = f * wx; s.wy = f * wy; s.wz = f * wz;
+    R ux = up[0], uy = up[1], uz = up[2];                               // quad_utils.py:47-57
+    normalize3(ux, uy, uz);
+    R fx, fy, fz;
+    if (T::INJECT) { fx = fw[0]; fy = fw[1]; fz = fw[2]; normalize3(fx, fy, fz); }
+    else {
+#pragma unroll 1
+      for (int tr = 0; tr < 8; ++tr) {                                  // rejection loop :51-52 (p(reject) = 2.5 %)
+        ns.rng.normal4(SLOT_RESET_FWD + tr, fw);
+        fx = fw[0]; fy = fw[1]; fz = fw[2];
+        normalize3(fx, fy, fz);
+        if (!(fx * ux + fy * uy + fz * uz > R(0.95))) break;
+      }
+    }
+    R lx = uy * fz - uz * fy, ly = uz * fx - ux * fz, lz = ux * fy - uy * fx;   // left = normalize(cross(up, fwd))
+    normalize3(lx, ly, lz);
+    ux = fy * lz - fz * ly; uy = fz * lx - fx * lz; uz = fx * ly - fy * lx;     // up = cross(fwd, left)
+    s.r[0] = fx; s.r[1] = lx; s.r[2] = ux;                              // column_stack([fwd, left, up])
+    s.r[3] = fy; s.r[4] = ly; s.r[5] = uy;
+    s.r[6] = fz; s.r[7] = lz; s.r[8] = uz;
+  } else {                                                              // :1118-1126
+    s.vx = s.vy = s.vz = R(0);
+    s.wx = s.wy = s.wz = R(0);
+    R psi;
+    if (T::INJECT) psi = PI * u[3];                                     // the accepted randyaw() draw
+    else psi = Mth<R>::atan2(-y, -x) + (PI / R(3)) * u[3];              // same law as the rejection loop :1124-1126
+    if (T::RARE) { if (p.dim_mode != 3) psi = R(0); }                   // :1120-1121
+    R sp, cp;
+    Mth<R>::sincos(psi, &sp, &cp);
+    s.r[0] = cp; s.r[1] = -sp; s.r[2] = R(0);
+    s.r[3] = sp; s.r[4] = cp; s.r[5] = R(0);
+    s.r[6] = R(0); s.r[7] = R(0); s.r[8] = R(1);
+  }
+  // set_state rounds omega to float32 (:223)
+  s.wx = (R)(float)s.wx; s.wy = (R)(float)s.wy; s.wz = (R)(float)s.wz;
+  s.w_is_f32 = true;
+  s.fresh = true;
+  s.ax = s.ay = s.az = R(0);                                            // :220
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s.rd[k] = R(0); s.cd[k] = R(0); s.pa[k] = R(0); }   // :438-440, :1141
+  s.tick = R(0);                                                        // :1140
+  s.ret = R(0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// swarm contact (builder-authored spec, no reference counterpart; see oracle collide_swarm and DESIGN.md).
+// M = n_agents consecutive lanes form one swarm env; each lane visits its M-1 partners by shuffle and sums the
+// impulses computed from the PRE-collision velocities, so the result is independent of pair order.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R shfl(R v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <typename R>
+__device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p) {
+  const int M = p.n_agents;
+  const int lane = threadIdx.x & 31;
+  const int base = lane & ~(M - 1);
+  R dvx = R(0), dvy = R(0), dvz = R(0);
+  bool hit = false;
+#pragma unroll 1
+  for (int j = 1; j < M; ++j) {
+    int src = base | ((lane + j) & (M - 1));
+    R qx = shfl(s.px, src), qy = shfl(s.py, src), qz = shfl(s.pz, src);
+    R ux = shfl(s.vx, src), uy = shfl(s.vy, src), uz = shfl(s.vz, src);
+    R dx = s.px - qx, dy = s.py - qy, dz = s.pz - qz;
+    R dist = Mth<R>::sqrt(dx * dx + dy * dy + dz * dz);
+    R inv = R(1) / Mth<R>::max(dist, R(1e-5));
+    R nx = dx * inv, ny = dy * inv, nz = dz * inv;
+    R delta = (ux - s.vx) * nx + (uy - s.vy) * ny + (uz - s.vz) * nz;
+    bool c = dist < p.coll_dist;
+    hit = hit || c;
+    if (c && delta > R(0)) { dvx += delta * nx; dvy += delta * ny; dvz += delta * nz; }
+  }
+  s.vx += dvx; s.vy += dvy; s.vz += dvz;
+  return hit;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// THE kernel: QuadrotorEnv.step for every env (quadrotor.py:942-1028), k_steps times, + auto-reset
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__ Params<R> p) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  R* tile = reinterpret_cast<R*>(smem_raw);                             // [BLOCK][obs_dim]
+  __shared__ double red[3][BLOCK / 32];
+
+  const long long block_first = p.begin + (long long)blockIdx.x * BLOCK;
+  const long long i = block_first + threadIdx.x;
+  const bool active = i < p.end;
+  const int ctrl = T::CTRL >= 0 ? T::CTRL : p.controller;
+
+  St<R> s;
+  load_state<R, T>(s, p, i, active);
+  NoiseSrc<R, T> ns(p, active ? i : 0);
+
+  double svd_t = p.svd_timer;
+  R rew_sum = R(0);
+  bool done_any = false;
+  R o[26];
+  double st_ret = 0.0, st_ret2 = 0.0, st_n = 0.0;
+
+#pragma unroll 1
+  for (int ks = 0; ks < p.k_steps; ++ks) {
+    ns.begin_step(p.step_count + (unsigned long long)ks);
+    // ---- action (:943-944) ----
+    R a[4] = {R(0), R(0), R(0), R(0)};
+    if (active && p.actions != nullptr) {
+      const R* ap = p.actions + ((long long)ks * p.n + i) * p.act_dim;
+      if (p.act_dim == 4) { V4<R> v = *reinterpret_cast<const V4<R>*>(ap); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k < p.act_dim) a[k] = ap[k];
+      }
+    }
+    R a_prev[4] = {s.pa[0], s.pa[1], s.pa[2], s.pa[3]};                 // actions[1]
+    // ---- controller + dynamics (:966-970, :261-262) ----
+    R cmd[4];
+    controller_cmds<R, T>(s, p, ctrl, a, cmd);
+#pragma unroll 1
+    for (int sub = 0; sub < p.sim_steps; ++sub) {
+      svd_t += p.dt_d;                                                  // :381
+      bool fire = svd_t > p.svd_period;                                 // :382
+      if (fire) svd_t = 0.0;
+      R z[4] = {R(0), R(0), R(0), R(0)};
+      const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+      if (ou_on) ns.ou(sub, z);
+      substep<R, T>(s, cmd, p, z, fire);
+    }
+    bool collided = false;
+    if (T::RARE) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
+    // ---- crash, reward, tick, done (:974-987) ----
+    bool crashed = s.pz <= p.arm;                                       // :977
+    R costs[10];
+    R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::RARE && p.info) ? costs : nullptr);
+    if (!Mth<R>::finite(rew) && active) atomicOr(p.status, 1);          // :633-636
+    s.tick += R(1);                                                     // :986
+    bool done = s.tick > (R)p.ep_len;                                   // :987
+    s.ret += rew;
+    rew_sum += rew;
+    done_any = done_any || done;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.pa[k] = a[k];                         // becomes actions[1] of the next step
+    const bool last = (ks == p.k_steps - 1);
+    if (T::RARE) {
+      if (p.info != nullptr && last && active) {
+        R* inf = p.info + i * INFO_DIM;
+        R am[3];
+        accelerometer(s, p, am);
+        inf[0] = s.ax; inf[1] = s.ay; inf[2] = s.az; inf[3] = am[0]; inf[4] = am[1]; inf[5] = am[2];
+        inf[6] = s.tqx; inf[7] = s.tqy; inf[8] = s.tqz; inf[9] = s.odx; inf[10] = s.ody; inf[11] = s.odz;
+        inf[12] = cmd[0]; inf[13] = cmd[1]; inf[14] = cmd[2]; inf[15] = cmd[3];
+        inf[16] = crashed ? R(1) : R(0); inf[17] = collided ? R(1) : R(0);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) inf[18 + k] = costs[k];
+        inf[28] = s.ret; inf[29] = s.tick; inf[30] = R(0); inf[31] = R(0);
+      }
+    }
+    // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----
+    const bool walk = T::RARE && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
+    const bool resetting = done && p.auto_reset;
+    if ((last && !resetting) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o);
+    if (done) {
+      if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
+      if (resetting) {
+        reset_env<R, T>(s, p, ns);
+        if (last || walk) build_obs<R, T>(s, p, ns, true, s.pa, o);     // :1143 (actions[1] = 0 after reset)
+      }
+    }
+  }
+
+  // ---- write back: state (float4 rows), obs (shared-memory transpose), reward, done ----
+  if (active) {
+    store_state<R, T>(s, p, i);
+    p.rew[i] = rew_sum;
+    p.done[i] = done_any ? 1 : 0;
+    obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
+  }
+  // finished-episode statistics: warp shuffle -> shared -> one double atomic triple per CTA
+  const bool any = __syncthreads_or(done_any ? 1 : 0);                  // also orders the tile writes
+  flush_tile(p, tile, block_first, nullptr);
+  if (any) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      st_ret += __shfl_down_sync(0xffffffffu, st_ret, off);
+      st_ret2 += __shfl_down_sync(0xffffffffu, st_ret2, off);
+      st_n += __shfl_down_sync(0xffffffffu, st_n, off);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = st_ret; red[1][threadIdx.x >> 5] = st_ret2; red[2][threadIdx.x >> 5] = st_n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; ++w) { a0 += red[0][w]; a1 += red[1][w]; a2 += red[2][w]; }
+      if (a2 > 0) { atomicAdd(&p.stats[0], a0); atomicAdd(&p.stats[1], a1); atomicAdd(&p.stats[2], a2); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// masked reset (QuadrotorEnv.reset, quadrotor.py:1149-1150)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant__ Params<R> p) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  R* tile = reinterpret_cast<R*>(smem_raw);
+  __shared__ uint8_t valid[BLOCK];
+  const long long block_first = p.begin + (long long)blockIdx.x * BLOCK;
+  const long long i = block_first + threadIdx.x;
+  const bool active = i < p.end;
+  const bool mine = active && (p.reset_mask == nullptr || p.reset_mask[i] != 0);
+  valid[threadIdx.x] = mine ? 1 : 0;
+  if (mine) {
+    St<R> s;
+    load_state<R, T>(s, p, i, true);
+    NoiseSrc<R, T> ns(p, i);
+    ns.begin_step(p.step_count);
+    reset_env<R, T>(s, p, ns);
+    R o[26];
+    build_obs<R, T>(s, p, ns, true, s.pa, o);
+    store_state<R, T>(s, p, i);
+    obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
+  }
+  __syncthreads();
+  flush_tile(p, tile, block_first, p.reset_mask ? valid : nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// controller.step_func / QuadrotorDynamics.step on the bound state, no env bookkeeping
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_constant__ Params<R> p) {
+  const long long i = p.begin + (long long)blockIdx.x * BLOCK + threadIdx.x;
+  const bool active = i < p.end;
+  St<R> s;
+  load_state<R, T>(s, p, i, active);
+  NoiseSrc<R, T> ns(p, active ? i : 0);
+  ns.begin_step(p.step_count);
+  R a[4] = {R(0), R(0), R(0), R(0)};
+  int adim = p.act_dim;
+  if (active && p.actions != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < adim) a[k] = p.actions[i * adim + k];
+  }
+  R cmd[4];
+  if (p.dyn_controller < 0) { cmd[0] = a[0]; cmd[1] = a[1]; cmd[2] = a[2]; cmd[3] = a[3]; }
+  else controller_cmds<R, T>(s, p, p.dyn_controller, a, cmd);
+  double svd_t = p.svd_timer;
+#pragma unroll 1
+  for (int sub = 0; sub < p.dyn_substeps; ++sub) {
+    svd_t += p.dt_d;
+    bool fire = svd_t > p.svd_period;
+    if (fire) svd_t = 0.0;
+    R z[4] = {R(0), R(0), R(0), R(0)};
+    if (p.ou_on) ns.ou(sub, z);
+    substep<R, T>(s, cmd, p, z, fire);
+  }
+  if (active) {
+    store_state<R, T>(s, p, i);
+    if (p.info != nullptr) {
+      R* inf = p.info + i * INFO_DIM;
+      R am[3];
+      accelerometer(s, p, am);
+      inf[0] = s.ax; inf[1] = s.ay; inf[2] = s.az; inf[3] = am[0]; inf[4] = am[1]; inf[5] = am[2];
+      inf[6] = s.tqx; inf[7] = s.tqy; inf[8] = s.tqz; inf[9] = s.odx; inf[10] = s.ody; inf[11] = s.odz;
+      inf[12] = cmd[0]; inf[13] = cmd[1]; inf[14] = cmd[2]; inf[15] = cmd[3];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch interface implemented once per real type (qs_kernels_f32.cu / qs_kernels_f64.cu)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R> cudaError_t launch_step(const Params<R>& p, cudaStream_t st, const char** variant_name);
+template <typename R> cudaError_t launch_reset(const Params<R>& p, cudaStream_t st);
+template <typename R> cudaError_t launch_dynamics(const Params<R>& p, cudaStream_t st);
+
+}  // namespace qs

@@ -1,0 +1,478 @@
+// quadsim_abi.cu - the C-ABI of libquadsim.so (include/quadsim.h): config validation, QsConfig -> kernel
+// parameter block, variant dispatch, clocks, host-buffer pipeline.  No torch, no Python.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/quadsim.h"
+#include "qs_device.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const int kObsDims[QS_OBS_COUNT] = {18, 19, 18, 19, 25, 22};
+const int kActDims[QS_CTRL_COUNT] = {4, 1, 2, 4, 4, 4, 4};
+const int kHostStreams = 4;
+
+}  // namespace
+
+struct QsHandle {
+  QsConfig cfg;
+  QsStateLayout lay;
+  void* state;
+  void* info;
+  const void* ou_z;
+  const void* obs_z;
+  const void* reset_z;
+  double* d_stats;
+  int* d_status;
+  double svd_timer;
+  uint64_t step_count;
+  uint64_t launches;
+  std::string err;
+  const char* last_variant;
+  // qs_step_host scratch (library-owned)
+  cudaStream_t hs[kHostStreams];
+  cudaEvent_t hev[kHostStreams];
+  bool host_ready;
+  void *h_act, *h_obs, *h_rew;
+  uint8_t* h_done;
+};
+
+namespace {
+
+int fail(QsHandle* h, int code, const char* fmt, const char* a = "") {
+  char buf[512];
+  snprintf(buf, sizeof(buf), fmt, a);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define QS_CUDA(h, call)                                                        \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) return fail((h), QS_ECUDA, #call ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int validate(const QsConfig* c, std::string* why) {
+  if (!c) { *why = "cfg is NULL"; return QS_EINVAL; }
+  if (c->abi_version != QS_ABI_VERSION || c->struct_size != (int32_t)sizeof(QsConfig)) {
+    *why = "QsConfig abi_version/struct_size mismatch"; return QS_EABI;
+  }
+  if (c->n_envs <= 0) { *why = "n_envs must be positive"; return QS_EINVAL; }
+  if (c->dtype != QS_F32 && c->dtype != QS_F64) { *why = "dtype must be QS_F32 or QS_F64"; return QS_EINVAL; }
+  if (c->controller < 0 || c->controller >= QS_CTRL_COUNT) { *why = "unknown controller"; return QS_EINVAL; }
+  if (c->obs_repr < 0 || c->obs_repr >= QS_OBS_COUNT) { *why = "unknown obs_repr"; return QS_EINVAL; }
+  if (c->noise_mode != QS_NOISE_PHILOX && c->noise_mode != QS_NOISE_INJECTED) { *why = "unknown noise_mode"; return QS_EINVAL; }
+  if (c->dim_mode < 1 || c->dim_mode > 3) { *why = "QuadEnv: Unknown dimensionality mode"; return QS_EINVAL; }   // quadrotor.py:131
+  if (c->dim_mode != 3 && c->init_random_state) { *why = "init_random_state is built for dim_mode 3D only"; return QS_EUNSUPPORTED; }
+  if (c->sim_steps < 1 || c->sim_steps > 64) { *why = "sim_steps must be in [1, 64]"; return QS_EINVAL; }
+  if (c->ep_len < 0 || c->ep_len > (1 << 23)) { *why = "ep_len out of range"; return QS_EINVAL; }
+  if (!(c->dt > 0.0)) { *why = "dt must be positive"; return QS_EINVAL; }
+  if (c->n_agents < 1 || c->n_agents > 32 || !is_pow2(c->n_agents)) { *why = "n_agents must be 1, 2, 4, 8, 16 or 32"; return QS_EINVAL; }
+  if (c->n_envs % c->n_agents != 0) { *why = "n_envs must be a multiple of n_agents"; return QS_EINVAL; }
+  if (!(c->model.mass > 0.0) || !(c->model.inertia[0] > 0.0) || !(c->model.inertia[1] > 0.0) || !(c->model.inertia[2] > 0.0)) {
+    *why = "model mass/inertia must be positive"; return QS_EINVAL;
+  }
+  return QS_OK;
+}
+
+bool needs_prev_action(const QsConfig* c) {
+  return c->obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT || c->obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACT ||
+         c->reward.action_change != 0.0;
+}
+
+void layout_of(const QsConfig* c, QsStateLayout* o) {
+  int rows = 7;
+  o->row_ou = (c->model.ou_sigma > 0.0) ? rows++ : -1;
+  o->row_prev_action = needs_prev_action(c) ? rows++ : -1;
+  o->row_gyro_bias = (c->sense.enabled && c->sense.gyro_norm_std != 0.0) ? rows++ : -1;
+  o->row_goal = c->per_env_goal ? rows++ : -1;
+  o->rows = rows;
+  o->obs_dim = kObsDims[c->obs_repr];
+  o->act_dim = kActDims[c->controller];
+  o->_pad = 0;
+}
+
+bool need_rare(const QsHandle* h) {
+  const QsConfig& c = h->cfg;
+  const QsModel& m = c.model;
+  const QsSensorNoise& s = c.sense;
+  if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) return true;
+  if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
+                    s.gyro_norm_std != 0.0)) return true;
+  if (c.reward.log_pos || c.n_agents > 1 || c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
+  return false;
+}
+
+template <typename R>
+void fill_params(const QsHandle* h, qs::Params<R>* pp) {
+  qs::Params<R>& p = *pp;
+  memset(&p, 0, sizeof(p));
+  const QsConfig& c = h->cfg;
+  const QsModel& m = c.model;
+  p.state = (R*)h->state;
+  p.info = (R*)h->info;
+  p.ou_z = (const R*)h->ou_z;
+  p.obs_z = (const R*)h->obs_z;
+  p.reset_z = (const R*)h->reset_z;
+  p.stats = h->d_stats;
+  p.status = h->d_status;
+  p.n = c.n_envs;
+  p.begin = 0; p.end = c.n_envs;
+  p.env_id_offset = c.env_id_offset;
+  p.step_count = h->step_count;
+  p.seed_lo = (unsigned)(c.seed & 0xffffffffu);
+  p.seed_hi = (unsigned)(c.seed >> 32);
+  p.svd_timer = h->svd_timer;
+  p.svd_period = c.svd_period;
+  p.dt_d = c.dt;
+  p.row_ou = h->lay.row_ou; p.row_act = h->lay.row_prev_action; p.row_gyro = h->lay.row_gyro_bias; p.row_goal = h->lay.row_goal;
+  p.obs_dim = h->lay.obs_dim; p.act_dim = h->lay.act_dim;
+  p.k_steps = 1; p.sim_steps = c.sim_steps; p.ep_len = c.ep_len;
+  p.controller = c.controller; p.zero_middle = c.zero_middle; p.n_agents = c.n_agents; p.dim_mode = c.dim_mode;
+  p.obs_rel = (c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA || c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_H);
+  p.obs_h = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_H || c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_H);
+  p.obs_acc = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT);
+  p.obs_act = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT || c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACT);
+  p.init_random = c.init_random_state; p.auto_reset = c.auto_reset;
+  p.sense_on = c.sense.enabled ? 1 : 0;
+  p.ou_on = (m.ou_sigma > 0.0) ? 1 : 0;
+  p.gyro_bias_mode = (c.sense.enabled && c.sense.gyro_norm_std != 0.0) ? 1 : 0;
+  p.dyn_controller = -1; p.dyn_substeps = c.sim_steps;
+  p.inject = (c.noise_mode == QS_NOISE_INJECTED) ? 1 : 0;
+  p.need_rare = need_rare(h) ? 1 : 0;
+  // model (quadrotor.py:142-208, :284-288)
+  p.dt = (R)c.dt;
+  const double eps = 1e-6;
+  double tau_up = 4.0 * c.dt / (m.damp_time_up + eps), tau_down = 4.0 * c.dt / (m.damp_time_down + eps);
+  if (tau_up > 1.0) tau_up = 1.0;
+  if (tau_down > 1.0) tau_down = 1.0;
+  for (int k = 0; k < 4; ++k) {
+    p.thrust_max[k] = (R)m.thrust_max[k];
+    p.tz[k] = (R)(m.torque_max[k] * m.prop_ccw[k]);
+    p.pcx[k] = (R)(m.prop_pos[k][1]);    // prop_pos x z_hat = (y, -x, 0)   (quadrotor.py:182)
+    p.pcy[k] = (R)(-m.prop_pos[k][0]);
+    p.ppx[k] = (R)m.prop_pos[k][0]; p.ppy[k] = (R)m.prop_pos[k][1]; p.ppz[k] = (R)m.prop_pos[k][2];
+    p.ccw[k] = (R)m.prop_ccw[k];
+    for (int j = 0; j < 4; ++j) p.jinv[k][j] = (R)m.Jinv[k][j];
+  }
+  for (int k = 0; k < 3; ++k) {
+    p.inertia[k] = (R)m.inertia[k];
+    p.inv_inertia[k] = (R)(1.0 / m.inertia[k]);
+    p.room_lo[k] = (R)c.room_box[0][k]; p.room_hi[k] = (R)c.room_box[1][k];
+    p.goal[k] = (R)c.goal[k];
+  }
+  p.mass = (R)m.mass; p.inv_mass = (R)(1.0 / m.mass);
+  p.lin = (R)m.linearity; p.c_drag = (R)m.C_drag; p.c_roll = (R)m.C_roll;
+  p.tau_up = (R)tau_up; p.tau_down = (R)tau_down;
+  p.vel_damp = (R)m.vel_damp; p.damp_omega_q = (R)m.damp_omega_quadratic;
+  p.ou_theta = (R)m.ou_theta; p.ou_sigma = (R)m.ou_sigma;
+  p.arm = (R)m.arm; p.omega_max = (R)m.omega_max; p.gravity = (R)m.gravity; p.t2w = (R)m.thrust_to_weight;
+  p.spawn_box = (R)c.spawn_box; p.max_init_vel = (R)c.max_init_vel; p.max_init_omega = (R)c.max_init_omega;
+  p.coll_dist = (R)(c.collision_k * 2.0 * m.arm);
+  const QsReward& r = c.reward;
+  p.c_pos = (R)r.pos; p.c_effort = (R)r.effort; p.c_act_change = (R)r.action_change; p.c_crash = (R)r.crash;
+  p.c_orient = (R)r.orient; p.c_yaw = (R)r.yaw; p.c_rot = (R)r.rot; p.c_attitude = (R)r.attitude; p.c_spin = (R)r.spin;
+  p.c_vel = (R)r.vel; p.c_pos_offset = (R)r.pos_offset; p.c_pos_log_w = (R)r.pos_log_weight; p.c_pos_lin_w = (R)r.pos_linear_weight;
+  p.c_collision = (R)r.collision; p.log_pos = r.log_pos;
+  const QsSensorNoise& s = c.sense;
+  p.sn_pos_std = (R)s.pos_norm_std; p.sn_pos_unif = (R)s.pos_unif_range; p.sn_vel_std = (R)s.vel_norm_std;
+  p.sn_vel_unif = (R)s.vel_unif_range; p.sn_quat_std = (R)s.quat_norm_std; p.sn_quat_unif = (R)s.quat_unif_range;
+  p.sn_gyro_density = (R)s.gyro_noise_density; p.sn_gyro_rw = (R)s.gyro_random_walk;
+  p.sn_acc_static = (R)s.acc_static_noise_std; p.sn_acc_dyn = (R)s.acc_dynamic_noise_ratio;
+  if (p.gyro_bias_mode) {   // sensor_noise.py:165-167, the walk folded over n add_noise calls
+    double T = s.gyro_bias_correlation_time;
+    double sg = s.gyro_noise_density / sqrt(c.dt);
+    double sb = sqrt(-(sg * sg) * (T / 2.0) * (exp(-2.0 * c.dt / T) - 1.0));
+    double pi1 = exp(-c.dt / T);
+    p.gb_pi1 = (R)pi1; p.gb_sig1 = (R)sb;
+    p.gb_pi3 = (R)(pi1 * pi1 * pi1);
+    p.gb_sig3 = (R)(sb * sqrt(1.0 + pi1 * pi1 + pi1 * pi1 * pi1 * pi1));
+  }
+}
+
+// advance the host copy of the global re-orthonormalisation timer exactly as the kernel does (quadrotor.py:381-386)
+void advance_clock(QsHandle* h, long long substeps) {
+  double t = h->svd_timer;
+  for (long long k = 0; k < substeps; ++k) {
+    t += h->cfg.dt;
+    if (t > h->cfg.svd_period) t = 0.0;
+  }
+  h->svd_timer = t;
+}
+
+template <typename R>
+int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8_t* done, cudaStream_t st,
+            long long begin, long long end) {
+  qs::Params<R> p;
+  fill_params<R>(h, &p);
+  p.k_steps = k;
+  p.actions = (const R*)actions; p.obs = (R*)obs; p.rew = (R*)rew; p.done = done;
+  p.begin = begin; p.end = end;
+  cudaError_t e = qs::launch_step<R>(p, st, &h->last_variant);
+  if (e != cudaSuccess) return fail(h, QS_ECUDA, "env_step launch: %s", cudaGetErrorString(e));
+  h->launches++;
+  return QS_OK;
+}
+
+int check_ready(QsHandle* h, bool need_actions, const void* actions) {
+  if (!h) return QS_EINVAL;
+  if (!h->state) return fail(h, QS_ESTATE, "state buffer not bound (qs_bind_state)");
+  if (need_actions && !actions && h->cfg.controller != QS_CTRL_MELLINGER)
+    return fail(h, QS_EINVAL, "actions may be NULL only for QS_CTRL_MELLINGER");
+  return QS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+
+int qs_state_layout(const QsConfig* cfg, QsStateLayout* out) {
+  std::string why;
+  int rc = validate(cfg, &why);
+  if (rc != QS_OK) { g_create_error = why; return rc; }
+  if (!out) return QS_EINVAL;
+  layout_of(cfg, out);
+  return QS_OK;
+}
+
+int qs_create(const QsConfig* cfg, QsHandle** out) {
+  std::string why;
+  int rc = validate(cfg, &why);
+  if (rc != QS_OK) { g_create_error = why; return rc; }
+  if (!out) { g_create_error = "out is NULL"; return QS_EINVAL; }
+  QsHandle* h = new (std::nothrow) QsHandle();
+  if (!h) { g_create_error = "out of host memory"; return QS_EINVAL; }
+  h->cfg = *cfg;
+  layout_of(cfg, &h->lay);
+  h->state = h->info = nullptr;
+  h->ou_z = h->obs_z = h->reset_z = nullptr;
+  h->d_stats = nullptr; h->d_status = nullptr;
+  h->svd_timer = 0.0; h->step_count = 0; h->launches = 0;
+  h->last_variant = "";
+  h->host_ready = false;
+  h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stats, 3 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_status, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, 3 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(h->d_status, 0, sizeof(int));
+  if (e != cudaSuccess) {
+    g_create_error = std::string("qs_create: ") + cudaGetErrorString(e);
+    if (h->d_stats) cudaFree(h->d_stats);
+    if (h->d_status) cudaFree(h->d_status);
+    delete h;
+    return QS_ECUDA;
+  }
+  *out = h;
+  return QS_OK;
+}
+
+int qs_destroy(QsHandle* h) {
+  if (!h) return QS_EINVAL;
+  cudaSetDevice(h->cfg.device);
+  if (h->host_ready) {
+    for (int k = 0; k < kHostStreams; ++k) { cudaStreamDestroy(h->hs[k]); cudaEventDestroy(h->hev[k]); }
+    cudaFree(h->h_act); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
+  }
+  cudaFree(h->d_stats);
+  cudaFree(h->d_status);
+  delete h;
+  return QS_OK;
+}
+
+const char* qs_last_error(const QsHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int qs_bind_state(QsHandle* h, void* state) {
+  if (!h) return QS_EINVAL;
+  if (!state) return fail(h, QS_EINVAL, "state is NULL");
+  if (((uintptr_t)state) % 32 != 0) return fail(h, QS_EINVAL, "state must be 32-byte aligned");
+  h->state = state;
+  return QS_OK;
+}
+
+int qs_bind_info(QsHandle* h, void* info) {
+  if (!h) return QS_EINVAL;
+  h->info = info;
+  return QS_OK;
+}
+
+int qs_set_noise_injection(QsHandle* h, const void* ou_z, const void* obs_z, const void* reset_z) {
+  if (!h) return QS_EINVAL;
+  if (h->cfg.noise_mode != QS_NOISE_INJECTED) return fail(h, QS_EINVAL, "handle was not created with QS_NOISE_INJECTED");
+  h->ou_z = ou_z; h->obs_z = obs_z; h->reset_z = reset_z;
+  return QS_OK;
+}
+
+int qs_reset(QsHandle* h, const uint8_t* mask, void* obs, qs_stream_t stream) {
+  int rc = check_ready(h, false, nullptr);
+  if (rc != QS_OK) return rc;
+  if (!obs) return fail(h, QS_EINVAL, "obs is NULL");
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaError_t e;
+  if (h->cfg.dtype == QS_F32) {
+    qs::Params<float> p; fill_params<float>(h, &p);
+    p.reset_mask = mask; p.obs = (float*)obs; p.begin = 0; p.end = p.n;
+    e = qs::launch_reset<float>(p, (cudaStream_t)stream);
+  } else {
+    qs::Params<double> p; fill_params<double>(h, &p);
+    p.reset_mask = mask; p.obs = (double*)obs; p.begin = 0; p.end = p.n;
+    e = qs::launch_reset<double>(p, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return fail(h, QS_ECUDA, "env_reset launch: %s", cudaGetErrorString(e));
+  h->launches++;
+  h->step_count++;   // a reset consumes one Philox step index so that its draws are never reused by a step
+  return QS_OK;
+}
+
+int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8_t* done, qs_stream_t stream) {
+  int rc = check_ready(h, true, actions);
+  if (rc != QS_OK) return rc;
+  if (k < 1) return fail(h, QS_EINVAL, "k must be >= 1");
+  if (!obs || !rew || !done) return fail(h, QS_EINVAL, "obs/rew/done must not be NULL");
+  if (k > 1 && h->cfg.noise_mode == QS_NOISE_INJECTED) return fail(h, QS_EUNSUPPORTED, "qs_step_k with injected noise needs k == 1");
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs);
+  else rc = do_step<double>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs);
+  if (rc != QS_OK) return rc;
+  advance_clock(h, (long long)k * h->cfg.sim_steps);
+  h->step_count += (uint64_t)k;
+  return QS_OK;
+}
+
+int qs_step(QsHandle* h, const void* actions, void* obs, void* rew, uint8_t* done, qs_stream_t stream) {
+  return qs_step_k(h, 1, actions, obs, rew, done, stream);
+}
+
+int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_substeps, qs_stream_t stream) {
+  int rc = check_ready(h, false, nullptr);
+  if (rc != QS_OK) return rc;
+  if (controller < -1 || controller >= QS_CTRL_COUNT) return fail(h, QS_EINVAL, "unknown controller");
+  if (n_substeps < 0) return fail(h, QS_EINVAL, "n_substeps must be >= 0");
+  if (!actions && controller != QS_CTRL_MELLINGER) return fail(h, QS_EINVAL, "actions is NULL");
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaError_t e;
+  if (h->cfg.dtype == QS_F32) {
+    qs::Params<float> p; fill_params<float>(h, &p);
+    p.actions = (const float*)actions; p.dyn_controller = controller; p.dyn_substeps = n_substeps;
+    p.act_dim = controller < 0 ? 4 : kActDims[controller]; p.begin = 0; p.end = p.n;
+    e = qs::launch_dynamics<float>(p, (cudaStream_t)stream);
+  } else {
+    qs::Params<double> p; fill_params<double>(h, &p);
+    p.actions = (const double*)actions; p.dyn_controller = controller; p.dyn_substeps = n_substeps;
+    p.act_dim = controller < 0 ? 4 : kActDims[controller]; p.begin = 0; p.end = p.n;
+    e = qs::launch_dynamics<double>(p, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return fail(h, QS_ECUDA, "dynamics_step launch: %s", cudaGetErrorString(e));
+  h->launches++;
+  advance_clock(h, n_substeps);
+  h->step_count++;
+  return QS_OK;
+}
+
+int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* rew_host, uint8_t* done_host) {
+  int rc = check_ready(h, true, actions_host);
+  if (rc != QS_OK) return rc;
+  if (!obs_host || !rew_host || !done_host) return fail(h, QS_EINVAL, "obs/rew/done must not be NULL");
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  const long long n = h->cfg.n_envs;
+  const size_t rs = h->cfg.dtype == QS_F32 ? sizeof(float) : sizeof(double);
+  const int od = h->lay.obs_dim, ad = h->lay.act_dim;
+  if (!h->host_ready) {
+    for (int k = 0; k < kHostStreams; ++k) {
+      QS_CUDA(h, cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
+      QS_CUDA(h, cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
+    }
+    QS_CUDA(h, cudaMalloc(&h->h_act, (size_t)n * ad * rs));
+    QS_CUDA(h, cudaMalloc(&h->h_obs, (size_t)n * od * rs));
+    QS_CUDA(h, cudaMalloc(&h->h_rew, (size_t)n * rs));
+    QS_CUDA(h, cudaMalloc((void**)&h->h_done, (size_t)n));
+    h->host_ready = true;
+  }
+  // chunks of whole CTAs (and whole warps, so swarm groups never straddle a chunk), one stream each:
+  // H2D(actions) -> fused step -> D2H(obs, rew, done); copies of one chunk overlap the kernel of another
+  long long per = (n + kHostStreams - 1) / kHostStreams;
+  per = ((per + qs::BLOCK - 1) / qs::BLOCK) * qs::BLOCK;
+  int used = 0;
+  for (int k = 0; k < kHostStreams; ++k) {
+    long long b = (long long)k * per, e = b + per < n ? b + per : n;
+    if (b >= n) break;
+    used = k + 1;
+    cudaStream_t st = h->hs[k];
+    if (actions_host)
+      QS_CUDA(h, cudaMemcpyAsync((char*)h->h_act + (size_t)b * ad * rs, (const char*)actions_host + (size_t)b * ad * rs,
+                                 (size_t)(e - b) * ad * rs, cudaMemcpyHostToDevice, st));
+    const void* act_dev = actions_host ? h->h_act : nullptr;
+    if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e);
+    else rc = do_step<double>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e);
+    if (rc != QS_OK) return rc;
+    QS_CUDA(h, cudaMemcpyAsync((char*)obs_host + (size_t)b * od * rs, (char*)h->h_obs + (size_t)b * od * rs,
+                               (size_t)(e - b) * od * rs, cudaMemcpyDeviceToHost, st));
+    QS_CUDA(h, cudaMemcpyAsync((char*)rew_host + (size_t)b * rs, (char*)h->h_rew + (size_t)b * rs, (size_t)(e - b) * rs,
+                               cudaMemcpyDeviceToHost, st));
+    QS_CUDA(h, cudaMemcpyAsync(done_host + b, h->h_done + b, (size_t)(e - b), cudaMemcpyDeviceToHost, st));
+  }
+  for (int k = 0; k < used; ++k) QS_CUDA(h, cudaStreamSynchronize(h->hs[k]));
+  advance_clock(h, h->cfg.sim_steps);
+  h->step_count += 1;
+  return QS_OK;
+}
+
+int qs_get_stats(QsHandle* h, double out[3], int clear, qs_stream_t stream) {
+  if (!h || !out) return QS_EINVAL;
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  QS_CUDA(h, cudaMemcpyAsync(out, h->d_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (clear) QS_CUDA(h, cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(double), (cudaStream_t)stream));
+  QS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return QS_OK;
+}
+
+int qs_stats_device_ptr(QsHandle* h, double** out) {
+  if (!h || !out) return QS_EINVAL;
+  *out = h->d_stats;
+  return QS_OK;
+}
+
+int qs_check(QsHandle* h, qs_stream_t stream) {
+  if (!h) return QS_EINVAL;
+  int flag = 0;
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  QS_CUDA(h, cudaMemcpyAsync(&flag, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  QS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag) return fail(h, QS_ENONFINITE, "QuadEnv: reward is Nan");   // quadrotor.py:636
+  return QS_OK;
+}
+
+int qs_get_clock(const QsHandle* h, double* svd_timer, uint64_t* step_count) {
+  if (!h) return QS_EINVAL;
+  if (svd_timer) *svd_timer = h->svd_timer;
+  if (step_count) *step_count = h->step_count;
+  return QS_OK;
+}
+
+int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count) {
+  if (!h) return QS_EINVAL;
+  h->svd_timer = svd_timer;
+  h->step_count = step_count;
+  return QS_OK;
+}
+
+int qs_launch_count(const QsHandle* h, uint64_t* out) {
+  if (!h || !out) return QS_EINVAL;
+  *out = h->launches;
+  return QS_OK;
+}
+
+const char* qs_last_variant(const QsHandle* h) { return h ? h->last_variant : ""; }
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+"""QuadVecEnv: N quadrotor envs stepped by one fused sm_100a kernel per env step.
+
+The batched counterpart of the reference's QuadrotorEnv (gym_art/quadrotor/quadrotor.py:647-1156): same ctor
+vocabulary, same per-env semantics (see DESIGN.md "behaviour checklist"), torch tensors in and out, state owned
+by torch in the structure-of-arrays layout of include/quadsim.h.  All arithmetic happens in libquadsim.so; this
+file only builds the QsConfig, owns the tensors and forwards pointers.  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .quadrotor import quadrotor_randomization as quad_rand
+from .quadrotor.model import GRAV, ModelConstants
+from .quadrotor.sensor_noise import SensorNoise
+
+CONTROLLERS = {"raw": _lib.QS_CTRL_RAW, "vertical": _lib.QS_CTRL_VERTICAL, "vertplane": _lib.QS_CTRL_VERTPLANE,
+               "shifted": _lib.QS_CTRL_SHIFTED, "omega_thrust": _lib.QS_CTRL_OMEGA_THRUST,
+               "velocity_yaw": _lib.QS_CTRL_VELOCITY_YAW, "mellinger": _lib.QS_CTRL_MELLINGER}
+
+REW_COEFF_DEFAULT = {"pos": 1., "effort": 0.05, "action_change": 0., "crash": 1., "orient": 1., "yaw": 0., "rot": 0.,
+                     "attitude": 0., "spin": 0.1, "vel": 0.}                          # quadrotor.py:799-806
+REW_COEFF_MULTI_DEFAULT = {"pos": 1., "pos_offset": 0.1, "pos_log_weight": 1., "pos_linear_weight": 0.1,
+                           "effort": 0.01, "action_change": 0., "crash": 1., "orient": 1., "yaw": 0., "rot": 0.,
+                           "attitude": 0., "spin": 0., "vel": 0.}                     # quadrotor_multi.py:810-818
+
+
+def resolve_dynamics_params(dynamics_params, dynamics_change=None):
+    """quadrotor.py:738-744 + :1030-1056: sampler name (or dict) -> checked parameter dict."""
+    if isinstance(dynamics_params, str):
+        params = getattr(quad_rand, dynamics_params)().sample()
+    else:
+        import copy
+        params = copy.deepcopy(dynamics_params)
+    if dynamics_change is not None:
+        quad_rand._update_existing(params, dynamics_change)
+    return quad_rand.check_quad_param_limits(params)
+
+
+def resolve_sense_noise(sense_noise):
+    """quadrotor.py:838-849."""
+    if isinstance(sense_noise, SensorNoise):
+        return sense_noise
+    if isinstance(sense_noise, dict):
+        return SensorNoise(**sense_noise)
+    if isinstance(sense_noise, str):
+        if sense_noise == "default":
+            return SensorNoise(bypass=False)
+        raise ValueError("ERROR: QuadEnv: sense_noise parameter is of unknown type: " + str(sense_noise))
+    if sense_noise is None:
+        return SensorNoise(bypass=True)
+    raise ValueError("ERROR: QuadEnv: sense_noise parameter is of unknown type: " + str(sense_noise))
+
+
+def resolve_rew_coeff(rew_coeff, multi_reward):
+    """quadrotor.py:799-818."""
+    base = dict(REW_COEFF_MULTI_DEFAULT if multi_reward else REW_COEFF_DEFAULT)
+    if rew_coeff is not None:
+        assert isinstance(rew_coeff, dict)
+        assert set(rew_coeff.keys()).issubset(set(base.keys()) | {"collision"}), "unknown reward coefficient"
+        base.update(rew_coeff)
+    return {k: float(v) for k, v in base.items()}
+
+
+def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True, dim_mode="3D", sim_freq=200.,
+                sim_steps=2, obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10, init_random_state=False,
+                rew_coeff=None, sense_noise=None, device_index=0, dtype="float32", seed=0, noise_mode="philox",
+                auto_reset=True, n_agents=1, per_env_goal=False, env_id_offset=0, multi_reward=False, collision_k=1.0,
+                goal=(0., 0., 2.), box=2.0):
+    """Pure host function (no GPU): ctor arguments -> QsConfig.  Raises the reference's ValueErrors."""
+    cfg = _lib.QsConfig()
+    cfg.abi_version = _lib.QS_ABI_VERSION
+    cfg.struct_size = C.sizeof(_lib.QsConfig)
+    cfg.n_envs = int(num_envs)
+    cfg.env_id_offset = int(env_id_offset)
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.n_agents = int(n_agents)
+    cfg.device = int(device_index)
+    cfg.dtype = {"float32": _lib.QS_F32, "float64": _lib.QS_F64}[dtype]
+    if controller not in CONTROLLERS:
+        raise ValueError("QuadEnv: unknown controller %s" % controller)
+    cfg.controller = CONTROLLERS[controller]
+    cfg.zero_middle = int(bool(raw_control_zero_middle))
+    if obs_repr not in _lib.OBS_REPRS:
+        raise ValueError("QuadEnv: obs_repr %s is not one of the working representations %s" % (obs_repr, _lib.OBS_REPRS))
+    cfg.obs_repr = _lib.OBS_REPRS.index(obs_repr)
+    cfg.noise_mode = {"philox": _lib.QS_NOISE_PHILOX, "injected": _lib.QS_NOISE_INJECTED}[noise_mode]
+    cfg.init_random_state = int(bool(init_random_state))
+    cfg.auto_reset = int(bool(auto_reset))
+    if dim_mode not in ("1D", "2D", "3D"):
+        raise ValueError('QuadEnv: Unknown dimensionality mode %s' % dim_mode)       # quadrotor.py:131
+    cfg.dim_mode = int(dim_mode[0])
+    cfg.sim_steps = int(sim_steps)
+    dt = 1.0 / sim_freq                                                               # quadrotor.py:790
+    cfg.ep_len = int(ep_time / (dt * sim_steps))                                      # quadrotor.py:792
+    cfg.per_env_goal = int(bool(per_env_goal))
+    cfg.dt = dt
+    cfg.svd_period = 0.5                                                              # quadrotor.py:105
+    for k in range(3):
+        cfg.goal[k] = float(goal[k])
+    cfg.spawn_box = float(box)                                                        # quadrotor.py:728
+    lo = [-room_size, -room_size, 0.]
+    hi = [room_size, room_size, room_size]                                            # quadrotor.py:723
+    for k in range(3):
+        cfg.room_box[0][k] = float(lo[k])
+        cfg.room_box[1][k] = float(hi[k])
+    cfg.max_init_vel = 1.                                                             # quadrotor.py:717
+    cfg.max_init_omega = 2 * np.pi                                                    # quadrotor.py:718
+    cfg.collision_k = float(collision_k)
+    cfg.model = model.to_qs()
+    rc = resolve_rew_coeff(rew_coeff, multi_reward)
+    for k in ("pos", "effort", "action_change", "crash", "orient", "yaw", "rot", "attitude", "spin", "vel"):
+        setattr(cfg.reward, k, rc[k])
+    cfg.reward.log_pos = int(bool(multi_reward))
+    if multi_reward:
+        cfg.reward.pos_offset, cfg.reward.pos_log_weight = rc["pos_offset"], rc["pos_log_weight"]
+        cfg.reward.pos_linear_weight = rc["pos_linear_weight"]
+    cfg.reward.collision = rc.get("collision", 0.0)
+    sn = resolve_sense_noise(sense_noise)
+    cfg.sense.enabled = int(not sn.bypass)
+    for k in ("pos_norm_std", "pos_unif_range", "vel_norm_std", "vel_unif_range", "quat_norm_std", "quat_unif_range",
+              "gyro_norm_std", "gyro_noise_density", "gyro_random_walk", "gyro_bias_correlation_time",
+              "acc_static_noise_std", "acc_dynamic_noise_ratio"):
+        setattr(cfg.sense, k, float(getattr(sn, k)))
+    return cfg, rc, sn
+
+
+class QuadVecEnv(object):
+    """N independent quadrotor envs (or N / n_agents swarms) on one GPU.
+
+    step(actions) -> (obs [N,O], reward [N], done [N] bool) as torch tensors on the device.  The returned
+    tensors are reused by the next call.  With auto_reset (default) an env that finishes an episode is re-spawned
+    inside the same kernel: the step returns the terminal reward/done and the first observation of the next
+    episode (standard vec-env semantics; the reference leaves reset() to the caller, quadrotor.py:1260-1305).
+    """
+
+    def __init__(self, num_envs, dynamics_params="DefaultQuad", dynamics_change=None, controller=None,
+                 raw_control=True, raw_control_zero_middle=True, dim_mode="3D", sim_freq=200., sim_steps=2,
+                 obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10, init_random_state=False, rew_coeff=None,
+                 sense_noise=None, gravity=GRAV, device="cuda:0", dtype="float32", seed=0, noise_mode="philox",
+                 auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
+                 info=False):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("QuadVecEnv runs on a CUDA device only (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("QuadVecEnv runs on a CUDA device only")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.tdtype = {"float32": torch.float32, "float64": torch.float64}[dtype]
+        if controller is None:                                                    # quadrotor.py:876-886
+            if raw_control:
+                controller = {"1D": "vertical", "2D": "vertplane", "3D": "raw"}.get(dim_mode, "raw")
+            else:
+                controller = "mellinger"
+        self.controller_name = controller
+        self.dynamics_params = resolve_dynamics_params(dynamics_params, dynamics_change)
+        self.model = ModelConstants(self.dynamics_params, gravity=gravity)
+        self.cfg, self.rew_coeff, self.sense_noise = make_config(
+            num_envs, self.model, controller=controller, raw_control_zero_middle=raw_control_zero_middle,
+            dim_mode=dim_mode, sim_freq=sim_freq, sim_steps=sim_steps, obs_repr=obs_repr, ep_time=ep_time,
+            room_size=room_size, init_random_state=init_random_state, rew_coeff=rew_coeff, sense_noise=sense_noise,
+            device_index=dev_index, dtype=dtype, seed=seed, noise_mode=noise_mode, auto_reset=auto_reset,
+            n_agents=n_agents, per_env_goal=goals is not None, env_id_offset=env_id_offset, multi_reward=multi_reward,
+            collision_k=collision_k)
+        self.layout = _lib.state_layout(self.cfg)
+        self.num_envs = int(num_envs)
+        self.n_agents = int(n_agents)
+        self.obs_dim, self.act_dim = self.layout.obs_dim, self.layout.act_dim
+        self.dt, self.sim_steps, self.ep_len = self.cfg.dt, int(sim_steps), self.cfg.ep_len
+        self.obs_repr = obs_repr
+        self.goal = np.array([self.cfg.goal[0], self.cfg.goal[1], self.cfg.goal[2]])
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros((self.layout.rows, N, 4), dtype=self.tdtype, device=self.device)
+            self.obs = torch.zeros((N, self.obs_dim), dtype=self.tdtype, device=self.device)
+            self.rew = torch.zeros((N,), dtype=self.tdtype, device=self.device)
+            self._done_u8 = torch.zeros((N,), dtype=torch.uint8, device=self.device)
+            self.info = torch.zeros((N, _lib.QS_INFO_DIM), dtype=self.tdtype, device=self.device) if info else None
+        self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.device).reshape(1, 9))
+        if goals is not None:
+            self.set_field("goals", np.asarray(goals, dtype=np.float64).reshape(N, 3))
+        self._h = C.c_void_p()
+        _lib.check(self.lib.qs_create(C.byref(self.cfg), C.byref(self._h)))
+        _lib.check(self.lib.qs_bind_state(self._h, self.state.data_ptr()), self._h)
+        if info:
+            _lib.check(self.lib.qs_bind_info(self._h, self.info.data_ptr()), self._h)
+        self._noise_refs = None
+
+    # ------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.qs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- logical fields of the structure-of-arrays state (include/quadsim.h "State buffer") ---------
+    # The per-env state is the word sequence [pos3 vel3 omega3 R9 tick ret rot_damp4 cmds_damp4 | optional rows],
+    # cut into 4-word vectors; word w of env i lives at state[w // 4, i, w % 4].
+    def _fields(self):
+        L = self.layout
+        return {"pos": (0, 3), "vel": (3, 3), "omega": (6, 3), "rot": (9, 9), "tick": (18, 1), "ep_return": (19, 1),
+                "thrust_rot_damp": (20, 4), "thrust_cmds_damp": (24, 4), "ou_state": (L.row_ou * 4, 4),
+                "prev_action": (L.row_prev_action * 4, 4), "gyro_bias": (L.row_gyro_bias * 4, 3),
+                "goals": (L.row_goal * 4, 3)}
+
+    def get_field(self, name):
+        """Snapshot (copy) of one logical field: [N, count] (rot: [N,3,3]; tick/ep_return: [N])."""
+        first, count = self._fields()[name]
+        if first < 0:
+            raise AttributeError("state has no %s row in this configuration" % name)
+        idx = self.torch.arange(first, first + count, device=self.device)
+        v = self.state[idx // 4, :, idx % 4].transpose(0, 1).contiguous()
+        if name == "rot":
+            return v.reshape(self.num_envs, 3, 3)
+        if count == 1:
+            return v.reshape(self.num_envs)
+        return v
+
+    pos = property(lambda self: self.get_field("pos"))
+    vel = property(lambda self: self.get_field("vel"))
+    omega = property(lambda self: self.get_field("omega"))
+    rot = property(lambda self: self.get_field("rot"))
+    tick = property(lambda self: self.get_field("tick"))
+    ep_return = property(lambda self: self.get_field("ep_return"))
+    thrust_rot_damp = property(lambda self: self.get_field("thrust_rot_damp"))
+    thrust_cmds_damp = property(lambda self: self.get_field("thrust_cmds_damp"))
+    ou_state = property(lambda self: self.get_field("ou_state"))
+    prev_action = property(lambda self: self.get_field("prev_action"))
+    gyro_bias = property(lambda self: self.get_field("gyro_bias"))
+    goals = property(lambda self: self.get_field("goals"))
+
+    def set_field(self, name, value, mask=None):
+        """Write one logical field for all envs (value broadcast over N) or for the envs selected by mask."""
+        t = self.torch
+        first, count = self._fields()[name]
+        if first < 0:
+            raise AttributeError("state has no %s row in this configuration" % name)
+        v = t.as_tensor(value, dtype=self.tdtype, device=self.device).reshape(-1, count).expand(self.num_envs, count)
+        idx = t.arange(first, first + count, device=self.device)
+        if mask is not None:
+            m = t.as_tensor(mask, device=self.device).bool()
+            v = t.where(m[:, None], v, self.state[idx // 4, :, idx % 4].transpose(0, 1))
+        self.state[idx // 4, :, idx % 4] = v.transpose(0, 1)
+
+    def set_state(self, pos, vel, rot, omega, mask=None):
+        """QuadrotorDynamics.set_state + reset() (quadrotor.py:213-224, :438-440) for all (or masked) envs."""
+        t = self.torch
+        om = t.as_tensor(omega, dtype=self.tdtype, device=self.device).float().to(self.tdtype)   # float32 cast, :223
+        self.set_field("pos", pos, mask)
+        self.set_field("vel", vel, mask)
+        self.set_field("rot", t.as_tensor(rot, dtype=self.tdtype, device=self.device).reshape(-1, 9), mask)
+        self.set_field("omega", om, mask)
+        self.set_field("thrust_rot_damp", [0., 0., 0., 0.], mask)
+        self.set_field("thrust_cmds_damp", [0., 0., 0., 0.], mask)
+
+    # ---- noise injection (test mode) -----------------------------------------------------------------
+    def set_noise(self, ou_z=None, obs_z=None, reset_z=None):
+        """QS_NOISE_INJECTED: unit draws for the next reset()/step() calls; shapes [N,sim_steps,4], [N,30], [N,48]."""
+        t = self.torch
+
+        def dev(x, shape):
+            if x is None:
+                return None
+            v = t.as_tensor(np.asarray(x), dtype=self.tdtype, device=self.device).reshape(shape).contiguous()
+            return v
+
+        N = self.num_envs
+        refs = (dev(ou_z, (N, self.sim_steps, 4)), dev(obs_z, (N, _lib.QS_OBS_Z)), dev(reset_z, (N, _lib.QS_RESET_Z)))
+        self._noise_refs = refs      # keep the device buffers alive until replaced
+        ptr = lambda v: None if v is None else v.data_ptr()
+        _lib.check(self.lib.qs_set_noise_injection(self._h, ptr(refs[0]), ptr(refs[1]), ptr(refs[2])), self._h)
+
+    # ---- the env API -----------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        m = None
+        if mask is not None:
+            m = self.torch.as_tensor(mask, device=self.device).to(self.torch.uint8).contiguous()
+        _lib.check(self.lib.qs_reset(self._h, None if m is None else m.data_ptr(), self.obs.data_ptr(), self._stream()),
+                   self._h)
+        return self.obs
+
+    def _actions(self, actions, k=None):
+        if actions is None:
+            return None
+        a = self.torch.as_tensor(actions, dtype=self.tdtype, device=self.device)
+        want = (self.num_envs, self.act_dim) if k is None else (k, self.num_envs, self.act_dim)
+        if tuple(a.shape) != want:
+            a = a.reshape(want)
+        return a.contiguous()
+
+    def step(self, actions=None):
+        a = self._actions(actions)
+        _lib.check(self.lib.qs_step(self._h, None if a is None else a.data_ptr(), self.obs.data_ptr(), self.rew.data_ptr(),
+                                    self._done_u8.data_ptr(), self._stream()), self._h)
+        return self.obs, self.rew, self._done_u8.bool()
+
+    def step_k(self, k, actions=None):
+        """k fused env steps in one launch; returns (last obs, summed reward, any-done)."""
+        a = self._actions(actions, k)
+        _lib.check(self.lib.qs_step_k(self._h, int(k), None if a is None else a.data_ptr(), self.obs.data_ptr(),
+                                      self.rew.data_ptr(), self._done_u8.data_ptr(), self._stream()), self._h)
+        return self.obs, self.rew, self._done_u8.bool()
+
+    def step_host(self, actions_host, obs_host, rew_host, done_host):
+        """End-to-end step on HOST tensors (pinned for full PCIe speed): H2D, fused step, D2H, synchronous."""
+        for x in (obs_host, rew_host, done_host):
+            assert x.device.type == "cpu" and x.is_contiguous()
+        ap = None
+        if actions_host is not None:
+            assert actions_host.device.type == "cpu" and actions_host.is_contiguous() and actions_host.dtype == self.tdtype
+            ap = actions_host.data_ptr()
+        assert obs_host.dtype == self.tdtype and rew_host.dtype == self.tdtype and done_host.dtype == self.torch.uint8
+        _lib.check(self.lib.qs_step_host(self._h, ap, obs_host.data_ptr(), rew_host.data_ptr(), done_host.data_ptr()),
+                   self._h)
+        return obs_host, rew_host, done_host
+
+    def dynamics_step(self, actions, controller=None, n_substeps=None):
+        """controller.step_func / QuadrotorDynamics.step on the bound state; controller=None: raw motor commands."""
+        cid = -1 if controller is None else CONTROLLERS[controller]
+        adim = 4 if cid < 0 else [4, 1, 2, 4, 4, 4, 4][cid]
+        a = None
+        if actions is not None:
+            a = self.torch.as_tensor(actions, dtype=self.tdtype, device=self.device).reshape(self.num_envs, adim).contiguous()
+        n = self.sim_steps if n_substeps is None else int(n_substeps)
+        _lib.check(self.lib.qs_dynamics_step(self._h, cid, None if a is None else a.data_ptr(), n, self._stream()), self._h)
+
+    # ---- bookkeeping -----------------------------------------------------------------------------------
+    def stats(self, clear=False):
+        out = (C.c_double * 3)()
+        _lib.check(self.lib.qs_get_stats(self._h, C.byref(out), int(clear), self._stream()), self._h)
+        return np.array([out[0], out[1], out[2]])
+
+    def stats_tensor(self):
+        """The device-resident double[3] {sum ret, sum ret^2, episodes} as a torch tensor (for NCCL all-reduce)."""
+        p = C.c_void_p()
+        _lib.check(self.lib.qs_stats_device_ptr(self._h, C.byref(p)), self._h)
+        from .stats import wrap_device_doubles
+        return wrap_device_doubles(p.value, 3, self.device)
+
+    def check_finite(self):
+        _lib.check(self.lib.qs_check(self._h, self._stream()), self._h)
+
+    @property
+    def clock(self):
+        t, s = C.c_double(), C.c_uint64()
+        _lib.check(self.lib.qs_get_clock(self._h, C.byref(t), C.byref(s)), self._h)
+        return t.value, s.value
+
+    @clock.setter
+    def clock(self, value):
+        _lib.check(self.lib.qs_set_clock(self._h, float(value[0]), int(value[1])), self._h)
+
+    @property
+    def launch_count(self):
+        n = C.c_uint64()
+        _lib.check(self.lib.qs_launch_count(self._h, C.byref(n)), self._h)
+        return n.value
+
+    @property
+    def kernel_variant(self):
+        return self.lib.qs_last_variant(self._h).decode()
+
+    def state_dict(self):
+        """Checkpoint: the state tensor plus the global clocks (SURVEY.md section 5 "Checkpoint / resume")."""
+        t, s = self.clock
+        return {"state": self.state.clone(), "svd_timer": t, "step_count": s}
+
+    def load_state_dict(self, d):
+        self.state.copy_(d["state"])
+        self.clock = (d["svd_timer"], d["step_count"])
