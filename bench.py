@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/s of the fused quadrotor env-step path on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (controller -> sim_steps x step1 -> reward/done -> auto-reset -> obs) over one
+batch of envs.  Workload (BASELINE.json configs[1], "cfg2"): Hummingbird, RawControl zero-middle, no sensor noise,
+OU thrust noise on (model default), obs xyz_vxyz_R_omega, 65,536 envs per batch, auto-reset, fp32, Philox noise.
+A ring of independent 65,536-env batches whose combined footprint exceeds the 126 MB L2 is cycled so that every
+step finds its inputs in HBM, not in L2.  The same run also times the HBM-resident size (4,194,304 envs per
+step, "hbm_resident" in the JSON) on which BASELINE.md quotes the roofline fraction.
+
+One JSON line is printed by rank 0 (contract in the task statement): value = whole-job env-steps/s on device-resident
+inputs; e2e = the same metric through qs_step_host with pinned HOST buffers (H2D + D2H inside the timed region);
+roofline = algorithmic bytes / measured launch duration vs MEASURED_PEAKS.json; cpu_baseline = the NumPy oracle port
+of the reference timed on this box's host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_BATCH = 65536              # cfg2
+N_LARGE = 4 * 1024 * 1024    # HBM-resident size the roofline fraction is quoted on
+SIM_STEPS = 2
+EP_TIME = 5                  # ep_len 500 -> 501-step episodes
+BYTES_PER_ENV_STEP = 2 * 4 * 32 + 4 * 4 + 4 * 18 + 4 + 1   # 349 B: S=32 state words r+w, 4 action words, 18 obs, reward, done
+METRIC = "env-steps/sec at 1/2/4/8 B200 (% HBM roofline) vs host-core numpy ref"
+WORKLOAD = ("cfg2: Hummingbird (DefaultQuad) RawControl zero-middle, no sensor noise, OU thrust noise on, "
+            "obs xyz_vxyz_R_omega, sim_steps=2, ep_len=500, auto-reset, %d envs per step" % N_BATCH)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the busiest half of the samples (the sampler also sees the idle gaps around the timed region)
+        busy = sm[len(sm) // 2:] if sm else []
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline: the NumPy oracle port of the reference, one env per process (the reference's own object model)
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seconds, seed, n_envs = args
+    import numpy as np
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import quadsim_oracle as qo
+    params = _hummingbird_params()
+    env = qo.OracleVecEnv(params, n_envs, controller=qo.CTRL_RAW, ep_time=EP_TIME, sim_steps=SIM_STEPS, auto_reset=True)
+    rng = np.random.RandomState(seed)
+    env.reset(reset_z=rng.uniform(-1, 1, (n_envs, qo.RESET_Z)))
+    for _ in range(20):
+        env.step(rng.uniform(-1, 1, (n_envs, 4)), ou_z=rng.standard_normal((n_envs, SIM_STEPS, 4)))
+    steps = 0
+    t0 = time.perf_counter()
+    while True:
+        for _ in range(50):
+            env.step(rng.uniform(-1, 1, (n_envs, 4)), ou_z=rng.standard_normal((n_envs, SIM_STEPS, 4)),
+                     reset_z=rng.uniform(-1, 1, (n_envs, qo.RESET_Z)))
+        steps += 50
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            return steps * n_envs / dt
+
+
+def _hummingbird_params():
+    # parameter *data* for the oracle (the oracle derives its own constants from it)
+    from gym_art_b200.quadrotor import quad_models
+    return quad_models.defaultquad_params()
+
+
+def cpu_baseline(seconds=6.0, cores=None):
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    single = _cpu_worker((min(seconds, 4.0), 0, 1))
+    with ctx.Pool(cores) as pool:
+        rates = pool.map(_cpu_worker, [(seconds, 100 + k, 1) for k in range(cores)])
+        batched = pool.map(_cpu_worker, [(seconds / 2, 200 + k, 4096) for k in range(cores)])
+    return {
+        "value": float(sum(rates)), "unit": "env-steps/s", "cores": cores, "kind": "port",
+        "sample": "NumPy oracle port (oracle/quadsim_oracle.py, bit-verified against the live reference), cfg2 semantics, "
+                  "one env per process as in the reference, %d processes x %.0f s, sum of per-process rates" % (cores, seconds),
+        "single_env_1core": float(single),
+        "batched_numpy_all_cores": float(sum(batched)),
+        "batched_note": "same port vectorised over 4096 envs per process (not how the reference runs; upper bound for NumPy)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def make_env(n, device, seed, env_id_offset=0):
+    from gym_art_b200 import QuadVecEnv
+    return QuadVecEnv(n, dynamics_params="DefaultQuad", controller="raw", raw_control_zero_middle=True, sense_noise=None,
+                      obs_repr="xyz_vxyz_R_omega", ep_time=EP_TIME, sim_steps=SIM_STEPS, device=device, dtype="float32",
+                      seed=seed, noise_mode="philox", auto_reset=True, env_id_offset=env_id_offset)
+
+
+def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, per_chunk_hook=None, chunk=501):
+    """Captures `fn_steps(i)` for i in a chunk into CUDA graphs and times exactly n_steps steps with CUDA events on
+    the launching stream.  Returns elapsed milliseconds (this rank)."""
+    stream = torch.cuda.Stream(device=device)
+    graphs = {}
+
+    def graph_for(first, count):
+        key = (first % RING_PERIOD[0], count)
+        if key not in graphs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(first, first + count):
+                    fn_steps(i)
+            graphs[key] = g
+        return graphs[key]
+
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            fn_steps(i)
+    stream.synchronize()
+    plan, done = [], 0
+    while done < n_steps:
+        c = min(chunk, n_steps - done)
+        plan.append(graph_for(warmup + done, c))
+        done += c
+    for g in set(plan):         # one untimed replay of every graph (instantiation / upload costs stay outside)
+        with torch.cuda.stream(stream):
+            g.replay()
+    stream.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for g in plan:
+            g.replay()
+            if per_chunk_hook is not None:
+                per_chunk_hook(stream)
+        e1.record(stream)
+    stream.synchronize()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1)
+
+
+RING_PERIOD = [1]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if multi:
+        dist.init_process_group("nccl", device_id=device)
+    hbm_peak, peak_src = load_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- primary workload: ring of 65,536-env batches (> L2) ---------------------------------------------------
+    ring = args.ring
+    RING_PERIOD[0] = ring
+    envs, acts = [], []
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1 + rank)
+    for b in range(ring):
+        e = make_env(N_BATCH, device, seed=1, env_id_offset=(rank * ring + b) * N_BATCH)
+        e.reset()
+        envs.append(e)
+        acts.append(torch.rand((N_BATCH, 4), device=device, generator=gen) * 2 - 1)
+    ring_bytes = ring * (envs[0].state.numel() * 4 + N_BATCH * (16 + 72 + 4 + 1))
+    launches0 = sum(e.launch_count for e in envs)
+
+    def step_ring(i):
+        b = i % ring
+        envs[b].step(acts[b])
+
+    stats_t = envs[0].stats_tensor()
+
+    def episode_allreduce(stream):
+        # the path's only collective: per-episode all-reduce of {sum ret, sum ret^2, episodes} (24 bytes, NCCL)
+        if multi:
+            t = stats_t.clone()
+            dist.all_reduce(t)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms = time_graph(torch, step_ring, K, W, device, dist if multi else None, episode_allreduce if multi else None)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * N_BATCH * K / (ms_max * 1e-3)
+    step_us = ms_max * 1e3 / K
+    achieved = N_BATCH * BYTES_PER_ENV_STEP / (step_us * 1e-6) / 1e9
+
+    # ---- HBM-resident size ----------------------------------------------------------------------------------------
+    for e in envs[1:]:
+        e.close()
+    big = make_env(N_LARGE, device, seed=2, env_id_offset=rank * N_LARGE)
+    big.reset()
+    big_act = torch.rand((N_LARGE, 4), device=device, generator=gen) * 2 - 1
+    KL = max(20, min(200, K // 10))
+    RING_PERIOD[0] = 1
+    ms_l = time_graph(torch, lambda i: big.step(big_act), KL, 5, device, dist if multi else None, None)
+    tl = torch.tensor([ms_l], device=device, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    ms_l = float(tl.item())
+    big_value = world * N_LARGE * KL / (ms_l * 1e-3)
+    big_achieved = N_LARGE * BYTES_PER_ENV_STEP / (ms_l * 1e-3 / KL) / 1e9
+    variant = big.kernel_variant
+    big.check_finite()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers through qs_step_host -------------------------------------------------------------------
+    e0 = envs[0]
+    a_h = torch.empty((N_BATCH, 4), dtype=torch.float32).pin_memory()
+    a_h.copy_(acts[0].cpu())
+    o_h = torch.empty((N_BATCH, 18), dtype=torch.float32).pin_memory()
+    r_h = torch.empty((N_BATCH,), dtype=torch.float32).pin_memory()
+    d_h = torch.empty((N_BATCH,), dtype=torch.uint8).pin_memory()
+    for _ in range(5):
+        e0.step_host(a_h, o_h, r_h, d_h)
+    KE = min(K, 2000)
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(KE):
+        e0.step_host(a_h, o_h, r_h, d_h)
+    torch.cuda.synchronize(device)
+    te = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_BATCH * KE / float(te.item())
+    assert bool(torch.isfinite(o_h).all())
+    launches = sum(e.launch_count for e in envs[:1]) + 0
+
+    if rank == 0:
+        cpu = cpu_baseline(seconds=args.cpu_seconds) if (world == 1 and not args.no_cpu) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_envs_per_gpu_step": N_BATCH, "sim_steps": SIM_STEPS, "substeps_per_s": value * SIM_STEPS,
+                       "l2": "ring of %d independent batches, %.0f MB footprint > 126 MB L2, cycled" % (ring, ring_bytes / 1e6),
+                       "launch": "CUDA graph of qs_step launches (device-resident clock), one kernel per step",
+                       "kernel_variant": variant, "parallelism": "env-index sharding x%d, no data-path collective" % world},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N_BATCH * 16,
+                    "d2h_bytes_per_step": N_BATCH * (72 + 4 + 1), "steps": KE,
+                    "api": "qs_step_host (pinned host buffers, 4-chunk H2D/kernel/D2H pipeline)"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "note": "65,536-env launches are launch/latency-bound (23 MB per launch); see hbm_resident"},
+            "hbm_resident": {"n_envs_per_gpu_step": N_LARGE, "steps": KL, "value": big_value, "unit": "env-steps/s",
+                             "ms_per_step": ms_l / KL,
+                             "roofline": {"bound": "hbm", "achieved": big_achieved, "peak": hbm_peak, "unit": "GB/s",
+                                          "frac": big_achieved / hbm_peak}},
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    cores = os.cpu_count() or 1
+    # each "step" of the reference arm is a bounded sample: every host core steps its own single env (the
+    # reference's object model) for a slice of wall-clock; K and W only scale the sample, capped to ~30 s
+    seconds = max(4.0, min(30.0, 0.01 * (K + W)))
+    cpu = cpu_baseline(seconds=seconds, cores=cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "env-steps/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path: oracle port, one env per process, all host cores"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100200)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ring", type=int, default=16)
+    ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libquadsim.so")
 
-QS_ABI_VERSION = 3
+QS_ABI_VERSION = 4
 QS_OK, QS_EINVAL, QS_ECUDA, QS_ENONFINITE, QS_ESTATE, QS_EUNSUPPORTED, QS_EABI = 0, -1, -2, -3, -4, -5, -6
 QS_F32, QS_F64 = 0, 1
 (QS_CTRL_RAW, QS_CTRL_VERTICAL, QS_CTRL_VERTPLANE, QS_CTRL_SHIFTED, QS_CTRL_OMEGA_THRUST, QS_CTRL_VELOCITY_YAW,
@@ -109,8 +109,8 @@ def load():
         "qs_get_stats": (C.c_int, [H, C.POINTER(C.c_double * 3), C.c_int, P]),
         "qs_stats_device_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
         "qs_check": (C.c_int, [H, P]),
-        "qs_get_clock": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
-        "qs_set_clock": (C.c_int, [H, C.c_double, C.c_uint64]),
+        "qs_get_clock": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(C.c_uint64), P]),
+        "qs_set_clock": (C.c_int, [H, C.c_double, C.c_uint64, P]),
         "qs_launch_count": (C.c_int, [H, C.POINTER(C.c_uint64)]),
         "qs_last_variant": (C.c_char_p, [H]),
     }

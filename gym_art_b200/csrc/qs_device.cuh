@@ -21,6 +21,14 @@ constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 32;
 
 enum Ctrl { CTRL_RAW = 0, CTRL_VERTICAL, CTRL_VERTPLANE, CTRL_SHIFTED, CTRL_OMEGA_THRUST, CTRL_VELOCITY_YAW, CTRL_MELLINGER };
 
+// Global bookkeeping that lives on the device so that a sequence of steps can be captured in a CUDA graph and
+// replayed: the re-orthonormalisation timer (quadrotor.py:104, :381-386 - a global phase that reset() never
+// touches) and the Philox step index.
+struct Clock {
+  double svd_timer;
+  unsigned long long step;
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // kernel parameter block (passed by value as a __grid_constant__; lives in the constant bank)
 // ---------------------------------------------------------------------------------------------------------
@@ -42,10 +50,12 @@ struct Params {
   long long n;              // envs on the handle = row stride of the state buffer
   long long begin, end;     // env range [begin, end) this launch covers (chunked host pipeline)
   long long env_id_offset;
-  unsigned long long step_count;
   unsigned int seed_lo, seed_hi;
   // clocks
-  double svd_timer, svd_period, dt_d;
+  double svd_period, dt_d;
+  Clock* clock;             // device-resident global clock (read by every CTA, advanced by the last one)
+  unsigned int* clock_ticket;
+  int clock_advance;        // 0: read only (chunked host pipeline advances it with clock_advance_kernel)
   // layout / config
   int row_ou, row_act, row_gyro, row_goal;
   int obs_dim, act_dim;
@@ -84,6 +94,28 @@ struct Traits {
   static constexpr bool RARE = RARE_;   // drag/roll, linearity != 1, damping, uniform/quaternion/gyro-bias noise,
                                         // log reward, swarm, dim_mode != 3, per-env goal, info buffer
 };
+
+// replay of `since_last_svd += dt; if since_last_svd > limit: ...; since_last_svd = 0` in double (quadrotor.py:381-386)
+__device__ __forceinline__ bool svd_tick(double& t, double dt, double period) {
+  t += dt;
+  const bool fire = t > period;
+  if (fire) t = 0.0;
+  return fire;
+}
+
+// last CTA of the launch advances the device clock: every CTA read it at its start, and a CTA only takes a ticket
+// after its last use of the value, so nobody can observe the update within this launch
+template <typename R>
+__device__ __forceinline__ void finish_clock(const Params<R>& p, double svd_t_end, unsigned long long steps) {
+  if (threadIdx.x == 0 && p.clock_advance) {
+    const unsigned int t = atomicAdd(p.clock_ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *p.clock_ticket = 0u;
+      p.clock->svd_timer = svd_t_end;
+      p.clock->step += steps;
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // scalar maths
@@ -861,7 +893,8 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
   load_state<R, T>(s, p, i, active);
   NoiseSrc<R, T> ns(p, active ? i : 0);
 
-  double svd_t = p.svd_timer;
+  double svd_t = p.clock->svd_timer;
+  const unsigned long long step0 = p.clock->step;
   R rew_sum = R(0);
   bool done_any = false;
   R o[26];
@@ -869,7 +902,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
 
 #pragma unroll 1
   for (int ks = 0; ks < p.k_steps; ++ks) {
-    ns.begin_step(p.step_count + (unsigned long long)ks);
+    ns.begin_step(step0 + (unsigned long long)ks);
     // ---- action (:943-944) ----
     R a[4] = {R(0), R(0), R(0), R(0)};
     if (active && p.actions != nullptr) {
@@ -886,9 +919,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
     controller_cmds<R, T>(s, p, ctrl, a, cmd);
 #pragma unroll 1
     for (int sub = 0; sub < p.sim_steps; ++sub) {
-      svd_t += p.dt_d;                                                  // :381
-      bool fire = svd_t > p.svd_period;                                 // :382
-      if (fire) svd_t = 0.0;
+      const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);          // :381-386
       R z[4] = {R(0), R(0), R(0), R(0)};
       const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
       if (ou_on) ns.ou(sub, z);
@@ -945,6 +976,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
   }
   // finished-episode statistics: warp shuffle -> shared -> one double atomic triple per CTA
   const bool any = __syncthreads_or(done_any ? 1 : 0);                  // also orders the tile writes
+  finish_clock(p, svd_t, (unsigned long long)p.k_steps);                // every thread of the CTA has read the clock
   flush_tile(p, tile, block_first, nullptr);
   if (any) {
 #pragma unroll
@@ -981,7 +1013,7 @@ __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant_
     St<R> s;
     load_state<R, T>(s, p, i, true);
     NoiseSrc<R, T> ns(p, i);
-    ns.begin_step(p.step_count);
+    ns.begin_step(p.clock->step);
     reset_env<R, T>(s, p, ns);
     R o[26];
     build_obs<R, T>(s, p, ns, true, s.pa, o);
@@ -990,6 +1022,8 @@ __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant_
   }
   __syncthreads();
   flush_tile(p, tile, block_first, p.reset_mask ? valid : nullptr);
+  // a reset consumes one Philox step index so that its draws are never reused by a step
+  finish_clock(p, p.clock->svd_timer, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1002,7 +1036,7 @@ __global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_const
   St<R> s;
   load_state<R, T>(s, p, i, active);
   NoiseSrc<R, T> ns(p, active ? i : 0);
-  ns.begin_step(p.step_count);
+  ns.begin_step(p.clock->step);
   R a[4] = {R(0), R(0), R(0), R(0)};
   int adim = p.act_dim;
   if (active && p.actions != nullptr) {
@@ -1012,12 +1046,10 @@ __global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_const
   R cmd[4];
   if (p.dyn_controller < 0) { cmd[0] = a[0]; cmd[1] = a[1]; cmd[2] = a[2]; cmd[3] = a[3]; }
   else controller_cmds<R, T>(s, p, p.dyn_controller, a, cmd);
-  double svd_t = p.svd_timer;
+  double svd_t = p.clock->svd_timer;
 #pragma unroll 1
   for (int sub = 0; sub < p.dyn_substeps; ++sub) {
-    svd_t += p.dt_d;
-    bool fire = svd_t > p.svd_period;
-    if (fire) svd_t = 0.0;
+    const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);
     R z[4] = {R(0), R(0), R(0), R(0)};
     if (p.ou_on) ns.ou(sub, z);
     substep<R, T>(s, cmd, p, z, fire);
@@ -1033,6 +1065,17 @@ __global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_const
       inf[12] = cmd[0]; inf[13] = cmd[1]; inf[14] = cmd[2]; inf[15] = cmd[3];
     }
   }
+  __syncthreads();
+  finish_clock(p, svd_t, 1ull);
+}
+
+// advances the clock by one env step on behalf of a set of read-only (clock_advance = 0) chunk launches
+template <typename R>
+__global__ void clock_advance_kernel(const __grid_constant__ Params<R> p) {
+  double t = p.clock->svd_timer;
+  for (int k = 0; k < p.k_steps * p.sim_steps; ++k) svd_tick(t, p.dt_d, p.svd_period);
+  p.clock->svd_timer = t;
+  p.clock->step += (unsigned long long)p.k_steps;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1041,5 +1084,6 @@ __global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_const
 template <typename R> cudaError_t launch_step(const Params<R>& p, cudaStream_t st, const char** variant_name);
 template <typename R> cudaError_t launch_reset(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_dynamics(const Params<R>& p, cudaStream_t st);
+template <typename R> cudaError_t launch_clock_advance(const Params<R>& p, cudaStream_t st);
 
 }  // namespace qs

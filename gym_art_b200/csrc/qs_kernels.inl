@@ -65,4 +65,10 @@ cudaError_t launch_dynamics<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) 
   return cudaGetLastError();
 }
 
+template <>
+cudaError_t launch_clock_advance<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) {
+  clock_advance_kernel<QS_REAL><<<1, 1, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace qs

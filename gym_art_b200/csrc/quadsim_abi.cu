@@ -31,8 +31,8 @@ struct QsHandle {
   const void* reset_z;
   double* d_stats;
   int* d_status;
-  double svd_timer;
-  uint64_t step_count;
+  qs::Clock* d_clock;        // device-resident {svd_timer, step}: steps stay CUDA-graph capturable
+  unsigned int* d_ticket;
   uint64_t launches;
   std::string err;
   const char* last_variant;
@@ -128,10 +128,9 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.n = c.n_envs;
   p.begin = 0; p.end = c.n_envs;
   p.env_id_offset = c.env_id_offset;
-  p.step_count = h->step_count;
   p.seed_lo = (unsigned)(c.seed & 0xffffffffu);
   p.seed_hi = (unsigned)(c.seed >> 32);
-  p.svd_timer = h->svd_timer;
+  p.clock = h->d_clock; p.clock_ticket = h->d_ticket; p.clock_advance = 1;
   p.svd_period = c.svd_period;
   p.dt_d = c.dt;
   p.row_ou = h->lay.row_ou; p.row_act = h->lay.row_prev_action; p.row_gyro = h->lay.row_gyro_bias; p.row_goal = h->lay.row_goal;
@@ -199,22 +198,13 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   }
 }
 
-// advance the host copy of the global re-orthonormalisation timer exactly as the kernel does (quadrotor.py:381-386)
-void advance_clock(QsHandle* h, long long substeps) {
-  double t = h->svd_timer;
-  for (long long k = 0; k < substeps; ++k) {
-    t += h->cfg.dt;
-    if (t > h->cfg.svd_period) t = 0.0;
-  }
-  h->svd_timer = t;
-}
-
 template <typename R>
 int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8_t* done, cudaStream_t st,
-            long long begin, long long end) {
+            long long begin, long long end, int advance) {
   qs::Params<R> p;
   fill_params<R>(h, &p);
   p.k_steps = k;
+  p.clock_advance = advance;
   p.actions = (const R*)actions; p.obs = (R*)obs; p.rew = (R*)rew; p.done = done;
   p.begin = begin; p.end = end;
   cudaError_t e = qs::launch_step<R>(p, st, &h->last_variant);
@@ -257,8 +247,8 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   layout_of(cfg, &h->lay);
   h->state = h->info = nullptr;
   h->ou_z = h->obs_z = h->reset_z = nullptr;
-  h->d_stats = nullptr; h->d_status = nullptr;
-  h->svd_timer = 0.0; h->step_count = 0; h->launches = 0;
+  h->d_stats = nullptr; h->d_status = nullptr; h->d_clock = nullptr; h->d_ticket = nullptr;
+  h->launches = 0;
   h->last_variant = "";
   h->host_ready = false;
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
@@ -267,10 +257,16 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_status, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, 3 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(h->d_status, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_clock, sizeof(qs::Clock));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_clock, 0, sizeof(qs::Clock));
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
   if (e != cudaSuccess) {
     g_create_error = std::string("qs_create: ") + cudaGetErrorString(e);
     if (h->d_stats) cudaFree(h->d_stats);
     if (h->d_status) cudaFree(h->d_status);
+    if (h->d_clock) cudaFree(h->d_clock);
+    if (h->d_ticket) cudaFree(h->d_ticket);
     delete h;
     return QS_ECUDA;
   }
@@ -287,6 +283,8 @@ int qs_destroy(QsHandle* h) {
   }
   cudaFree(h->d_stats);
   cudaFree(h->d_status);
+  cudaFree(h->d_clock);
+  cudaFree(h->d_ticket);
   delete h;
   return QS_OK;
 }
@@ -331,7 +329,6 @@ int qs_reset(QsHandle* h, const uint8_t* mask, void* obs, qs_stream_t stream) {
   }
   if (e != cudaSuccess) return fail(h, QS_ECUDA, "env_reset launch: %s", cudaGetErrorString(e));
   h->launches++;
-  h->step_count++;   // a reset consumes one Philox step index so that its draws are never reused by a step
   return QS_OK;
 }
 
@@ -342,12 +339,9 @@ int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uin
   if (!obs || !rew || !done) return fail(h, QS_EINVAL, "obs/rew/done must not be NULL");
   if (k > 1 && h->cfg.noise_mode == QS_NOISE_INJECTED) return fail(h, QS_EUNSUPPORTED, "qs_step_k with injected noise needs k == 1");
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
-  if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs);
-  else rc = do_step<double>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs);
-  if (rc != QS_OK) return rc;
-  advance_clock(h, (long long)k * h->cfg.sim_steps);
-  h->step_count += (uint64_t)k;
-  return QS_OK;
+  if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs, 1);
+  else rc = do_step<double>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs, 1);
+  return rc;
 }
 
 int qs_step(QsHandle* h, const void* actions, void* obs, void* rew, uint8_t* done, qs_stream_t stream) {
@@ -375,8 +369,6 @@ int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_sub
   }
   if (e != cudaSuccess) return fail(h, QS_ECUDA, "dynamics_step launch: %s", cudaGetErrorString(e));
   h->launches++;
-  advance_clock(h, n_substeps);
-  h->step_count++;
   return QS_OK;
 }
 
@@ -413,8 +405,8 @@ int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* re
       QS_CUDA(h, cudaMemcpyAsync((char*)h->h_act + (size_t)b * ad * rs, (const char*)actions_host + (size_t)b * ad * rs,
                                  (size_t)(e - b) * ad * rs, cudaMemcpyHostToDevice, st));
     const void* act_dev = actions_host ? h->h_act : nullptr;
-    if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e);
-    else rc = do_step<double>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e);
+    if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e, 0);
+    else rc = do_step<double>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e, 0);
     if (rc != QS_OK) return rc;
     QS_CUDA(h, cudaMemcpyAsync((char*)obs_host + (size_t)b * od * rs, (char*)h->h_obs + (size_t)b * od * rs,
                                (size_t)(e - b) * od * rs, cudaMemcpyDeviceToHost, st));
@@ -423,8 +415,13 @@ int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* re
     QS_CUDA(h, cudaMemcpyAsync(done_host + b, h->h_done + b, (size_t)(e - b), cudaMemcpyDeviceToHost, st));
   }
   for (int k = 0; k < used; ++k) QS_CUDA(h, cudaStreamSynchronize(h->hs[k]));
-  advance_clock(h, h->cfg.sim_steps);
-  h->step_count += 1;
+  // the chunk launches only read the clock; advance it once for the whole step
+  cudaError_t ce;
+  if (h->cfg.dtype == QS_F32) { qs::Params<float> p; fill_params<float>(h, &p); ce = qs::launch_clock_advance<float>(p, h->hs[0]); }
+  else { qs::Params<double> p; fill_params<double>(h, &p); ce = qs::launch_clock_advance<double>(p, h->hs[0]); }
+  if (ce != cudaSuccess) return fail(h, QS_ECUDA, "clock_advance launch: %s", cudaGetErrorString(ce));
+  h->launches++;
+  QS_CUDA(h, cudaStreamSynchronize(h->hs[0]));
   return QS_OK;
 }
 
@@ -453,17 +450,25 @@ int qs_check(QsHandle* h, qs_stream_t stream) {
   return QS_OK;
 }
 
-int qs_get_clock(const QsHandle* h, double* svd_timer, uint64_t* step_count) {
+int qs_get_clock(QsHandle* h, double* svd_timer, uint64_t* step_count, qs_stream_t stream) {
   if (!h) return QS_EINVAL;
-  if (svd_timer) *svd_timer = h->svd_timer;
-  if (step_count) *step_count = h->step_count;
+  qs::Clock c;
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  QS_CUDA(h, cudaMemcpyAsync(&c, h->d_clock, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  QS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  if (svd_timer) *svd_timer = c.svd_timer;
+  if (step_count) *step_count = c.step;
   return QS_OK;
 }
 
-int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count) {
+int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count, qs_stream_t stream) {
   if (!h) return QS_EINVAL;
-  h->svd_timer = svd_timer;
-  h->step_count = step_count;
+  qs::Clock c;
+  c.svd_timer = svd_timer;
+  c.step = step_count;
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  QS_CUDA(h, cudaMemcpyAsync(h->d_clock, &c, sizeof(c), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  QS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
   return QS_OK;
 }
 

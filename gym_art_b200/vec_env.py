@@ -178,6 +178,7 @@ class QuadVecEnv(object):
             self.obs = torch.zeros((N, self.obs_dim), dtype=self.tdtype, device=self.device)
             self.rew = torch.zeros((N,), dtype=self.tdtype, device=self.device)
             self._done_u8 = torch.zeros((N,), dtype=torch.uint8, device=self.device)
+            self.done = self._done_u8.view(torch.bool)      # zero-copy: the kernel writes 0 / 1
             self.info = torch.zeros((N, _lib.QS_INFO_DIM), dtype=self.tdtype, device=self.device) if info else None
         self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.device).reshape(1, 9))
         if goals is not None:
@@ -303,14 +304,14 @@ class QuadVecEnv(object):
         a = self._actions(actions)
         _lib.check(self.lib.qs_step(self._h, None if a is None else a.data_ptr(), self.obs.data_ptr(), self.rew.data_ptr(),
                                     self._done_u8.data_ptr(), self._stream()), self._h)
-        return self.obs, self.rew, self._done_u8.bool()
+        return self.obs, self.rew, self.done
 
     def step_k(self, k, actions=None):
         """k fused env steps in one launch; returns (last obs, summed reward, any-done)."""
         a = self._actions(actions, k)
         _lib.check(self.lib.qs_step_k(self._h, int(k), None if a is None else a.data_ptr(), self.obs.data_ptr(),
                                       self.rew.data_ptr(), self._done_u8.data_ptr(), self._stream()), self._h)
-        return self.obs, self.rew, self._done_u8.bool()
+        return self.obs, self.rew, self.done
 
     def step_host(self, actions_host, obs_host, rew_host, done_host):
         """End-to-end step on HOST tensors (pinned for full PCIe speed): H2D, fused step, D2H, synchronous."""
@@ -354,12 +355,12 @@ class QuadVecEnv(object):
     @property
     def clock(self):
         t, s = C.c_double(), C.c_uint64()
-        _lib.check(self.lib.qs_get_clock(self._h, C.byref(t), C.byref(s)), self._h)
+        _lib.check(self.lib.qs_get_clock(self._h, C.byref(t), C.byref(s), self._stream()), self._h)
         return t.value, s.value
 
     @clock.setter
     def clock(self, value):
-        _lib.check(self.lib.qs_set_clock(self._h, float(value[0]), int(value[1])), self._h)
+        _lib.check(self.lib.qs_set_clock(self._h, float(value[0]), int(value[1]), self._stream()), self._h)
 
     @property
     def launch_count(self):

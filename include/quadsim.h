@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 3
+#define QS_ABI_VERSION 4
 
 typedef struct QsHandle QsHandle;
 typedef void* qs_stream_t; /* cudaStream_t */
@@ -247,9 +247,11 @@ int qs_stats_device_ptr(QsHandle* h, double** out);
 int qs_check(QsHandle* h, qs_stream_t stream);
 
 /* Global bookkeeping that is part of a checkpoint: the re-orthonormalisation timer (quadrotor.py:104,381-386;
- * a global phase, never reset by reset()) and the Philox step counter. */
-int qs_get_clock(const QsHandle* h, double* svd_timer, uint64_t* step_count);
-int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count);
+ * a global phase, never reset by reset()) and the Philox step counter.  Both live on the device (the last CTA
+ * of every launch advances them), so a sequence of qs_step calls can be captured in a CUDA graph and replayed.
+ * These two calls copy across PCIe and synchronise the stream. */
+int qs_get_clock(QsHandle* h, double* svd_timer, uint64_t* step_count, qs_stream_t stream);
+int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count, qs_stream_t stream);
 
 /* Number of kernels this handle has launched (bench.py reports it as gpu_launches). */
 int qs_launch_count(const QsHandle* h, uint64_t* out);

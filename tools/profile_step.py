@@ -1,0 +1,50 @@
+"""Small driver for ncu: steps one QuadVecEnv a few times with plain launches (no CUDA graph).
+
+    python tools/profile_step.py --envs 4194304 --steps 8 --config cfg2
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    from gym_art_b200 import QuadVecEnv
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4 * 1024 * 1024)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg4"])
+    a = ap.parse_args()
+    kw = dict(device="cuda:0", ep_time=5, seed=1)
+    if a.config == "cfg2":
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", **kw)
+    elif a.config == "cfg3":
+        env = QuadVecEnv(a.envs, dynamics_params="Crazyflie", controller="omega_thrust", sense_noise="default",
+                         init_random_state=True, **kw)
+    elif a.config == "cfg5":
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="mellinger", **kw)
+    else:
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", n_agents=8, **kw)
+    env.reset()
+    act = torch.rand((a.envs, env.act_dim), device="cuda:0") * 2 - 1
+    if a.config == "cfg3":
+        act[:, 0] *= 0.2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        env.step(act)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.steps):
+        env.step(act)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print("variant %s  %.1f us/step  %.3e env-steps/s  %.0f GB/s algorithmic (349 B/env-step)" % (
+        env.kernel_variant, ms * 1e3, a.envs / (ms * 1e-3), a.envs * 349 / (ms * 1e-3) / 1e9))
+    env.check_finite()
+
+
+if __name__ == "__main__":
+    main()

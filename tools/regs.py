@@ -3,7 +3,7 @@ import re
 import subprocess
 import sys
 import os
-B = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gym_art_b200", "_build")
+B = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gym_art_b200", "_build")
 for f in ["qs_kernels_f32.o.log", "qs_kernels_f64.o.log"]:
     txt = open(os.path.join(B, f)).read()
     for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", txt):
