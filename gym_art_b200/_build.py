@@ -15,8 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libquadsim.so")
-SOURCES = ["qs_kernels_f32.cu", "qs_kernels_f64.cu", "quadsim_abi.cu"]
-DEPS = ["qs_device.cuh", "qs_kernels.inl", os.path.join("..", "..", "include", "quadsim.h")]
+SOURCES = ["qs_kernels_f32.cu", "qs_kernels_f32_fast_philox.cu", "qs_kernels_f32_fast_inject.cu", "qs_kernels_f64.cu",
+           "quadsim_abi.cu"]
+DEPS = ["qs_device.cuh", "qs_kernels.inl", "qs_fast.inl", os.path.join("..", "..", "include", "quadsim.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # no --use_fast_math: parity with the float64 reference is part of the contract (fast intrinsics are used
 # explicitly, and only inside the Philox Box-Muller transform)

@@ -65,6 +65,7 @@ struct Params {
   int init_random, auto_reset, sense_on, ou_on, gyro_bias_mode;
   int dyn_controller, dyn_substeps;   // qs_dynamics_step
   int inject, need_rare;              // variant selection (host)
+  int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
   // model
   R dt;
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
@@ -245,31 +246,57 @@ template <typename R> __device__ __forceinline__ void st4(R* base, long long n, 
   *reinterpret_cast<V4<R>*>(base + ((long long)row * n + i) * 4) = v;
 }
 
+template <typename R, typename Q>
+__device__ __forceinline__ void unpack_core(St<R>& s, const Q& q0, const Q& q1, const Q& q2, const Q& q3, const Q& q4,
+                                            const Q& q5, const Q& q6) {
+  s.px = q0.x; s.py = q0.y; s.pz = q0.z; s.vx = q0.w;
+  s.vy = q1.x; s.vz = q1.y; s.wx = q1.z; s.wy = q1.w;
+  s.wz = q2.x; s.r[0] = q2.y; s.r[1] = q2.z; s.r[2] = q2.w;
+  s.r[3] = q3.x; s.r[4] = q3.y; s.r[5] = q3.z; s.r[6] = q3.w;
+  s.r[7] = q4.x; s.r[8] = q4.y; s.tick = q4.z; s.ret = q4.w;
+  s.rd[0] = q5.x; s.rd[1] = q5.y; s.rd[2] = q5.z; s.rd[3] = q5.w;
+  s.cd[0] = q6.x; s.cd[1] = q6.y; s.cd[2] = q6.z; s.cd[3] = q6.w;
+}
+
+template <typename R>
+__device__ __forceinline__ void default_core(St<R>& s) {   // lanes beyond the last env: harmless identity state
+  s.px = s.py = s.pz = s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) s.r[k] = (k % 4 == 0) ? R(1) : R(0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s.rd[k] = R(0); s.cd[k] = R(0); }
+  s.tick = R(0); s.ret = R(0);
+}
+
+template <typename R>
+__device__ __forceinline__ void init_optional(St<R>& s, const Params<R>& p) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s.ou[k] = R(0); s.pa[k] = R(0); }
+  s.gb[0] = s.gb[1] = s.gb[2] = R(0);
+  s.gx = p.goal[0]; s.gy = p.goal[1]; s.gz = p.goal[2];
+}
+
+template <typename R>
+__device__ __forceinline__ void finish_load(St<R>& s) {
+  s.ax = s.ay = s.az = R(0);
+  s.tqx = s.tqy = s.tqz = s.odx = s.ody = s.odz = R(0);
+  // straight after set_state()/reset() (tick 0, motor filter zeroed, :438-440) omega is still the float32 array of :223
+  s.w_is_f32 = (s.tick == R(0)) && (s.rd[0] == R(0)) && (s.rd[1] == R(0)) && (s.rd[2] == R(0)) && (s.rd[3] == R(0)) &&
+               (s.cd[0] == R(0)) && (s.cd[1] == R(0)) && (s.cd[2] == R(0)) && (s.cd[3] == R(0));
+  s.fresh = false;
+}
+
 template <typename R, class T>
 __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long long i, bool active) {
   if (active) {
     V4<R> q0 = ld4(p.state, p.n, 0, i), q1 = ld4(p.state, p.n, 1, i), q2 = ld4(p.state, p.n, 2, i);
     V4<R> q3 = ld4(p.state, p.n, 3, i), q4 = ld4(p.state, p.n, 4, i), q5 = ld4(p.state, p.n, 5, i);
     V4<R> q6 = ld4(p.state, p.n, 6, i);
-    s.px = q0.x; s.py = q0.y; s.pz = q0.z; s.vx = q0.w;
-    s.vy = q1.x; s.vz = q1.y; s.wx = q1.z; s.wy = q1.w;
-    s.wz = q2.x; s.r[0] = q2.y; s.r[1] = q2.z; s.r[2] = q2.w;
-    s.r[3] = q3.x; s.r[4] = q3.y; s.r[5] = q3.z; s.r[6] = q3.w;
-    s.r[7] = q4.x; s.r[8] = q4.y; s.tick = q4.z; s.ret = q4.w;
-    s.rd[0] = q5.x; s.rd[1] = q5.y; s.rd[2] = q5.z; s.rd[3] = q5.w;
-    s.cd[0] = q6.x; s.cd[1] = q6.y; s.cd[2] = q6.z; s.cd[3] = q6.w;
+    unpack_core(s, q0, q1, q2, q3, q4, q5, q6);
   } else {
-    s.px = s.py = s.pz = s.vx = s.vy = s.vz = s.wx = s.wy = s.wz = R(0);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s.r[k] = (k % 4 == 0) ? R(1) : R(0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { s.rd[k] = R(0); s.cd[k] = R(0); }
-    s.tick = R(0); s.ret = R(0);
+    default_core(s);
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { s.ou[k] = R(0); s.pa[k] = R(0); }
-  s.gb[0] = s.gb[1] = s.gb[2] = R(0);
-  s.gx = p.goal[0]; s.gy = p.goal[1]; s.gz = p.goal[2];
+  init_optional(s, p);
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (active) {
     if (ou_on) { V4<R> q = ld4(p.state, p.n, p.row_ou, i); s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
@@ -279,12 +306,7 @@ __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long lo
       if (p.row_goal >= 0) { V4<R> q = ld4(p.state, p.n, p.row_goal, i); s.gx = q.x; s.gy = q.y; s.gz = q.z; }
     }
   }
-  s.ax = s.ay = s.az = R(0);
-  s.tqx = s.tqy = s.tqz = s.odx = s.ody = s.odz = R(0);
-  // straight after set_state()/reset() (tick 0, motor filter zeroed, :438-440) omega is still the float32 array of :223
-  s.w_is_f32 = (s.tick == R(0)) && (s.rd[0] == R(0)) && (s.rd[1] == R(0)) && (s.rd[2] == R(0)) && (s.rd[3] == R(0)) &&
-               (s.cd[0] == R(0)) && (s.cd[1] == R(0)) && (s.cd[2] == R(0)) && (s.cd[3] == R(0));
-  s.fresh = false;
+  finish_load(s);
 }
 
 template <typename R, class T>
@@ -876,28 +898,25 @@ __device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// THE kernel: QuadrotorEnv.step for every env (quadrotor.py:942-1028), k_steps times, + auto-reset
+// QuadrotorEnv.step (quadrotor.py:942-1028) for one env held in registers, k_steps times, + folded auto-reset.
+// Shared by the direct-load kernel and the TMA-pipelined kernel below.
 // ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct StepOut {
+  R rew_sum;
+  bool done_any;
+  double st_ret, st_ret2, st_n;   // finished-episode statistics of this thread
+  double svd_t;                   // value of the global re-orthonormalisation timer after the last substep
+};
+
 template <typename R, class T>
-__global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__ Params<R> p) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  R* tile = reinterpret_cast<R*>(smem_raw);                             // [BLOCK][obs_dim]
-  __shared__ double red[3][BLOCK / 32];
-
-  const long long block_first = p.begin + (long long)blockIdx.x * BLOCK;
-  const long long i = block_first + threadIdx.x;
-  const bool active = i < p.end;
+__device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long long i, bool active, const R* a_first,
+                                          double svd_t0, unsigned long long step0, R* o, StepOut<R>& out) {
   const int ctrl = T::CTRL >= 0 ? T::CTRL : p.controller;
-
-  St<R> s;
-  load_state<R, T>(s, p, i, active);
   NoiseSrc<R, T> ns(p, active ? i : 0);
-
-  double svd_t = p.clock->svd_timer;
-  const unsigned long long step0 = p.clock->step;
+  double svd_t = svd_t0;
   R rew_sum = R(0);
   bool done_any = false;
-  R o[26];
   double st_ret = 0.0, st_ret2 = 0.0, st_n = 0.0;
 
 #pragma unroll 1
@@ -905,7 +924,9 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
     ns.begin_step(step0 + (unsigned long long)ks);
     // ---- action (:943-944) ----
     R a[4] = {R(0), R(0), R(0), R(0)};
-    if (active && p.actions != nullptr) {
+    if (a_first != nullptr && ks == 0) {
+      a[0] = a_first[0]; a[1] = a_first[1]; a[2] = a_first[2]; a[3] = a_first[3];
+    } else if (active && p.actions != nullptr) {
       const R* ap = p.actions + ((long long)ks * p.n + i) * p.act_dim;
       if (p.act_dim == 4) { V4<R> v = *reinterpret_cast<const V4<R>*>(ap); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
       else {
@@ -966,34 +987,197 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
       }
     }
   }
+  out.rew_sum = rew_sum; out.done_any = done_any;
+  out.st_ret = st_ret; out.st_ret2 = st_ret2; out.st_n = st_n; out.svd_t = svd_t;
+}
+
+// finished-episode statistics of a CTA: warp shuffle -> shared -> one double atomic triple (called by all threads)
+template <typename R>
+__device__ __forceinline__ void block_stats(const Params<R>& p, double (*red)[BLOCK / 32], double st_ret, double st_ret2, double st_n) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    st_ret += __shfl_down_sync(0xffffffffu, st_ret, off);
+    st_ret2 += __shfl_down_sync(0xffffffffu, st_ret2, off);
+    st_n += __shfl_down_sync(0xffffffffu, st_n, off);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = st_ret; red[1][threadIdx.x >> 5] = st_ret2; red[2][threadIdx.x >> 5] = st_n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) { a0 += red[0][w]; a1 += red[1][w]; a2 += red[2][w]; }
+    if (a2 > 0) { atomicAdd(&p.stats[0], a0); atomicAdd(&p.stats[1], a1); atomicAdd(&p.stats[2], a2); }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel 1 (generic): one CTA per 128 envs, direct vector loads.  Used by the fp64 build and by every
+// configuration outside the fast subset.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__ Params<R> p) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  R* tile = reinterpret_cast<R*>(smem_raw);                             // [BLOCK][obs_dim]
+  __shared__ double red[3][BLOCK / 32];
+
+  const long long block_first = p.begin + (long long)blockIdx.x * BLOCK;
+  const long long i = block_first + threadIdx.x;
+  const bool active = i < p.end;
+
+  St<R> s;
+  load_state<R, T>(s, p, i, active);
+  R o[26];
+  StepOut<R> out;
+  run_steps<R, T>(s, p, i, active, nullptr, p.clock->svd_timer, p.clock->step, o, out);
 
   // ---- write back: state (float4 rows), obs (shared-memory transpose), reward, done ----
   if (active) {
     store_state<R, T>(s, p, i);
-    p.rew[i] = rew_sum;
-    p.done[i] = done_any ? 1 : 0;
+    p.rew[i] = out.rew_sum;
+    p.done[i] = out.done_any ? 1 : 0;
     obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
   }
-  // finished-episode statistics: warp shuffle -> shared -> one double atomic triple per CTA
-  const bool any = __syncthreads_or(done_any ? 1 : 0);                  // also orders the tile writes
-  finish_clock(p, svd_t, (unsigned long long)p.k_steps);                // every thread of the CTA has read the clock
+  const bool any = __syncthreads_or(out.done_any ? 1 : 0);              // also orders the tile writes
+  finish_clock(p, out.svd_t, (unsigned long long)p.k_steps);            // every thread of the CTA has read the clock
   flush_tile(p, tile, block_first, nullptr);
-  if (any) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      st_ret += __shfl_down_sync(0xffffffffu, st_ret, off);
-      st_ret2 += __shfl_down_sync(0xffffffffu, st_ret2, off);
-      st_n += __shfl_down_sync(0xffffffffu, st_n, off);
+  if (any) block_stats(p, red, out.st_ret, out.st_ret2, out.st_n);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel 2 (fp32 fast subset): persistent CTAs, TMA-pipelined.
+//   * grid = min(tiles, resident CTA slots); each CTA walks tiles of 128 envs with stride gridDim.x;
+//   * one elected thread fetches the NEXT tile (every state row + the action row: contiguous 2 KB runs of the
+//     structure-of-arrays layout) with cp.async.bulk into the other shared-memory stage and arms an mbarrier with
+//     the expected byte count, while all threads compute the current tile out of shared memory -> the HBM read
+//     latency never sits on a warp's scoreboard;
+//   * the state is written back straight from registers (coalesced 16-byte stores), the observation tile goes
+//     through shared memory and leaves as ONE cp.async.bulk store per tile.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+constexpr int TMA_MIN_CTAS = 4;   // resident CTAs per SM the fast kernel is tuned for (registers <= 128)
+
+template <class T>
+__global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const __grid_constant__ Params<float> p) {
+  typedef float R;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ double red[3][BLOCK / 32];
+
+  const int tid = threadIdx.x;
+  const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
+  const bool has_act = p.actions != nullptr;
+  const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
+  float4* in = reinterpret_cast<float4*>(smem_raw);
+  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4));
+  const int obs_tile_floats = BLOCK * p.obs_dim;
+  const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
+
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  __syncthreads();
+
+  const double svd_t0 = p.clock->svd_timer;
+  const unsigned long long step0 = p.clock->step;
+  double svd_end = svd_t0;
+
+  auto issue_load = [&](long long tile, int stage) {
+    const long long first = p.begin + tile * BLOCK;
+    long long rows = p.end - first;
+    if (rows > BLOCK) rows = BLOCK;
+    const uint32_t bytes = (uint32_t)rows * 16u;
+    mbar_expect_tx(&bar[stage], bytes * (uint32_t)(rows_in + (has_act ? 1 : 0)));
+    float4* dst = in + (size_t)stage * stage_vecs;
+    const float* src = p.state + first * 4;
+    for (int r = 0; r < rows_in; ++r) bulk_g2s(dst + r * BLOCK, src + (long long)r * p.n * 4, bytes, &bar[stage]);
+    if (has_act) bulk_g2s(dst + rows_in * BLOCK, p.actions + first * 4, bytes, &bar[stage]);
+  };
+
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
+
+  int j = 0;
+  for (; tile < n_tiles; tile += gridDim.x, ++j) {
+    const int stage = j & 1;
+    const long long next = tile + gridDim.x;
+    if (tid == 0 && next < n_tiles) issue_load(next, stage ^ 1);         // prefetch: a whole iteration to land
+    const long long block_first = p.begin + tile * BLOCK;
+    const long long i = block_first + tid;
+    const bool active = i < p.end;
+
+    mbar_wait(&bar[stage], (uint32_t)((j >> 1) & 1));
+    const float4* buf = in + (size_t)stage * stage_vecs + tid;
+    St<R> s;
+    if (active) {
+      unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
+    } else {
+      default_core(s);
     }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = st_ret; red[1][threadIdx.x >> 5] = st_ret2; red[2][threadIdx.x >> 5] = st_n; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll
-      for (int w = 0; w < BLOCK / 32; ++w) { a0 += red[0][w]; a1 += red[1][w]; a2 += red[2][w]; }
-      if (a2 > 0) { atomicAdd(&p.stats[0], a0); atomicAdd(&p.stats[1], a1); atomicAdd(&p.stats[2], a2); }
+    init_optional(s, p);
+    R a0[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+      if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
+      if (p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+      if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
     }
+    finish_load(s);
+
+    R o[26];
+    StepOut<R> out;
+    run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out);
+    svd_end = out.svd_t;
+
+    float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
+    if (active) {
+      store_state<R, T>(s, p, i);
+      p.rew[i] = out.rew_sum;
+      p.done[i] = out.done_any ? 1 : 0;
+      obs_to_tile(p, o, tile_obs + tid * p.obs_dim);
+    }
+    // the bulk store issued one iteration ago must have drained the OTHER obs tile before anybody rewrites it in
+    // the next iteration; it has had a whole iteration to do so
+    if (tid == 0) bulk_wait_read0();
+    fence_proxy_async();                                                // generic-proxy tile writes -> async proxy
+    const bool any = __syncthreads_or(out.done_any ? 1 : 0);
+    long long rows = p.end - block_first;
+    if (rows > BLOCK) rows = BLOCK;
+    const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
+    if ((obs_bytes & 15u) == 0u) {
+      if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
+    } else {
+      flush_tile(p, tile_obs, block_first, nullptr);                    // ragged last tile
+    }
+    if (any) block_stats(p, red, out.st_ret, out.st_ret2, out.st_n);
   }
+  if (tid == 0) bulk_wait_read0();                                      // shared memory must outlive the bulk stores
+  finish_clock(p, svd_end, (unsigned long long)p.k_steps);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1085,5 +1269,8 @@ template <typename R> cudaError_t launch_step(const Params<R>& p, cudaStream_t s
 template <typename R> cudaError_t launch_reset(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_dynamics(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_clock_advance(const Params<R>& p, cudaStream_t st);
+// fp32 fast subset (qs_fast.inl)
+cudaError_t launch_fast_philox(const Params<float>& p, cudaStream_t st, const char** variant_name);
+cudaError_t launch_fast_inject(const Params<float>& p, cudaStream_t st, const char** variant_name);
 
 }  // namespace qs

@@ -1,4 +1,4 @@
-// qs_kernels.inl - kernel instantiation + variant dispatch for one real type (QS_REAL), included by
+// qs_kernels.inl - generic kernel instantiation + variant dispatch for one real type (QS_REAL), included by
 // qs_kernels_f32.cu / qs_kernels_f64.cu so that the two precisions compile in parallel.
 #include "qs_device.cuh"
 
@@ -15,33 +15,16 @@ static cudaError_t launch_step_t(const Params<R>& p, cudaStream_t st) {
 typedef Traits<-1, -1, -1, true, true> TGenInject;
 typedef Traits<-1, -1, -1, false, true> TGenPhilox;
 
-#ifdef QS_FAST_VARIANTS
-// default-feature subset, compile-time controller / OU / sensor-noise switches (fp32 throughput path)
-template <typename R, int C>
-static cudaError_t launch_fast_c(const Params<R>& p, cudaStream_t st) {
-  if (p.ou_on) {
-    if (p.sense_on) return launch_step_t<R, Traits<C, 1, 1, false, false> >(p, st);
-    return launch_step_t<R, Traits<C, 1, 0, false, false> >(p, st);
-  }
-  if (p.sense_on) return launch_step_t<R, Traits<C, 0, 1, false, false> >(p, st);
-  return launch_step_t<R, Traits<C, 0, 0, false, false> >(p, st);
-}
-#endif
-
 template <>
 cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, const char** name) {
   typedef QS_REAL R;
-  if (p.inject) { if (name) *name = "generic-injected"; return launch_step_t<R, TGenInject>(p, st); }
 #ifdef QS_FAST_VARIANTS
-  if (!p.need_rare) {
-    switch (p.controller) {
-      case CTRL_RAW: if (name) *name = "fast-raw"; return launch_fast_c<R, CTRL_RAW>(p, st);
-      case CTRL_OMEGA_THRUST: if (name) *name = "fast-omega-thrust"; return launch_fast_c<R, CTRL_OMEGA_THRUST>(p, st);
-      case CTRL_MELLINGER: if (name) *name = "fast-mellinger"; return launch_fast_c<R, CTRL_MELLINGER>(p, st);
-      default: break;
-    }
+  if (!p.need_rare && p.act_dim == 4 &&
+      (p.controller == CTRL_RAW || p.controller == CTRL_OMEGA_THRUST || p.controller == CTRL_MELLINGER)) {
+    return p.inject ? launch_fast_inject(p, st, name) : launch_fast_philox(p, st, name);
   }
 #endif
+  if (p.inject) { if (name) *name = "generic-injected"; return launch_step_t<R, TGenInject>(p, st); }
   if (name) *name = "generic-philox";
   return launch_step_t<R, TGenPhilox>(p, st);
 }
