@@ -166,6 +166,38 @@ template <> struct Mth<double> {
 
 template <typename R> __device__ __forceinline__ R clampr(R x, R lo, R hi) { return Mth<R>::min(Mth<R>::max(x, lo), hi); }
 
+// Fast fp32 forms used by the throughput variants (Traits::RARE == false): MUFU.RSQ / MUFU.RCP based, ~2 ulp, no
+// denormal / special-case branches.  The per-step parity tests run these same variants (injected-noise twins).
+template <typename R, bool FAST> __device__ __forceinline__ R q_rsqrt(R x) {
+  if (FAST && sizeof(R) == 4) return (R)rsqrtf((float)x);
+  return R(1) / Mth<R>::sqrt(x);
+}
+template <typename R, bool FAST> __device__ __forceinline__ R q_sqrt(R x) {       // x >= 0
+  if (FAST && sizeof(R) == 4) { float xf = (float)x; return (R)(xf * rsqrtf(fmaxf(xf, 1e-30f))); }
+  return Mth<R>::sqrt(x);
+}
+template <typename R, bool FAST> __device__ __forceinline__ R q_rcp(R x) {
+  if (FAST && sizeof(R) == 4) return (R)__frcp_rn((float)x);
+  return R(1) / x;
+}
+// sin and cos of a small angle (the half rotation angle of one substep, <= omega_max*sqrt(3)*dt/2 ~ 0.17 rad at the
+// default dt): Taylor polynomials to x^9 / x^8, relative truncation error < 3e-8 for |x| <= 0.8, far below
+// the fp32 rounding of the matrix update; larger angles take the library routine.
+template <typename R, bool FAST> __device__ __forceinline__ void q_sincos_small(R x, R* s, R* c) {
+  if (FAST && sizeof(R) == 4) {
+    float xf = (float)x;
+    if (fabsf(xf) <= 0.8f) {
+      float x2 = xf * xf;
+      float sp = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
+      float cp = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587e-5f, -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
+      *s = (R)(xf * sp);
+      *c = (R)cp;
+      return;
+    }
+  }
+  Mth<R>::sincos(x, s, c);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter-based: no RNG state in HBM
 // ---------------------------------------------------------------------------------------------------------
@@ -359,7 +391,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
   for (int k = 0; k < 4; ++k) {
     R c = clampr(cmd[k], R(0), R(1));                                   // :279
     R tau = (c < s.cd[k]) ? p.tau_down : p.tau_up;                      // :284-288 (tau pre-clipped to 1 on the host)
-    R rt = Mth<R>::sqrt(c);                                             // :294
+    R rt = q_sqrt<R, !T::RARE>(c);                                      // :294
     s.rd[k] = tau * (rt - s.rd[k]) + s.rd[k];                           // :295
     R cd = s.rd[k] * s.rd[k];                                           // :296
     if (ou_on) {
@@ -414,13 +446,15 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     R ox = s.r[0] * s.wx + s.r[1] * s.wy + s.r[2] * s.wz;
     R oy = s.r[3] * s.wx + s.r[4] * s.wy + s.r[5] * s.wz;
     R oz = s.r[6] * s.wx + s.r[7] * s.wy + s.r[8] * s.wz;
-    R on = Mth<R>::sqrt(ox * ox + oy * oy + oz * oz);
-    if (on != R(0)) {
-      R inv = R(1) / on;
+    R on2 = ox * ox + oy * oy + oz * oz;
+    if (on2 != R(0)) {
+      R inv, on;
+      if (!T::RARE && sizeof(R) == 4) { inv = q_rsqrt<R, true>(Mth<R>::max(on2, R(1e-30))); on = on2 * inv; }
+      else { on = Mth<R>::sqrt(on2); inv = R(1) / on; }
       R kx = ox * inv, ky = oy * inv, kz = oz * inv;
       // sin(a) and 1 - cos(a) from the half angle: no cancellation for the small per-substep angles
       R sh, ch;
-      Mth<R>::sincos(R(0.5) * (on * dt), &sh, &ch);
+      q_sincos_small<R, !T::RARE>(R(0.5) * (on * dt), &sh, &ch);
       R sa = R(2) * sh * ch, cm = R(2) * sh * sh;
       R kxx = kx * kx, kyy = ky * ky, kzz = kz * kz, kxy = kx * ky, kxz = kx * kz, kyz = ky * kz;
       R d00 = R(1) - cm * (kyy + kzz), d01 = cm * kxy - sa * kz, d02 = cm * kxz + sa * ky;
@@ -498,7 +532,12 @@ __device__ __forceinline__ void accelerometer(const St<R>& s, const Params<R>& p
 // ---------------------------------------------------------------------------------------------------------
 // controllers: policy action -> 4 normalized motor commands (quadrotor_control.py)
 // ---------------------------------------------------------------------------------------------------------
-template <typename R> __device__ __forceinline__ void normalize3(R& x, R& y, R& z) {   // quad_utils.py:35-41
+template <typename R, bool FAST = false> __device__ __forceinline__ void normalize3(R& x, R& y, R& z) {   // quad_utils.py:35-41
+  if (FAST && sizeof(R) == 4) {
+    R n2 = x * x + y * y + z * z;
+    if (!(n2 < R(1e-10))) { R inv = q_rsqrt<R, true>(n2); x = x * inv; y = y * inv; z = z * inv; }
+    return;
+  }
   R n = Mth<R>::sqrt(x * x + y * y + z * z);
   if (!(n < R(0.00001))) { x = x / n; y = y / n; z = z / n; }
 }
@@ -510,13 +549,16 @@ __device__ __forceinline__ void jinv_mix(const Params<R>& p, R d0, R d1, R d2, R
     cmd[k] = clampr(p.jinv[k][0] * d0 + p.jinv[k][1] * d1 + p.jinv[k][2] * d2 + p.jinv[k][3] * d3, R(0), R(1));
 }
 
-template <typename R>
+template <typename R, bool FAST>
 __device__ __forceinline__ void attitude_controller(const St<R>& s, const Params<R>& p, bool mellinger, const R* a, R* cmd) {
   R adx, ady, adz, xcx, xcy, xcz, ewx, ewy, ewz, kp_a, kd_a, yaw_scale;
   if (mellinger) {                                                      // :315-362
     R tx = s.gx - s.px, ty = s.gy - s.py, tz = s.gz - s.pz;
-    R n = Mth<R>::sqrt(tx * tx + ty * ty + tz * tz);
-    if (!(n <= R(4))) { R f = R(4) / n; tx = f * tx; ty = f * ty; tz = f * tz; }   // clamp_norm, quad_utils.py:63-67
+    R n2 = tx * tx + ty * ty + tz * tz;
+    if (!(n2 <= R(16))) {                                               // clamp_norm, quad_utils.py:63-67
+      R f = FAST ? R(4) * q_rsqrt<R, FAST>(n2) : R(4) / Mth<R>::sqrt(n2);
+      tx = f * tx; ty = f * ty; tz = f * tz;
+    }
     R epx = -tx, epy = -ty, epz = -tz;                                  // :320
     adx = R(-4.5) * epx - R(3.5) * s.vx;                                // :323
     ady = R(-4.5) * epy - R(3.5) * s.vy;
@@ -531,9 +573,9 @@ __device__ __forceinline__ void attitude_controller(const St<R>& s, const Params
     kp_a = R(100); kd_a = R(50); yaw_scale = R(1);
   }
   R zx = adx, zy = ady, zz = adz;
-  normalize3(zx, zy, zz);                                               // :338
+  normalize3<R, FAST>(zx, zy, zz);                                      // :338
   R yx = zy * xcz - zz * xcy, yy = zz * xcx - zx * xcz, yz = zx * xcy - zy * xcx;   // cross(zb, xc)
-  normalize3(yx, yy, yz);                                               // :339
+  normalize3<R, FAST>(yx, yy, yz);                                      // :339
   R xx = yy * zz - yz * zy, xy = yz * zx - yx * zz, xz = yx * zy - yy * zx;          // cross(yb, zb) :340
   // A = R_des^T R ; e_R = 0.5 * vee(A - A^T) (:344-346)
   R a21 = zx * s.r[1] + zy * s.r[4] + zz * s.r[7], a12 = yx * s.r[2] + yy * s.r[5] + yz * s.r[8];
@@ -571,7 +613,7 @@ __device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>&
     R acc_des = R(9.81) * (a[0] + R(1));
     jinv_mix(p, acc_des, dwx, dwy, dwz, cmd);
   } else {
-    attitude_controller(s, p, ctrl == CTRL_MELLINGER, a, cmd);
+    attitude_controller<R, !T::RARE>(s, p, ctrl == CTRL_MELLINGER, a, cmd);
   }
 }
 
@@ -582,11 +624,11 @@ template <typename R, class T>
 __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, const R* a, const R* a_prev,
                                             bool crashed, bool collided, R* costs) {
   R dx = s.gx - s.px, dy = s.gy - s.py, dz = s.gz - s.pz;
-  R dist = Mth<R>::sqrt(dx * dx + dy * dy + dz * dz);
+  R dist = q_sqrt<R, !T::RARE>(dx * dx + dy * dy + dz * dz);
   R c_pos;
   if (T::RARE && p.log_pos) c_pos = p.c_pos * (p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist);
   else c_pos = p.c_pos * dist;                                          // :547-549
-  R c_eff = p.c_effort * Mth<R>::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
+  R c_eff = p.c_effort * q_sqrt<R, !T::RARE>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
   R c_ac = R(0);
   if (p.c_act_change != R(0)) {                                         // :556-558
     R e0 = a[0] - a_prev[0], e1 = a[1] - a_prev[1], e2 = a[2] - a_prev[2], e3 = a[3] - a_prev[3];
@@ -599,7 +641,7 @@ __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, 
   R c_rot = R(0), c_att = R(0);
   if (p.c_rot != R(0)) c_rot = p.c_rot * Mth<R>::acos(clampr(((s.r[0] + s.r[4] + s.r[8]) - R(1)) / R(2), R(-1), R(1)));
   if (p.c_attitude != R(0)) c_att = p.c_attitude * Mth<R>::acos(clampr(s.r[8], R(-1), R(1)));      // :580-581
-  R c_spin = p.c_spin * Mth<R>::sqrt(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);                     // :585-586
+  R c_spin = p.c_spin * q_sqrt<R, !T::RARE>(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);              // :585-586
   R c_crash = crashed ? p.c_crash : R(0);                               // :590-591
   R sum = ((c_pos + c_eff) + (c_crash + c_or)) + ((c_yaw + c_rot) + (c_att + c_spin));            // np.sum pairwise
   sum = (sum + c_ac) + c_vel;                                           // :593-604
@@ -650,10 +692,17 @@ struct NoiseSrc {
 // ---------------------------------------------------------------------------------------------------------
 // SensorNoise.add_noise (sensor_noise.py:100-159) + observation assembly (get_state.py)
 // ---------------------------------------------------------------------------------------------------------
-template <typename R>
+template <typename R, bool FAST>
 __device__ __forceinline__ void rot2quat(const R* r, R* q) {            // sensor_noise.py:26-55
   R tr = r[0] + r[4] + r[8];
   if (tr > R(0)) {
+    if (FAST && sizeof(R) == 4) {                                       // the common branch: 1/S by MUFU.RSQ
+      R t = tr + R(1);
+      R is = q_rsqrt<R, true>(t);                                       // S = 2 sqrt(t), 1/S = is/2
+      R h = R(0.5) * is;
+      q[0] = R(0.5) * (t * is); q[1] = (r[7] - r[5]) * h; q[2] = (r[2] - r[6]) * h; q[3] = (r[3] - r[1]) * h;
+      return;
+    }
     R S = Mth<R>::sqrt(tr + R(1)) * R(2);
     q[0] = R(0.25) * S; q[1] = (r[7] - r[5]) / S; q[2] = (r[2] - r[6]) / S; q[3] = (r[3] - r[1]) / S;
   } else if (r[0] > r[4] && r[0] > r[8]) {
@@ -704,7 +753,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     }
     // rotation: R -> quaternion -> (x small-angle quaternion) -> R (:134-147); a pure round trip by default
     R q[4];
-    rot2quat(s.r, q);
+    rot2quat<R, !T::RARE>(s.r, q);
     if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) {
       R zn[3], zu[3];
       ns.obs3(reset_obs, 6, false, zn);
@@ -1100,8 +1149,13 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
   const int obs_tile_floats = BLOCK * p.obs_dim;
   const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
 
-  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
-  __syncthreads();
+  // A CTA that owns a single tile (small N: one wave) never touches the async machinery: its tile is read with
+  // plain vector loads, which have the lowest latency.  Only CTAs that walk several tiles set up the pipeline.
+  const bool multi = (long long)blockIdx.x + gridDim.x < n_tiles;
+  if (multi) {
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    __syncthreads();
+  }
 
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
@@ -1119,11 +1173,9 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     if (has_act) bulk_g2s(dst + rows_in * BLOCK, p.actions + first * 4, bytes, &bar[stage]);
   };
 
-  long long tile = blockIdx.x;
-  if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
-
+  uint32_t phase0 = 0, phase1 = 0;                                       // mbarrier phase parity per stage
   int j = 0;
-  for (; tile < n_tiles; tile += gridDim.x, ++j) {
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
     const int stage = j & 1;
     const long long next = tile + gridDim.x;
     if (tid == 0 && next < n_tiles) issue_load(next, stage ^ 1);         // prefetch: a whole iteration to land
@@ -1131,23 +1183,29 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     const long long i = block_first + tid;
     const bool active = i < p.end;
 
-    mbar_wait(&bar[stage], (uint32_t)((j >> 1) & 1));
-    const float4* buf = in + (size_t)stage * stage_vecs + tid;
     St<R> s;
-    if (active) {
-      unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
-    } else {
-      default_core(s);
-    }
-    init_optional(s, p);
     R a0[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-      const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
-      if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
-      if (p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
-      if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
+    if (j == 0) {
+      // first tile of the CTA: direct loads (nothing was prefetched yet)
+      load_state<R, T>(s, p, i, active);
+      if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
+    } else {
+      if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1u; }
+      const float4* buf = in + (size_t)stage * stage_vecs + tid;
+      if (active) {
+        unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
+      } else {
+        default_core(s);
+      }
+      init_optional(s, p);
+      if (active) {
+        const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+        if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
+        if (p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+        if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
+      }
+      finish_load(s);
     }
-    finish_load(s);
 
     R o[26];
     StepOut<R> out;
@@ -1161,18 +1219,21 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       p.done[i] = out.done_any ? 1 : 0;
       obs_to_tile(p, o, tile_obs + tid * p.obs_dim);
     }
-    // the bulk store issued one iteration ago must have drained the OTHER obs tile before anybody rewrites it in
-    // the next iteration; it has had a whole iteration to do so
-    if (tid == 0) bulk_wait_read0();
-    fence_proxy_async();                                                // generic-proxy tile writes -> async proxy
-    const bool any = __syncthreads_or(out.done_any ? 1 : 0);
     long long rows = p.end - block_first;
     if (rows > BLOCK) rows = BLOCK;
     const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
-    if ((obs_bytes & 15u) == 0u) {
+    const bool bulk_out = multi && (obs_bytes & 15u) == 0u;
+    if (multi) {
+      // the bulk store issued one iteration ago must have drained the OTHER obs tile before anybody rewrites it
+      // in the next iteration; it has had a whole iteration to do so
+      if (tid == 0) bulk_wait_read0();
+      fence_proxy_async();                                              // generic-proxy tile writes -> async proxy
+    }
+    const bool any = __syncthreads_or(out.done_any ? 1 : 0);
+    if (bulk_out) {
       if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
     } else {
-      flush_tile(p, tile_obs, block_first, nullptr);                    // ragged last tile
+      flush_tile(p, tile_obs, block_first, nullptr);                    // single-tile CTA, or ragged last tile
     }
     if (any) block_stats(p, red, out.st_ret, out.st_ret2, out.st_n);
   }
