@@ -66,6 +66,7 @@ struct Params {
   int dyn_controller, dyn_substeps;   // qs_dynamics_step
   int inject, need_rare;              // variant selection (host)
   int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
+  long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
   // model
   R dt;
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
@@ -321,9 +322,15 @@ __device__ __forceinline__ void finish_load(St<R>& s) {
 template <typename R, class T>
 __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long long i, bool active) {
   if (active) {
-    V4<R> q0 = ld4(p.state, p.n, 0, i), q1 = ld4(p.state, p.n, 1, i), q2 = ld4(p.state, p.n, 2, i);
-    V4<R> q3 = ld4(p.state, p.n, 3, i), q4 = ld4(p.state, p.n, 4, i), q5 = ld4(p.state, p.n, 5, i);
-    V4<R> q6 = ld4(p.state, p.n, 6, i);
+    const char* ptr = reinterpret_cast<const char*>(p.state + i * 4);   // row 0; rows are row_bytes apart
+    const long long rb = p.row_bytes;
+    V4<R> q0 = *reinterpret_cast<const V4<R>*>(ptr); ptr += rb;
+    V4<R> q1 = *reinterpret_cast<const V4<R>*>(ptr); ptr += rb;
+    V4<R> q2 = *reinterpret_cast<const V4<R>*>(ptr); ptr += rb;
+    V4<R> q3 = *reinterpret_cast<const V4<R>*>(ptr); ptr += rb;
+    V4<R> q4 = *reinterpret_cast<const V4<R>*>(ptr); ptr += rb;
+    V4<R> q5 = *reinterpret_cast<const V4<R>*>(ptr); ptr += rb;
+    V4<R> q6 = *reinterpret_cast<const V4<R>*>(ptr);
     unpack_core(s, q0, q1, q2, q3, q4, q5, q6);
   } else {
     default_core(s);
@@ -341,15 +348,23 @@ __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long lo
   finish_load(s);
 }
 
+template <typename R> __device__ __forceinline__ void st4p(char*& ptr, long long stride, R x, R y, R z, R w) {
+  V4<R> v; v.x = x; v.y = y; v.z = z; v.w = w;
+  *reinterpret_cast<V4<R>*>(ptr) = v;
+  ptr += stride;
+}
+
 template <typename R, class T>
 __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, long long i) {
-  st4(p.state, p.n, 0, i, s.px, s.py, s.pz, s.vx);
-  st4(p.state, p.n, 1, i, s.vy, s.vz, s.wx, s.wy);
-  st4(p.state, p.n, 2, i, s.wz, s.r[0], s.r[1], s.r[2]);
-  st4(p.state, p.n, 3, i, s.r[3], s.r[4], s.r[5], s.r[6]);
-  st4(p.state, p.n, 4, i, s.r[7], s.r[8], s.tick, s.ret);
-  st4(p.state, p.n, 5, i, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
-  st4(p.state, p.n, 6, i, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
+  char* ptr = reinterpret_cast<char*>(p.state + i * 4);                 // row 0; rows are row_bytes apart
+  const long long rb = p.row_bytes;
+  st4p(ptr, rb, s.px, s.py, s.pz, s.vx);
+  st4p(ptr, rb, s.vy, s.vz, s.wx, s.wy);
+  st4p(ptr, rb, s.wz, s.r[0], s.r[1], s.r[2]);
+  st4p(ptr, rb, s.r[3], s.r[4], s.r[5], s.r[6]);
+  st4p(ptr, rb, s.r[7], s.r[8], s.tick, s.ret);
+  st4p(ptr, rb, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
+  st4p(ptr, rb, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (ou_on) st4(p.state, p.n, p.row_ou, i, s.ou[0], s.ou[1], s.ou[2], s.ou[3]);
   if (p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
@@ -1132,78 +1147,96 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 constexpr int TMA_MIN_CTAS = 4;   // resident CTAs per SM the fast kernel is tuned for (registers <= 128)
+constexpr int WARPS = BLOCK / 32;
 
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// warp-level finished-episode statistics: shuffle reduce + one double atomic triple per warp (rare: episode ends)
+template <typename R>
+__device__ __forceinline__ void warp_stats(const Params<R>& p, double st_ret, double st_ret2, double st_n) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    st_ret += __shfl_down_sync(0xffffffffu, st_ret, off);
+    st_ret2 += __shfl_down_sync(0xffffffffu, st_ret2, off);
+    st_n += __shfl_down_sync(0xffffffffu, st_n, off);
+  }
+  if ((threadIdx.x & 31) == 0 && st_n > 0) { atomicAdd(&p.stats[0], st_ret); atomicAdd(&p.stats[1], st_ret2); atomicAdd(&p.stats[2], st_n); }
+}
+
+// Every WARP runs its own pipeline over tiles of 32 envs (stride = warps in the grid): there is no CTA-wide barrier
+// inside the loop, so a warp never waits for its neighbours.
+//   * lane 0 prefetches the warp's NEXT tile - every state row and the action row are contiguous 512-byte runs of the
+//     structure-of-arrays layout - with cp.async.bulk into the warp's other shared-memory stage, completion counted
+//     on a per-warp mbarrier, while the warp computes the current tile;
+//   * a warp that owns a single tile (small N: one wave) skips the async machinery and reads with plain vector loads;
+//   * the state goes back to HBM straight from registers (coalesced 16-byte stores); the observation rows are
+//     transposed through the warp's shared tile and leave as one cp.async.bulk store.
 template <class T>
 __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   typedef float R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bar[2];
-  __shared__ double red[3][BLOCK / 32];
+  __shared__ __align__(8) unsigned long long bars[WARPS][2];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
   const bool has_act = p.actions != nullptr;
-  const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
-  float4* in = reinterpret_cast<float4*>(smem_raw);
-  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4));
-  const int obs_tile_floats = BLOCK * p.obs_dim;
-  const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
+  const int stage_vecs = (rows_in + 1) * 32;                             // float4 slots per warp stage, last row = actions
+  const int obs_tile_floats = 32 * p.obs_dim;
+  float4* in = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * 2 * stage_vecs;
+  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)WARPS * 2 * stage_vecs * sizeof(float4)) +
+                     (size_t)warp * 2 * obs_tile_floats;
+  unsigned long long* bar = bars[warp];
 
-  // A CTA that owns a single tile (small N: one wave) never touches the async machinery: its tile is read with
-  // plain vector loads, which have the lowest latency.  Only CTAs that walk several tiles set up the pipeline.
-  const bool multi = (long long)blockIdx.x + gridDim.x < n_tiles;
+  const long long n_wtiles = (p.end - p.begin + 31) / 32;
+  const long long wstride = (long long)gridDim.x * WARPS;
+  const long long wt0 = (long long)blockIdx.x * WARPS + warp;
+  const bool multi = wt0 + wstride < n_wtiles;
   if (multi) {
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
-    __syncthreads();
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    __syncwarp();
   }
 
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
   double svd_end = svd_t0;
 
-  auto issue_load = [&](long long tile, int stage) {
-    const long long first = p.begin + tile * BLOCK;
+  auto issue_load = [&](long long wt, int stage) {
+    const long long first = p.begin + wt * 32;
     long long rows = p.end - first;
-    if (rows > BLOCK) rows = BLOCK;
+    if (rows > 32) rows = 32;
     const uint32_t bytes = (uint32_t)rows * 16u;
     mbar_expect_tx(&bar[stage], bytes * (uint32_t)(rows_in + (has_act ? 1 : 0)));
     float4* dst = in + (size_t)stage * stage_vecs;
-    const float* src = p.state + first * 4;
-    for (int r = 0; r < rows_in; ++r) bulk_g2s(dst + r * BLOCK, src + (long long)r * p.n * 4, bytes, &bar[stage]);
-    if (has_act) bulk_g2s(dst + rows_in * BLOCK, p.actions + first * 4, bytes, &bar[stage]);
+    const char* src = reinterpret_cast<const char*>(p.state + first * 4);
+    for (int r = 0; r < rows_in; ++r) { bulk_g2s(dst + r * 32, src, bytes, &bar[stage]); src += p.row_bytes; }
+    if (has_act) bulk_g2s(dst + rows_in * 32, p.actions + first * 4, bytes, &bar[stage]);
   };
 
   uint32_t phase0 = 0, phase1 = 0;                                       // mbarrier phase parity per stage
   int j = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+  for (long long wt = wt0; wt < n_wtiles; wt += wstride, ++j) {
     const int stage = j & 1;
-    const long long next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) issue_load(next, stage ^ 1);         // prefetch: a whole iteration to land
-    const long long block_first = p.begin + tile * BLOCK;
-    const long long i = block_first + tid;
+    const long long first = p.begin + wt * 32;
+    const long long i = first + lane;
     const bool active = i < p.end;
+    if (lane == 0 && wt + wstride < n_wtiles) issue_load(wt + wstride, stage ^ 1);   // a whole iteration to land
 
     St<R> s;
     R a0[4] = {0.f, 0.f, 0.f, 0.f};
     if (j == 0) {
-      // first tile of the CTA: direct loads (nothing was prefetched yet)
+      // first tile of the warp: direct loads (nothing was prefetched yet)
       load_state<R, T>(s, p, i, active);
       if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
     } else {
       if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1u; }
-      const float4* buf = in + (size_t)stage * stage_vecs + tid;
-      if (active) {
-        unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
-      } else {
-        default_core(s);
-      }
+      // lanes beyond the last env of a ragged tile read stale shared memory: harmless, nothing of theirs is stored
+      const float4* buf = in + (size_t)stage * stage_vecs + lane;
+      unpack_core(s, buf[0 * 32], buf[1 * 32], buf[2 * 32], buf[3 * 32], buf[4 * 32], buf[5 * 32], buf[6 * 32]);
       init_optional(s, p);
-      if (active) {
-        const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
-        if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
-        if (p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
-        if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
-      }
+      const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+      if (ou_on) { float4 q = buf[p.row_ou * 32]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
+      if (p.row_act >= 0) { float4 q = buf[p.row_act * 32]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+      if (has_act) { float4 q = buf[rows_in * 32]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
       finish_load(s);
     }
 
@@ -1212,32 +1245,32 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out);
     svd_end = out.svd_t;
 
-    float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
     if (active) {
       store_state<R, T>(s, p, i);
       p.rew[i] = out.rew_sum;
       p.done[i] = out.done_any ? 1 : 0;
-      obs_to_tile(p, o, tile_obs + tid * p.obs_dim);
     }
-    long long rows = p.end - block_first;
-    if (rows > BLOCK) rows = BLOCK;
+    // observation rows: registers -> the warp's shared tile -> one bulk store
+    float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
+    if (lane == 0) bulk_wait_read1();            // the store issued two tiles ago has drained this tile
+    __syncwarp();
+    obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
+    fence_proxy_async();                         // generic-proxy tile writes -> async proxy
+    __syncwarp();
+    long long rows = p.end - first;
+    if (rows > 32) rows = 32;
     const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
-    const bool bulk_out = multi && (obs_bytes & 15u) == 0u;
-    if (multi) {
-      // the bulk store issued one iteration ago must have drained the OTHER obs tile before anybody rewrites it
-      // in the next iteration; it has had a whole iteration to do so
-      if (tid == 0) bulk_wait_read0();
-      fence_proxy_async();                                              // generic-proxy tile writes -> async proxy
+    if ((obs_bytes & 15u) == 0u) {
+      if (lane == 0) { bulk_s2g(p.obs + first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
+    } else {                                     // ragged last tile
+      float* dst = p.obs + first * p.obs_dim;
+      for (int k = lane; k < (int)rows * p.obs_dim; k += 32) dst[k] = tile_obs[k];
+      __syncwarp();
     }
-    const bool any = __syncthreads_or(out.done_any ? 1 : 0);
-    if (bulk_out) {
-      if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
-    } else {
-      flush_tile(p, tile_obs, block_first, nullptr);                    // single-tile CTA, or ragged last tile
-    }
-    if (any) block_stats(p, red, out.st_ret, out.st_ret2, out.st_n);
+    if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
   }
-  if (tid == 0) bulk_wait_read0();                                      // shared memory must outlive the bulk stores
+  if (lane == 0) bulk_wait_read0();              // shared memory must outlive the bulk stores
+  __syncthreads();                               // every thread of the CTA has read the clock
   finish_clock(p, svd_end, (unsigned long long)p.k_steps);
 }
 

@@ -149,6 +149,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.inject = (c.noise_mode == QS_NOISE_INJECTED) ? 1 : 0;
   p.need_rare = need_rare(h) ? 1 : 0;
   p.tma_rows = h->lay.rows;
+  p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
