@@ -1163,81 +1163,95 @@ __device__ __forceinline__ void warp_stats(const Params<R>& p, double st_ret, do
   if ((threadIdx.x & 31) == 0 && st_n > 0) { atomicAdd(&p.stats[0], st_ret); atomicAdd(&p.stats[1], st_ret2); atomicAdd(&p.stats[2], st_n); }
 }
 
-// Every WARP runs its own pipeline over tiles of 32 envs (stride = warps in the grid): there is no CTA-wide barrier
-// inside the loop, so a warp never waits for its neighbours.
-//   * lane 0 prefetches the warp's NEXT tile - every state row and the action row are contiguous 512-byte runs of the
-//     structure-of-arrays layout - with cp.async.bulk into the warp's other shared-memory stage, completion counted
-//     on a per-warp mbarrier, while the warp computes the current tile;
-//   * a warp that owns a single tile (small N: one wave) skips the async machinery and reads with plain vector loads;
-//   * the state goes back to HBM straight from registers (coalesced 16-byte stores); the observation rows are
-//     transposed through the warp's shared tile and leave as one cp.async.bulk store.
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent CTAs walk tiles of 128 envs (stride gridDim.x) through a two-stage full/empty mbarrier pipeline:
+//   * producer = thread 0: fetches the NEXT tile - every state row and the action row are contiguous 2 KB runs of the
+//     structure-of-arrays layout - with cp.async.bulk into the other shared-memory stage (completion counted on the
+//     stage's `full` barrier) while the CTA computes the current tile, so HBM read latency never sits on a warp's
+//     scoreboard; it reuses a stage only after all four warps have released it on the stage's `empty` barrier;
+//   * consumers = all four warps, loosely coupled: there is no CTA-wide barrier per tile, a warp only waits for data;
+//   * a CTA that owns a single tile (small N: one wave) skips the async machinery and uses plain vector loads;
+//   * the state goes back to HBM straight from registers (coalesced 16-byte stores); each warp transposes its 32
+//     observation rows through its own shared tile and ships them as one cp.async.bulk store.
 template <class T>
 __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   typedef float R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[WARPS][2];
+  __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
   const bool has_act = p.actions != nullptr;
-  const int stage_vecs = (rows_in + 1) * 32;                             // float4 slots per warp stage, last row = actions
-  const int obs_tile_floats = 32 * p.obs_dim;
-  float4* in = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * 2 * stage_vecs;
-  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)WARPS * 2 * stage_vecs * sizeof(float4)) +
+  const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
+  const int obs_tile_floats = 32 * p.obs_dim;                            // per warp, per stage
+  float4* in = reinterpret_cast<float4*>(smem_raw);
+  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4)) +
                      (size_t)warp * 2 * obs_tile_floats;
-  unsigned long long* bar = bars[warp];
+  const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
 
-  const long long n_wtiles = (p.end - p.begin + 31) / 32;
-  const long long wstride = (long long)gridDim.x * WARPS;
-  const long long wt0 = (long long)blockIdx.x * WARPS + warp;
-  const bool multi = wt0 + wstride < n_wtiles;
+  const bool multi = (long long)blockIdx.x + gridDim.x < n_tiles;
   if (multi) {
-    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
-    __syncwarp();
+    if (tid == 0) {
+      mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+      mbar_init(&empty_bar[0], WARPS); mbar_init(&empty_bar[1], WARPS);
+      fence_mbar_init();
+    }
+    __syncthreads();
   }
 
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
   double svd_end = svd_t0;
 
-  auto issue_load = [&](long long wt, int stage) {
-    const long long first = p.begin + wt * 32;
+  auto issue_load = [&](long long tile, int stage) {
+    const long long first = p.begin + tile * BLOCK;
     long long rows = p.end - first;
-    if (rows > 32) rows = 32;
+    if (rows > BLOCK) rows = BLOCK;
     const uint32_t bytes = (uint32_t)rows * 16u;
-    mbar_expect_tx(&bar[stage], bytes * (uint32_t)(rows_in + (has_act ? 1 : 0)));
+    mbar_expect_tx(&full_bar[stage], bytes * (uint32_t)(rows_in + (has_act ? 1 : 0)));
     float4* dst = in + (size_t)stage * stage_vecs;
     const char* src = reinterpret_cast<const char*>(p.state + first * 4);
-    for (int r = 0; r < rows_in; ++r) { bulk_g2s(dst + r * 32, src, bytes, &bar[stage]); src += p.row_bytes; }
-    if (has_act) bulk_g2s(dst + rows_in * 32, p.actions + first * 4, bytes, &bar[stage]);
+    for (int r = 0; r < rows_in; ++r) { bulk_g2s(dst + r * BLOCK, src, bytes, &full_bar[stage]); src += p.row_bytes; }
+    if (has_act) bulk_g2s(dst + rows_in * BLOCK, p.actions + first * 4, bytes, &full_bar[stage]);
   };
 
-  uint32_t phase0 = 0, phase1 = 0;                                       // mbarrier phase parity per stage
+  uint32_t full_phase = 0;        // bit s: parity to wait for on full_bar[s]
+  uint32_t empty_phase = 0;       // (producer only) bit s: parity to wait for on empty_bar[s]
   int j = 0;
-  for (long long wt = wt0; wt < n_wtiles; wt += wstride, ++j) {
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
     const int stage = j & 1;
-    const long long first = p.begin + wt * 32;
-    const long long i = first + lane;
+    const long long block_first = p.begin + tile * BLOCK;
+    const long long i = block_first + tid;
     const bool active = i < p.end;
-    if (lane == 0 && wt + wstride < n_wtiles) issue_load(wt + wstride, stage ^ 1);   // a whole iteration to land
+    if (tid == 0 && tile + gridDim.x < n_tiles) {
+      const int ns = stage ^ 1;
+      if (j >= 2) { mbar_wait(&empty_bar[ns], (empty_phase >> ns) & 1u); empty_phase ^= (1u << ns); }
+      issue_load(tile + gridDim.x, ns);                                  // a whole iteration to land
+    }
 
     St<R> s;
     R a0[4] = {0.f, 0.f, 0.f, 0.f};
     if (j == 0) {
-      // first tile of the warp: direct loads (nothing was prefetched yet)
+      // first tile of the CTA: direct loads (nothing was prefetched yet)
       load_state<R, T>(s, p, i, active);
       if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
     } else {
-      if (stage == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1u; }
+      mbar_wait(&full_bar[stage], (full_phase >> stage) & 1u);
+      full_phase ^= (1u << stage);
       // lanes beyond the last env of a ragged tile read stale shared memory: harmless, nothing of theirs is stored
-      const float4* buf = in + (size_t)stage * stage_vecs + lane;
-      unpack_core(s, buf[0 * 32], buf[1 * 32], buf[2 * 32], buf[3 * 32], buf[4 * 32], buf[5 * 32], buf[6 * 32]);
+      const float4* buf = in + (size_t)stage * stage_vecs + tid;
+      unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
       init_optional(s, p);
       const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
-      if (ou_on) { float4 q = buf[p.row_ou * 32]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
-      if (p.row_act >= 0) { float4 q = buf[p.row_act * 32]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
-      if (has_act) { float4 q = buf[rows_in * 32]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
+      if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
+      if (p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+      if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
       finish_load(s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);                     // this warp is done with the stage
     }
 
     R o[26];
@@ -1250,22 +1264,24 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       p.rew[i] = out.rew_sum;
       p.done[i] = out.done_any ? 1 : 0;
     }
-    // observation rows: registers -> the warp's shared tile -> one bulk store
+    // observation rows: registers -> the warp's shared tile -> one bulk store per warp
     float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
     if (lane == 0) bulk_wait_read1();            // the store issued two tiles ago has drained this tile
     __syncwarp();
     obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
     fence_proxy_async();                         // generic-proxy tile writes -> async proxy
     __syncwarp();
-    long long rows = p.end - first;
+    const long long wfirst = block_first + warp * 32;
+    long long rows = p.end - wfirst;
     if (rows > 32) rows = 32;
-    const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
-    if ((obs_bytes & 15u) == 0u) {
-      if (lane == 0) { bulk_s2g(p.obs + first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
-    } else {                                     // ragged last tile
-      float* dst = p.obs + first * p.obs_dim;
-      for (int k = lane; k < (int)rows * p.obs_dim; k += 32) dst[k] = tile_obs[k];
-      __syncwarp();
+    if (rows > 0) {
+      const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
+      if ((obs_bytes & 15u) == 0u) {
+        if (lane == 0) { bulk_s2g(p.obs + wfirst * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
+      } else {                                   // ragged last tile
+        float* dst = p.obs + wfirst * p.obs_dim;
+        for (int k = lane; k < (int)rows * p.obs_dim; k += 32) dst[k] = tile_obs[k];
+      }
     }
     if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
   }
