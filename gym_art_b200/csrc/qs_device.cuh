@@ -67,6 +67,7 @@ struct Params {
   int inject, need_rare;              // variant selection (host)
   int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
   long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
+  int tile_sync;                      // TMA kernel: re-couple the CTA's warps with one barrier per tile (DRAM locality)
   // model
   R dt;
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
@@ -132,13 +133,17 @@ template <> struct Mth<float> {
   static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ bool finite(float x) { return isfinite(x); }
+  // raw MUFU forms: no denormal pre/post-scaling (callers guarantee normal, positive arguments)
+  static __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   // Box-Muller pair from two 32-bit words (Philox mode only; distribution parity, not bit parity)
   static __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float* z0, float* z1) {
-    float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-08f;   // (0, 1]
-    float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;          // [0, 1)
-    float r = sqrtf(-2.0f * __logf(u1));
+    float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-08f;   // (0, 1], never denormal
+    float t = lg2_ftz(u1) * -1.3862943611198906f;                  // -2 ln(u1) >= 0
+    float r = t * rsqrt_ftz(fmaxf(t, 1e-30f));                     // sqrt(t), exact 0 at t == 0
+    float ang = (float)(b >> 8) * 3.7450704e-07f;                  // 2 pi * 2^-24 * [0, 2^24)
     float s, c;
-    __sincosf(6.283185307179586f * u2, &s, &c);
+    __sincosf(ang, &s, &c);
     *z0 = r * c;
     *z1 = r * s;
   }
@@ -170,11 +175,11 @@ template <typename R> __device__ __forceinline__ R clampr(R x, R lo, R hi) { ret
 // Fast fp32 forms used by the throughput variants (Traits::RARE == false): MUFU.RSQ / MUFU.RCP based, ~2 ulp, no
 // denormal / special-case branches.  The per-step parity tests run these same variants (injected-noise twins).
 template <typename R, bool FAST> __device__ __forceinline__ R q_rsqrt(R x) {
-  if (FAST && sizeof(R) == 4) return (R)rsqrtf((float)x);
+  if (FAST && sizeof(R) == 4) return (R)Mth<float>::rsqrt_ftz((float)x);   // callers pass normal positive values
   return R(1) / Mth<R>::sqrt(x);
 }
 template <typename R, bool FAST> __device__ __forceinline__ R q_sqrt(R x) {       // x >= 0
-  if (FAST && sizeof(R) == 4) { float xf = (float)x; return (R)(xf * rsqrtf(fmaxf(xf, 1e-30f))); }
+  if (FAST && sizeof(R) == 4) { float xf = (float)x; return (R)(xf * Mth<float>::rsqrt_ftz(fmaxf(xf, 1e-30f))); }
   return Mth<R>::sqrt(x);
 }
 template <typename R, bool FAST> __device__ __forceinline__ R q_rcp(R x) {
@@ -410,7 +415,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     s.rd[k] = tau * (rt - s.rd[k]) + s.rd[k];                           // :295
     R cd = s.rd[k] * s.rd[k];                                           // :296
     if (ou_on) {
-      s.ou[k] = s.ou[k] + (p.ou_theta * (R(0) - s.ou[k]) + p.ou_sigma * z[k]);   // quad_utils.py:197-201
+      s.ou[k] = s.ou[k] + (p.ou_theta * (-s.ou[k]) + p.ou_sigma * z[k]);   // quad_utils.py:197-201 (mu = 0)
       cd = cd + c * s.ou[k];                                            // :299
     }
     cd = clampr(cd, R(0), R(1));                                        // :300
@@ -462,7 +467,9 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     R oy = s.r[3] * s.wx + s.r[4] * s.wy + s.r[5] * s.wz;
     R oz = s.r[6] * s.wx + s.r[7] * s.wy + s.r[8] * s.wz;
     R on2 = ox * ox + oy * oy + oz * oz;
-    if (on2 != R(0)) {
+    // reference: skipped when |omega| == 0 (:373).  The fast form needs no branch: with omega == 0 the axis is the
+    // zero vector and the half angle is 0, so dR is exactly the identity and R comes out bit-identical.
+    if ((!T::RARE && sizeof(R) == 4) || on2 != R(0)) {
       R inv, on;
       if (!T::RARE && sizeof(R) == 4) { inv = q_rsqrt<R, true>(Mth<R>::max(on2, R(1e-30))); on = on2 * inv; }
       else { on = Mth<R>::sqrt(on2); inv = R(1) / on; }
@@ -1284,6 +1291,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       }
     }
     if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
+    if (p.tile_sync) __syncthreads();            // keeps the four warps' 512-byte row segments adjacent in time
   }
   if (lane == 0) bulk_wait_read0();              // shared memory must outlive the bulk stores
   __syncthreads();                               // every thread of the CTA has read the clock

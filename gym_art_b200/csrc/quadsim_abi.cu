@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -34,6 +35,7 @@ struct QsHandle {
   qs::Clock* d_clock;        // device-resident {svd_timer, step}: steps stay CUDA-graph capturable
   unsigned int* d_ticket;
   uint64_t launches;
+  int tile_sync;
   std::string err;
   const char* last_variant;
   // qs_step_host scratch (library-owned)
@@ -150,6 +152,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.need_rare = need_rare(h) ? 1 : 0;
   p.tma_rows = h->lay.rows;
   p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
+  p.tile_sync = h->tile_sync;
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
@@ -251,6 +254,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->ou_z = h->obs_z = h->reset_z = nullptr;
   h->d_stats = nullptr; h->d_status = nullptr; h->d_clock = nullptr; h->d_ticket = nullptr;
   h->launches = 0;
+  { const char* e = getenv("QUADSIM_TILE_SYNC"); h->tile_sync = e ? atoi(e) : 1; }   // tuning knob, default on
   h->last_variant = "";
   h->host_ready = false;
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
