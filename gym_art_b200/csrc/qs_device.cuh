@@ -1195,8 +1195,8 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
   const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
   const int obs_tile_floats = 32 * p.obs_dim;                            // per warp, per stage
   float4* in = reinterpret_cast<float4*>(smem_raw);
-  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4)) +
-                     (size_t)warp * 2 * obs_tile_floats;
+  // observation staging: [stage][warp][32][obs_dim] == [stage][128][obs_dim]
+  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4));
   const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
 
   const bool multi = (long long)blockIdx.x + gridDim.x < n_tiles;
@@ -1271,27 +1271,44 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       p.rew[i] = out.rew_sum;
       p.done[i] = out.done_any ? 1 : 0;
     }
-    // observation rows: registers -> the warp's shared tile -> one bulk store per warp
-    float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
-    if (lane == 0) bulk_wait_read1();            // the store issued two tiles ago has drained this tile
-    __syncwarp();
-    obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
-    fence_proxy_async();                         // generic-proxy tile writes -> async proxy
-    __syncwarp();
-    const long long wfirst = block_first + warp * 32;
-    long long rows = p.end - wfirst;
-    if (rows > 32) rows = 32;
-    if (rows > 0) {
+    // observation rows: registers -> shared tile -> bulk store (one per CTA, or one per warp when the warps run free)
+    float* tile_obs = obs_tiles + ((size_t)stage * WARPS + warp) * obs_tile_floats;
+    const bool cta_store = p.tile_sync != 0;
+    if (cta_store) {
+      obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
+      fence_proxy_async();                       // generic-proxy tile writes -> async proxy
+      if (tid == 0) bulk_wait_read0();           // last tile's store has drained the OTHER stage (it had a whole tile)
+      __syncthreads();                           // also keeps the four warps' 512-byte row segments adjacent in time
+      long long rows = p.end - block_first;
+      if (rows > BLOCK) rows = BLOCK;
       const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
+      float* cta_tile = obs_tiles + (size_t)stage * WARPS * obs_tile_floats;
       if ((obs_bytes & 15u) == 0u) {
-        if (lane == 0) { bulk_s2g(p.obs + wfirst * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
+        if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, cta_tile, obs_bytes); bulk_commit(); }
       } else {                                   // ragged last tile
-        float* dst = p.obs + wfirst * p.obs_dim;
-        for (int k = lane; k < (int)rows * p.obs_dim; k += 32) dst[k] = tile_obs[k];
+        float* dst = p.obs + block_first * p.obs_dim;
+        for (int k = tid; k < (int)rows * p.obs_dim; k += BLOCK) dst[k] = cta_tile[k];
+      }
+    } else {
+      if (lane == 0) bulk_wait_read1();          // the store issued two tiles ago has drained this tile
+      __syncwarp();
+      obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
+      fence_proxy_async();
+      __syncwarp();
+      const long long wfirst = block_first + warp * 32;
+      long long rows = p.end - wfirst;
+      if (rows > 32) rows = 32;
+      if (rows > 0) {
+        const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
+        if ((obs_bytes & 15u) == 0u) {
+          if (lane == 0) { bulk_s2g(p.obs + wfirst * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
+        } else {                                 // ragged last tile
+          float* dst = p.obs + wfirst * p.obs_dim;
+          for (int k = lane; k < (int)rows * p.obs_dim; k += 32) dst[k] = tile_obs[k];
+        }
       }
     }
     if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
-    if (p.tile_sync) __syncthreads();            // keeps the four warps' 512-byte row segments adjacent in time
   }
   if (lane == 0) bulk_wait_read0();              // shared memory must outlive the bulk stores
   __syncthreads();                               // every thread of the CTA has read the clock
