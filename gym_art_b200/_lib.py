@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libquadsim.so")
+LIB_PATH = os.environ.get("QUADSIM_LIB") or os.path.join(HERE, "libquadsim.so")   # override: A/B builds only
 
 QS_ABI_VERSION = 4
 QS_OK, QS_EINVAL, QS_ECUDA, QS_ENONFINITE, QS_ESTATE, QS_EUNSUPPORTED, QS_EABI = 0, -1, -2, -3, -4, -5, -6

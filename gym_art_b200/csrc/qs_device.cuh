@@ -361,6 +361,15 @@ template <typename R> __device__ __forceinline__ void st4p(char*& ptr, long long
 
 template <typename R, class T>
 __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, long long i) {
+#ifdef QS_EXP_OLD_ADDR
+  st4(p.state, p.n, 0, i, s.px, s.py, s.pz, s.vx);
+  st4(p.state, p.n, 1, i, s.vy, s.vz, s.wx, s.wy);
+  st4(p.state, p.n, 2, i, s.wz, s.r[0], s.r[1], s.r[2]);
+  st4(p.state, p.n, 3, i, s.r[3], s.r[4], s.r[5], s.r[6]);
+  st4(p.state, p.n, 4, i, s.r[7], s.r[8], s.tick, s.ret);
+  st4(p.state, p.n, 5, i, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
+  st4(p.state, p.n, 6, i, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
+#else
   char* ptr = reinterpret_cast<char*>(p.state + i * 4);                 // row 0; rows are row_bytes apart
   const long long rb = p.row_bytes;
   st4p(ptr, rb, s.px, s.py, s.pz, s.vx);
@@ -370,6 +379,7 @@ __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, 
   st4p(ptr, rb, s.r[7], s.r[8], s.tick, s.ret);
   st4p(ptr, rb, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
   st4p(ptr, rb, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
+#endif
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (ou_on) st4(p.state, p.n, p.row_ou, i, s.ou[0], s.ou[1], s.ou[2], s.ou[3]);
   if (p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
@@ -1227,17 +1237,21 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
 
   uint32_t full_phase = 0;        // bit s: parity to wait for on full_bar[s]
   uint32_t empty_phase = 0;       // (producer only) bit s: parity to wait for on empty_bar[s]
+  // Tile j of this CTA lives in stage j & 1 (j >= 1; tile 0 is read directly).  A stage is free again as soon as the
+  // four warps have copied their slices into registers, i.e. at the START of the tile's compute phase, so the
+  // producer refills it right away with tile j + 2: two tiles (2 x 18 KB per CTA) are in flight during every compute
+  // phase, which is what keeps enough bytes outstanding per SM to cover the HBM latency at full bandwidth.
+  const long long G = gridDim.x;
+  if (multi && tid == 0) {
+    issue_load(blockIdx.x + G, 1);
+    if ((long long)blockIdx.x + 2 * G < n_tiles) issue_load(blockIdx.x + 2 * G, 0);
+  }
   int j = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += G, ++j) {
     const int stage = j & 1;
     const long long block_first = p.begin + tile * BLOCK;
     const long long i = block_first + tid;
     const bool active = i < p.end;
-    if (tid == 0 && tile + gridDim.x < n_tiles) {
-      const int ns = stage ^ 1;
-      if (j >= 2) { mbar_wait(&empty_bar[ns], (empty_phase >> ns) & 1u); empty_phase ^= (1u << ns); }
-      issue_load(tile + gridDim.x, ns);                                  // a whole iteration to land
-    }
 
     St<R> s;
     R a0[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1259,6 +1273,11 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       finish_load(s);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);                     // this warp is done with the stage
+      if (tid == 0 && tile + 2 * G < n_tiles) {
+        mbar_wait(&empty_bar[stage], (empty_phase >> stage) & 1u);       // all four warps have drained it
+        empty_phase ^= (1u << stage);
+        issue_load(tile + 2 * G, stage);
+      }
     }
 
     R o[26];

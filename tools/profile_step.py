@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg4"])
+    ap.add_argument("--copy", action="store_true")
     a = ap.parse_args()
     kw = dict(device="cuda:0", ep_time=5, seed=1)
     if a.config == "cfg2":
@@ -27,6 +28,17 @@ def main():
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="mellinger", **kw)
     else:
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", n_agents=8, **kw)
+    # same-run yardstick: STREAM-style copy bandwidth of this very GPU (method of MEASURED_PEAKS.json)
+    if a.copy:
+        x = torch.empty(1 << 30, dtype=torch.bfloat16, device="cuda:0")
+        y = torch.empty_like(x)
+        best = 0.0
+        for _ in range(10):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); y.copy_(x); c1.record(); torch.cuda.synchronize()
+            best = max(best, 2 * x.numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+        print("copy bandwidth on this GPU: %.0f GB/s" % best)
+        del x, y
     env.reset()
     act = torch.rand((a.envs, env.act_dim), device="cuda:0") * 2 - 1
     if a.config == "cfg3":
