@@ -55,6 +55,8 @@ struct Params {
   double svd_period, dt_d;
   Clock* clock;             // device-resident global clock (read by every CTA, advanced by the last one)
   unsigned int* clock_ticket;
+  unsigned int* tile_counter;  // dynamic tile scheduler of the TMA kernel (zero between launches)
+  unsigned int* launch_ticket; // per-launch-slot ticket (the host pipeline runs several chunk launches concurrently)
   int clock_advance;        // 0: read only (chunked host pipeline advances it with clock_advance_kernel)
   // layout / config
   int row_ou, row_act, row_gyro, row_goal;
@@ -94,6 +96,11 @@ struct Traits {
   static constexpr int OU = OU_;
   static constexpr int SENSE = SENSE_;
   static constexpr bool INJECT = INJECT_;
+#ifdef QS_EXP_NO_FASTM
+  static constexpr bool FASTM = false;
+#else
+  static constexpr bool FASTM = !RARE_; // MUFU-based sqrt / rsqrt / small-angle sincos forms (fp32 fast subset only)
+#endif
   static constexpr bool RARE = RARE_;   // drag/roll, linearity != 1, damping, uniform/quaternion/gyro-bias noise,
                                         // log reward, swarm, dim_mode != 3, per-env goal, info buffer
 };
@@ -116,6 +123,20 @@ __device__ __forceinline__ void finish_clock(const Params<R>& p, double svd_t_en
       *p.clock_ticket = 0u;
       p.clock->svd_timer = svd_t_end;
       p.clock->step += steps;
+    }
+  }
+}
+
+// same ticket scheme for launches that must not advance the clock (chunks of the host pipeline) but still have to
+// leave the work counter of the tile scheduler at zero
+template <typename R>
+__device__ __forceinline__ void finish_launch(const Params<R>& p, double svd_t_end, unsigned long long steps) {
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(p.launch_ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *p.launch_ticket = 0u;
+      *p.tile_counter = 0u;
+      if (p.clock_advance) { p.clock->svd_timer = svd_t_end; p.clock->step += steps; }
     }
   }
 }
@@ -421,7 +442,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
   for (int k = 0; k < 4; ++k) {
     R c = clampr(cmd[k], R(0), R(1));                                   // :279
     R tau = (c < s.cd[k]) ? p.tau_down : p.tau_up;                      // :284-288 (tau pre-clipped to 1 on the host)
-    R rt = q_sqrt<R, !T::RARE>(c);                                      // :294
+    R rt = q_sqrt<R, T::FASTM>(c);                                      // :294
     s.rd[k] = tau * (rt - s.rd[k]) + s.rd[k];                           // :295
     R cd = s.rd[k] * s.rd[k];                                           // :296
     if (ou_on) {
@@ -479,14 +500,14 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     R on2 = ox * ox + oy * oy + oz * oz;
     // reference: skipped when |omega| == 0 (:373).  The fast form needs no branch: with omega == 0 the axis is the
     // zero vector and the half angle is 0, so dR is exactly the identity and R comes out bit-identical.
-    if ((!T::RARE && sizeof(R) == 4) || on2 != R(0)) {
+    if ((T::FASTM && sizeof(R) == 4) || on2 != R(0)) {
       R inv, on;
-      if (!T::RARE && sizeof(R) == 4) { inv = q_rsqrt<R, true>(Mth<R>::max(on2, R(1e-30))); on = on2 * inv; }
+      if (T::FASTM && sizeof(R) == 4) { inv = q_rsqrt<R, true>(Mth<R>::max(on2, R(1e-30))); on = on2 * inv; }
       else { on = Mth<R>::sqrt(on2); inv = R(1) / on; }
       R kx = ox * inv, ky = oy * inv, kz = oz * inv;
       // sin(a) and 1 - cos(a) from the half angle: no cancellation for the small per-substep angles
       R sh, ch;
-      q_sincos_small<R, !T::RARE>(R(0.5) * (on * dt), &sh, &ch);
+      q_sincos_small<R, T::FASTM>(R(0.5) * (on * dt), &sh, &ch);
       R sa = R(2) * sh * ch, cm = R(2) * sh * sh;
       R kxx = kx * kx, kyy = ky * ky, kzz = kz * kz, kxy = kx * ky, kxz = kx * kz, kyz = ky * kz;
       R d00 = R(1) - cm * (kyy + kzz), d01 = cm * kxy - sa * kz, d02 = cm * kxz + sa * ky;
@@ -645,7 +666,7 @@ __device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>&
     R acc_des = R(9.81) * (a[0] + R(1));
     jinv_mix(p, acc_des, dwx, dwy, dwz, cmd);
   } else {
-    attitude_controller<R, !T::RARE>(s, p, ctrl == CTRL_MELLINGER, a, cmd);
+    attitude_controller<R, T::FASTM>(s, p, ctrl == CTRL_MELLINGER, a, cmd);
   }
 }
 
@@ -656,11 +677,11 @@ template <typename R, class T>
 __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, const R* a, const R* a_prev,
                                             bool crashed, bool collided, R* costs) {
   R dx = s.gx - s.px, dy = s.gy - s.py, dz = s.gz - s.pz;
-  R dist = q_sqrt<R, !T::RARE>(dx * dx + dy * dy + dz * dz);
+  R dist = q_sqrt<R, T::FASTM>(dx * dx + dy * dy + dz * dz);
   R c_pos;
   if (T::RARE && p.log_pos) c_pos = p.c_pos * (p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist);
   else c_pos = p.c_pos * dist;                                          // :547-549
-  R c_eff = p.c_effort * q_sqrt<R, !T::RARE>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
+  R c_eff = p.c_effort * q_sqrt<R, T::FASTM>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
   R c_ac = R(0);
   if (p.c_act_change != R(0)) {                                         // :556-558
     R e0 = a[0] - a_prev[0], e1 = a[1] - a_prev[1], e2 = a[2] - a_prev[2], e3 = a[3] - a_prev[3];
@@ -673,7 +694,7 @@ __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, 
   R c_rot = R(0), c_att = R(0);
   if (p.c_rot != R(0)) c_rot = p.c_rot * Mth<R>::acos(clampr(((s.r[0] + s.r[4] + s.r[8]) - R(1)) / R(2), R(-1), R(1)));
   if (p.c_attitude != R(0)) c_att = p.c_attitude * Mth<R>::acos(clampr(s.r[8], R(-1), R(1)));      // :580-581
-  R c_spin = p.c_spin * q_sqrt<R, !T::RARE>(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);              // :585-586
+  R c_spin = p.c_spin * q_sqrt<R, T::FASTM>(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);              // :585-586
   R c_crash = crashed ? p.c_crash : R(0);                               // :590-591
   R sum = ((c_pos + c_eff) + (c_crash + c_or)) + ((c_yaw + c_rot) + (c_att + c_spin));            // np.sum pairwise
   sum = (sum + c_ac) + c_vel;                                           // :593-604
@@ -785,7 +806,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     }
     // rotation: R -> quaternion -> (x small-angle quaternion) -> R (:134-147); a pure round trip by default
     R q[4];
-    rot2quat<R, !T::RARE>(s.r, q);
+    rot2quat<R, T::FASTM>(s.r, q);
     if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) {
       R zn[3], zu[3];
       ns.obs3(reset_obs, 6, false, zn);
@@ -1098,7 +1119,7 @@ __device__ __forceinline__ void block_stats(const Params<R>& p, double (*red)[BL
 // ---------------------------------------------------------------------------------------------------------
 template <typename R, class T>
 __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__ Params<R> p) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   R* tile = reinterpret_cast<R*>(smem_raw);                             // [BLOCK][obs_dim]
   __shared__ double red[3][BLOCK / 32];
 
@@ -1184,40 +1205,34 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Persistent CTAs walk tiles of 128 envs (stride gridDim.x) through a two-stage full/empty mbarrier pipeline:
-//   * producer = thread 0: fetches the NEXT tile - every state row and the action row are contiguous 2 KB runs of the
-//     structure-of-arrays layout - with cp.async.bulk into the other shared-memory stage (completion counted on the
-//     stage's `full` barrier) while the CTA computes the current tile, so HBM read latency never sits on a warp's
-//     scoreboard; it reuses a stage only after all four warps have released it on the stage's `empty` barrier;
-//   * consumers = all four warps, loosely coupled: there is no CTA-wide barrier per tile, a warp only waits for data;
-//   * a CTA that owns a single tile (small N: one wave) skips the async machinery and uses plain vector loads;
-//   * the state goes back to HBM straight from registers (coalesced 16-byte stores); each warp transposes its 32
-//     observation rows through its own shared tile and ships them as one cp.async.bulk store.
+// Persistent CTAs pull tiles of 128 envs from a device-wide work counter and run them through a two-stage
+// full/empty mbarrier pipeline:
+//   * producer = thread 0: fetches the tile after next - every state row and the action row are contiguous 2 KB runs
+//     of the structure-of-arrays layout - with cp.async.bulk into the stage the four warps have just drained into
+//     registers (completion counted on the stage's `full` barrier, the drain on its `empty` barrier), so two tiles
+//     (2 x 18 KB) are in flight per CTA during every compute phase and HBM latency never sits on a scoreboard;
+//   * tiles are handed out dynamically (atomicAdd on a work counter): when the kernel is bandwidth-bound the SMs do
+//     not progress at the same rate, and a static stride would leave the fast ones idle at the end;
+//   * a launch that fits in one wave (small N) skips the async machinery and uses plain vector loads;
+//   * the state goes back to HBM straight from registers (coalesced 16-byte stores); the CTA transposes its 128
+//     observation rows through shared memory and ships them as one cp.async.bulk store.
 template <class T>
 __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   typedef float R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
+  __shared__ long long tile_slot[2];                                     // tile held by each stage (-1: none)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
   const bool has_act = p.actions != nullptr;
   const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
-  const int obs_tile_floats = 32 * p.obs_dim;                            // per warp, per stage
+  const int obs_tile_floats = BLOCK * p.obs_dim;                         // per stage
   float4* in = reinterpret_cast<float4*>(smem_raw);
-  // observation staging: [stage][warp][32][obs_dim] == [stage][128][obs_dim]
   float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4));
   const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
-
-  const bool multi = (long long)blockIdx.x + gridDim.x < n_tiles;
-  if (multi) {
-    if (tid == 0) {
-      mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
-      mbar_init(&empty_bar[0], WARPS); mbar_init(&empty_bar[1], WARPS);
-      fence_mbar_init();
-    }
-    __syncthreads();
-  }
+  const long long G = gridDim.x;
+  const bool multi = n_tiles > G;                                        // more tiles than resident CTAs
 
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
@@ -1234,20 +1249,33 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     for (int r = 0; r < rows_in; ++r) { bulk_g2s(dst + r * BLOCK, src, bytes, &full_bar[stage]); src += p.row_bytes; }
     if (has_act) bulk_g2s(dst + rows_in * BLOCK, p.actions + first * 4, bytes, &full_bar[stage]);
   };
+  // next unassigned tile (the first G tiles are owned statically: tile b belongs to CTA b)
+  auto fetch_tile = [&]() -> long long {
+    const long long t = (long long)atomicAdd(p.tile_counter, 1u) + G;
+    return t < n_tiles ? t : -1;
+  };
+
+  if (multi) {
+    if (tid == 0) {
+      mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+      mbar_init(&empty_bar[0], WARPS); mbar_init(&empty_bar[1], WARPS);
+      fence_mbar_init();
+      // tile j of this CTA lives in stage j & 1 (tile 0 is read directly): prefetch the next two right away
+      const long long t1 = fetch_tile();
+      tile_slot[1] = t1;
+      if (t1 >= 0) issue_load(t1, 1);
+      const long long t2 = t1 >= 0 ? fetch_tile() : -1;
+      tile_slot[0] = t2;
+      if (t2 >= 0) issue_load(t2, 0);
+    }
+    __syncthreads();
+  }
 
   uint32_t full_phase = 0;        // bit s: parity to wait for on full_bar[s]
   uint32_t empty_phase = 0;       // (producer only) bit s: parity to wait for on empty_bar[s]
-  // Tile j of this CTA lives in stage j & 1 (j >= 1; tile 0 is read directly).  A stage is free again as soon as the
-  // four warps have copied their slices into registers, i.e. at the START of the tile's compute phase, so the
-  // producer refills it right away with tile j + 2: two tiles (2 x 18 KB per CTA) are in flight during every compute
-  // phase, which is what keeps enough bytes outstanding per SM to cover the HBM latency at full bandwidth.
-  const long long G = gridDim.x;
-  if (multi && tid == 0) {
-    issue_load(blockIdx.x + G, 1);
-    if ((long long)blockIdx.x + 2 * G < n_tiles) issue_load(blockIdx.x + 2 * G, 0);
-  }
   int j = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += G, ++j) {
+  long long tile = blockIdx.x;
+  while (tile >= 0) {
     const int stage = j & 1;
     const long long block_first = p.begin + tile * BLOCK;
     const long long i = block_first + tid;
@@ -1273,10 +1301,13 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       finish_load(s);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);                     // this warp is done with the stage
-      if (tid == 0 && tile + 2 * G < n_tiles) {
-        mbar_wait(&empty_bar[stage], (empty_phase >> stage) & 1u);       // all four warps have drained it
+      if (tid == 0) {
+        // refill the stage with the tile after next as soon as all four warps have drained it
+        mbar_wait(&empty_bar[stage], (empty_phase >> stage) & 1u);
         empty_phase ^= (1u << stage);
-        issue_load(tile + 2 * G, stage);
+        const long long t = fetch_tile();
+        tile_slot[stage] = t;                                            // read by everybody two tiles from now
+        if (t >= 0) issue_load(t, stage);
       }
     }
 
@@ -1290,48 +1321,29 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       p.rew[i] = out.rew_sum;
       p.done[i] = out.done_any ? 1 : 0;
     }
-    // observation rows: registers -> shared tile -> bulk store (one per CTA, or one per warp when the warps run free)
-    float* tile_obs = obs_tiles + ((size_t)stage * WARPS + warp) * obs_tile_floats;
-    const bool cta_store = p.tile_sync != 0;
-    if (cta_store) {
-      obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
+    // observation rows: registers -> shared tile -> one bulk store per CTA
+    float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
+    obs_to_tile(p, o, tile_obs + tid * p.obs_dim);
+    if (multi) {
       fence_proxy_async();                       // generic-proxy tile writes -> async proxy
       if (tid == 0) bulk_wait_read0();           // last tile's store has drained the OTHER stage (it had a whole tile)
-      __syncthreads();                           // also keeps the four warps' 512-byte row segments adjacent in time
-      long long rows = p.end - block_first;
-      if (rows > BLOCK) rows = BLOCK;
-      const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
-      float* cta_tile = obs_tiles + (size_t)stage * WARPS * obs_tile_floats;
-      if ((obs_bytes & 15u) == 0u) {
-        if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, cta_tile, obs_bytes); bulk_commit(); }
-      } else {                                   // ragged last tile
-        float* dst = p.obs + block_first * p.obs_dim;
-        for (int k = tid; k < (int)rows * p.obs_dim; k += BLOCK) dst[k] = cta_tile[k];
-      }
+    }
+    __syncthreads();                             // tile complete; also keeps the warps' 512-byte row segments adjacent in time
+    long long rows = p.end - block_first;
+    if (rows > BLOCK) rows = BLOCK;
+    const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
+    if (multi && (obs_bytes & 15u) == 0u) {
+      if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
     } else {
-      if (lane == 0) bulk_wait_read1();          // the store issued two tiles ago has drained this tile
-      __syncwarp();
-      obs_to_tile(p, o, tile_obs + lane * p.obs_dim);
-      fence_proxy_async();
-      __syncwarp();
-      const long long wfirst = block_first + warp * 32;
-      long long rows = p.end - wfirst;
-      if (rows > 32) rows = 32;
-      if (rows > 0) {
-        const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
-        if ((obs_bytes & 15u) == 0u) {
-          if (lane == 0) { bulk_s2g(p.obs + wfirst * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
-        } else {                                 // ragged last tile
-          float* dst = p.obs + wfirst * p.obs_dim;
-          for (int k = lane; k < (int)rows * p.obs_dim; k += 32) dst[k] = tile_obs[k];
-        }
-      }
+      flush_tile(p, tile_obs, block_first, nullptr);                     // one-wave launch, or ragged last tile
     }
     if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
+    ++j;
+    tile = multi ? tile_slot[j & 1] : -1;        // written at least one barrier ago
   }
-  if (lane == 0) bulk_wait_read0();              // shared memory must outlive the bulk stores
+  if (tid == 0) bulk_wait_read0();               // shared memory must outlive the bulk stores
   __syncthreads();                               // every thread of the CTA has read the clock
-  finish_clock(p, svd_end, (unsigned long long)p.k_steps);
+  finish_launch(p, svd_end, (unsigned long long)p.k_steps);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1339,7 +1351,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
 // ---------------------------------------------------------------------------------------------------------
 template <typename R, class T>
 __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant__ Params<R> p) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   R* tile = reinterpret_cast<R*>(smem_raw);
   __shared__ uint8_t valid[BLOCK];
   const long long block_first = p.begin + (long long)blockIdx.x * BLOCK;

@@ -33,7 +33,7 @@ struct QsHandle {
   double* d_stats;
   int* d_status;
   qs::Clock* d_clock;        // device-resident {svd_timer, step}: steps stay CUDA-graph capturable
-  unsigned int* d_ticket;
+  unsigned int* d_ticket;    // [0]: clock ticket; [1 + 2k], [2 + 2k]: launch ticket and tile counter of launch slot k
   uint64_t launches;
   int tile_sync;
   std::string err;
@@ -133,6 +133,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.seed_lo = (unsigned)(c.seed & 0xffffffffu);
   p.seed_hi = (unsigned)(c.seed >> 32);
   p.clock = h->d_clock; p.clock_ticket = h->d_ticket; p.clock_advance = 1;
+  p.launch_ticket = h->d_ticket + 1; p.tile_counter = h->d_ticket + 2;   // launch slot 0
   p.svd_period = c.svd_period;
   p.dt_d = c.dt;
   p.row_ou = h->lay.row_ou; p.row_act = h->lay.row_prev_action; p.row_gyro = h->lay.row_gyro_bias; p.row_goal = h->lay.row_goal;
@@ -205,11 +206,13 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
 
 template <typename R>
 int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8_t* done, cudaStream_t st,
-            long long begin, long long end, int advance) {
+            long long begin, long long end, int advance, int slot = 0) {
   qs::Params<R> p;
   fill_params<R>(h, &p);
   p.k_steps = k;
   p.clock_advance = advance;
+  p.launch_ticket = h->d_ticket + 1 + 2 * slot;
+  p.tile_counter = h->d_ticket + 2 + 2 * slot;
   p.actions = (const R*)actions; p.obs = (R*)obs; p.rew = (R*)rew; p.done = done;
   p.begin = begin; p.end = end;
   cudaError_t e = qs::launch_step<R>(p, st, &h->last_variant);
@@ -264,9 +267,9 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, 3 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(h->d_status, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_clock, sizeof(qs::Clock));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ticket, (1 + 2 * kHostStreams) * sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaMemset(h->d_clock, 0, sizeof(qs::Clock));
-  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, (1 + 2 * kHostStreams) * sizeof(unsigned int));
   if (e != cudaSuccess) {
     g_create_error = std::string("qs_create: ") + cudaGetErrorString(e);
     if (h->d_stats) cudaFree(h->d_stats);
@@ -411,8 +414,8 @@ int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* re
       QS_CUDA(h, cudaMemcpyAsync((char*)h->h_act + (size_t)b * ad * rs, (const char*)actions_host + (size_t)b * ad * rs,
                                  (size_t)(e - b) * ad * rs, cudaMemcpyHostToDevice, st));
     const void* act_dev = actions_host ? h->h_act : nullptr;
-    if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e, 0);
-    else rc = do_step<double>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e, 0);
+    if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e, 0, k);
+    else rc = do_step<double>(h, 1, act_dev, h->h_obs, h->h_rew, h->h_done, st, b, e, 0, k);
     if (rc != QS_OK) return rc;
     QS_CUDA(h, cudaMemcpyAsync((char*)obs_host + (size_t)b * od * rs, (char*)h->h_obs + (size_t)b * od * rs,
                                (size_t)(e - b) * od * rs, cudaMemcpyDeviceToHost, st));
