@@ -191,7 +191,15 @@ template <> struct Mth<double> {
   static __device__ __forceinline__ double unif(uint32_t a) { return (double)(int32_t)a * 4.656612873077393e-10; }
 };
 
-template <typename R> __device__ __forceinline__ R clampr(R x, R lo, R hi) { return Mth<R>::min(Mth<R>::max(x, lo), hi); }
+// np.clip semantics: a NaN argument stays NaN (fminf/fmaxf would return the bound and hide a diverged env from the
+// non-finite reward check, quadrotor.py:633-636).  fp32: FMNMX.NAN, one instruction per bound like the plain form.
+__device__ __forceinline__ float clampr(float x, float lo, float hi) {
+  float y;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(y), "f"(hi));
+  return y;
+}
+__device__ __forceinline__ double clampr(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // Fast fp32 forms used by the throughput variants (Traits::RARE == false): MUFU.RSQ / MUFU.RCP based, ~2 ulp, no
 // denormal / special-case branches.  The per-step parity tests run these same variants (injected-noise twins).

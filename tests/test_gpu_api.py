@@ -1,0 +1,251 @@
+"""GPU: behaviour of the C-ABI entry points beyond single-step parity - Philox streams, sharding invariance,
+K-step fusion, the host-buffer pipeline, CUDA-graph replay, checkpointing, statistics, error paths."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(n, **kw):
+    from gym_art_b200 import QuadVecEnv
+    base = dict(dynamics_params="DefaultQuad", controller="raw", ep_time=1, seed=7)
+    base.update(kw)
+    return QuadVecEnv(n, **base)
+
+
+def _rollout(env, steps, actions=None):
+    import torch
+    env.reset()
+    out = []
+    for t in range(steps):
+        a = actions[t] if actions is not None else None
+        o, r, d = env.step(a)
+        out.append((o.clone(), r.clone(), d.clone()))
+    torch.cuda.synchronize()
+    return out
+
+
+def test_philox_is_deterministic_and_seed_dependent():
+    import torch
+    n, T = 3000, 30
+    acts = torch.rand((T, n, 4), device="cuda") * 2 - 1
+    a = _rollout(_env(n, sense_noise="default"), T, acts)
+    b = _rollout(_env(n, sense_noise="default"), T, acts)
+    c = _rollout(_env(n, sense_noise="default", seed=8), T, acts)
+    for (oa, ra, da), (ob, rb, db) in zip(a, b):
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    assert not torch.equal(a[-1][0], c[-1][0])
+
+
+def test_sharding_invariance_global_env_ids():
+    """Philox is keyed by the GLOBAL env id: one 4096-env handle == two 2048-env handles with env_id_offset."""
+    import torch
+    n, T = 4096, 25
+    acts = torch.rand((T, n, 4), device="cuda") * 2 - 1
+    kw = dict(dynamics_params="Crazyflie", controller="omega_thrust", sense_noise="default", init_random_state=True)
+    whole = _rollout(_env(n, **kw), T, acts)
+    lo = _rollout(_env(n // 2, env_id_offset=0, **kw), T, acts[:, : n // 2])
+    hi = _rollout(_env(n // 2, env_id_offset=n // 2, **kw), T, acts[:, n // 2:])
+    for t in range(T):
+        assert torch.equal(whole[t][0][: n // 2], lo[t][0]) and torch.equal(whole[t][0][n // 2:], hi[t][0])
+        assert torch.equal(whole[t][1][n // 2:], hi[t][1])
+
+
+def test_fast_and_generic_kernels_agree_on_philox_streams():
+    """The TMA fast variant and the generic kernel (forced by binding an info buffer) consume identical Philox
+    streams; their arithmetic differs only by the fast-math forms, so trajectories agree to fp32 round-off."""
+    import torch
+    n, T = 2048 + 13, 20
+    acts = torch.rand((T, n, 4), device="cuda") * 2 - 1
+    fast = _env(n, sense_noise="default")
+    gen = _env(n, sense_noise="default", info=True)
+    a, b = _rollout(fast, T, acts), _rollout(gen, T, acts)
+    assert fast.kernel_variant.startswith("tma-") and gen.kernel_variant == "generic-philox"
+    for t in range(T):
+        assert torch.allclose(a[t][0], b[t][0], rtol=0, atol=2e-4), t
+        assert torch.allclose(a[t][1], b[t][1], rtol=0, atol=1e-5)
+
+
+def test_ou_and_sensor_noise_moments():
+    """Distribution parity for the Philox mode: OU thrust noise stationary std = sigma / sqrt(1 - (1-theta)^2)
+    (quad_utils.py:197-201), sensor-noise std = the SensorNoise parameters (sensor_noise.py:58-63)."""
+    import torch
+    n = 200000
+    env = _env(n, dynamics_params="Crazyflie", sense_noise="default", ep_time=5)
+    env.reset()
+    a = torch.zeros((n, 4), device="cuda")
+    for _ in range(60):
+        obs, _, _ = env.step(a)
+    ou = env.ou_state
+    want = 0.01 / np.sqrt(1 - 0.85 ** 2)
+    assert abs(ou.std().item() - want) / want < 0.02 and abs(ou.mean().item()) < 3e-4
+    # kurtosis of a Gaussian is 3
+    z = (ou / ou.std()).flatten()
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1
+    pos_err = obs[:, 0:3] - (env.pos - torch.tensor(env.goal, device="cuda", dtype=torch.float32))
+    vel_err = obs[:, 3:6] - env.vel
+    om_err = obs[:, 15:18] - env.omega
+    assert abs(pos_err.std().item() - 0.005) / 0.005 < 0.02
+    assert abs(vel_err.std().item() - 0.01) / 0.01 < 0.02
+    assert abs(om_err.std().item() - 0.000175) / 0.000175 < 0.05
+    # independent components / envs: tiny cross-correlation
+    c = torch.corrcoef(torch.stack([pos_err[:, 0], pos_err[:, 1], vel_err[:, 0], ou[:, 0]]))
+    assert (c - torch.eye(4, device="cuda")).abs().max().item() < 0.02
+
+
+def test_reset_distributions():
+    """Spawn law of QuadrotorEnv._reset (quadrotor.py:1085-1126, :227-239)."""
+    import torch
+    n = 200000
+    env = _env(n)
+    env.reset()
+    pos, rot = env.pos, env.rot
+    assert pos[:, 0].min() >= -2.0 and pos[:, 0].max() <= 2.0 and pos[:, 2].min() >= 0.25 and pos[:, 2].max() <= 4.0
+    assert abs(pos[:, 0].std().item() - 4 / np.sqrt(12)) < 0.02
+    assert abs((pos[:, 2] == 0.25).float().mean().item() - 0.0625) < 0.005       # z = max(U(0,4), 0.25)
+    # heading within +-60 deg of the direction to the origin: R[:,0] . xyhat(-pos) >= 0.5
+    to = -pos[:, :2] / pos[:, :2].norm(dim=1, keepdim=True)
+    dot = (rot[:, 0:2, 0] * to).sum(1)
+    assert dot.min().item() >= 0.5 - 1e-4 and abs(dot.mean().item() - (np.sin(np.pi / 3) / (np.pi / 3))) < 0.01
+    assert torch.allclose(rot[:, 2, 2], torch.ones(n, device="cuda")) and env.vel.abs().max().item() == 0
+    env = _env(n, init_random_state=True)
+    env.reset()
+    speed, spin, rot = env.vel.norm(dim=1), env.omega.norm(dim=1), env.rot
+    assert speed.max().item() <= 1.0 + 1e-5 and abs(speed.mean().item() - 0.5) < 0.01
+    assert spin.max().item() <= 2 * np.pi + 1e-4 and abs(spin.mean().item() - np.pi) < 0.05
+    eye = torch.eye(3, device="cuda").expand(n, 3, 3)
+    assert (rot @ rot.transpose(1, 2) - eye).abs().max().item() < 1e-5           # orthonormal (test_noise.py:265)
+    assert abs(torch.linalg.det(rot).mean().item() - 1.0) < 1e-5
+    assert abs(rot[:, 2, 2].mean().item()) < 0.01                                # uniform on SO(3): E[R22] = 0
+
+
+def test_step_k_equals_k_steps():
+    import torch
+    n, K = 5000, 7
+    acts = torch.rand((K, n, 4), device="cuda") * 2 - 1
+    for ctrl, a in (("raw", acts), ("mellinger", None)):
+        e1, e2 = _env(n, controller=ctrl, ep_time=0.05), _env(n, controller=ctrl, ep_time=0.05)   # ep_len 5: resets inside
+        e1.reset(), e2.reset()
+        rsum = torch.zeros(n, device="cuda")
+        dany = torch.zeros(n, device="cuda", dtype=torch.bool)
+        for k in range(K):
+            o1, r1, d1 = e1.step(None if a is None else a[k])
+            rsum += r1
+            dany |= d1
+        o2, r2, d2 = e2.step_k(K, a)
+        assert torch.equal(o1, o2) and torch.equal(dany, d2) and torch.allclose(rsum, r2, rtol=0, atol=1e-6)
+        assert torch.equal(e1.state, e2.state) and e1.clock == e2.clock
+
+
+def test_step_host_equals_step():
+    import torch
+    n = 70000 + 5            # several chunks, ragged tail
+    e1, e2 = _env(n, sense_noise="default"), _env(n, sense_noise="default")
+    e1.reset(), e2.reset()
+    a_h = (torch.rand((n, 4)) * 2 - 1).pin_memory()
+    o_h = torch.empty((n, 18)).pin_memory()
+    r_h, d_h = torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    a_d = a_h.cuda()
+    for _ in range(4):
+        o, r, d = e1.step(a_d)
+        e2.step_host(a_h, o_h, r_h, d_h)
+        assert torch.equal(o.cpu(), o_h) and torch.equal(r.cpu(), r_h) and torch.equal(d.cpu(), d_h.bool())
+    assert e1.clock == e2.clock and torch.equal(e1.state, e2.state)
+
+
+def test_cuda_graph_replay_advances_device_clock():
+    """Steps captured in a CUDA graph keep drawing fresh Philox numbers on replay (device-resident clock)."""
+    import torch
+    n, G = 4096, 6
+    acts = torch.rand((n, 4), device="cuda") * 2 - 1
+    ref, env = _env(n), _env(n)
+    ref.reset(), env.reset()
+    for _ in range(2):
+        env.step(acts), ref.step(acts)
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=st):
+        for _ in range(G):
+            env.step(acts)
+    # capture does not execute: env is still 2 steps in
+    for rep in range(3):
+        g.replay()
+        for _ in range(G):
+            ref.step(acts)
+    torch.cuda.synchronize()
+    assert env.clock == ref.clock and env.clock[1] == 1 + 2 + 3 * G       # reset consumes one step index
+    assert torch.equal(env.state, ref.state) and torch.equal(env.obs, ref.obs)
+
+
+def test_state_dict_roundtrip():
+    import torch
+    n = 3000
+    acts = torch.rand((n, 4), device="cuda") * 2 - 1
+    a, b = _env(n, sense_noise="default"), _env(n, sense_noise="default", seed=7)
+    a.reset()
+    for _ in range(5):
+        a.step(acts)
+    b.load_state_dict(a.state_dict())
+    for _ in range(5):
+        oa, ra, _ = a.step(acts)
+        ob, rb, _ = b.step(acts)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb)
+
+
+def test_stats_and_masked_reset():
+    import torch
+    n = 1000
+    env = _env(n, ep_time=0.1)       # ep_len 10 -> 11-step episodes
+    env.reset()
+    a = torch.zeros((n, 4), device="cuda")
+    total = torch.zeros(n, device="cuda", dtype=torch.float64)
+    for t in range(11):
+        _, r, d = env.step(a)
+        total += r.double()
+        assert bool(d.all()) == (t == 10)
+    s = env.stats(clear=True)
+    assert s[2] == n and abs(s[0] - total.sum().item()) < 1e-3 * abs(s[0]) and env.stats()[2] == 0
+    assert env.tick.max().item() == 0                     # auto-reset happened
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    env.step(a)
+    before = env.pos.clone()
+    obs_before = env.obs.clone()
+    env.reset(mask)
+    moved = (env.pos != before).any(dim=1)
+    assert torch.equal(moved, mask) and torch.equal(env.tick == 0, mask)
+    assert torch.equal(env.obs[~mask], obs_before[~mask])
+
+
+def test_nonfinite_reward_is_flagged():
+    import torch
+    from gym_art_b200 import _lib
+    env = _env(256)
+    env.reset()
+    env.check_finite()
+    env.set_field("pos", [float("nan"), 0.0, 1.0])
+    env.step(torch.zeros((256, 4), device="cuda"))
+    with pytest.raises(_lib.QuadsimError, match="reward is Nan") as ei:       # reference: ValueError, quadrotor.py:636
+        env.check_finite()
+    assert ei.value.code == _lib.QS_ENONFINITE
+
+
+def test_errors_without_state_or_actions():
+    import ctypes as C
+    import torch
+    from gym_art_b200 import _lib
+    from gym_art_b200.quadrotor.model import ModelConstants
+    from gym_art_b200.vec_env import make_config, resolve_dynamics_params
+    lib = _lib.load()
+    cfg, _, _ = make_config(128, ModelConstants(resolve_dynamics_params("DefaultQuad")))
+    h = C.c_void_p()
+    assert lib.qs_create(C.byref(cfg), C.byref(h)) == _lib.QS_OK
+    buf = torch.zeros(128 * 18, device="cuda")
+    assert lib.qs_step(h, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == _lib.QS_ESTATE
+    assert b"not bound" in lib.qs_last_error(h)
+    state = torch.zeros((8, 128, 4), device="cuda")
+    assert lib.qs_bind_state(h, state.data_ptr()) == _lib.QS_OK
+    assert lib.qs_step(h, None, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == _lib.QS_EINVAL   # raw needs actions
+    assert lib.qs_set_noise_injection(h, None, None, None) == _lib.QS_EINVAL                            # Philox handle
+    assert lib.qs_destroy(h) == _lib.QS_OK
