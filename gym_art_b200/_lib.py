@@ -10,15 +10,16 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QUADSIM_LIB") or os.path.join(HERE, "libquadsim.so")   # override: A/B builds only
 
-QS_ABI_VERSION = 4
+QS_ABI_VERSION = 5
 QS_OK, QS_EINVAL, QS_ECUDA, QS_ENONFINITE, QS_ESTATE, QS_EUNSUPPORTED, QS_EABI = 0, -1, -2, -3, -4, -5, -6
 QS_F32, QS_F64 = 0, 1
 (QS_CTRL_RAW, QS_CTRL_VERTICAL, QS_CTRL_VERTPLANE, QS_CTRL_SHIFTED, QS_CTRL_OMEGA_THRUST, QS_CTRL_VELOCITY_YAW,
  QS_CTRL_MELLINGER) = range(7)
 QS_NOISE_PHILOX, QS_NOISE_INJECTED = 0, 1
-QS_OBS_Z, QS_RESET_Z, QS_INFO_DIM = 30, 48, 32
+QS_OBS_Z, QS_RESET_Z, QS_INFO_DIM = 30, 48, 48
 (QS_INFO_ACC, QS_INFO_ACCELEROMETER, QS_INFO_TORQUE, QS_INFO_OMEGA_DOT, QS_INFO_CMDS, QS_INFO_CRASHED, QS_INFO_COLLIDED,
- QS_INFO_COSTS, QS_INFO_EP_RETURN, QS_INFO_TICK) = (0, 3, 6, 9, 12, 16, 17, 18, 28, 29)
+ QS_INFO_COSTS, QS_INFO_EP_RETURN, QS_INFO_TICK, QS_INFO_REWARD, QS_INFO_DONE, QS_INFO_COSTS_RAW) = (
+    0, 3, 6, 9, 12, 16, 17, 18, 28, 29, 30, 31, 32)
 
 OBS_REPRS = ["xyz_vxyz_R_omega", "xyz_vxyz_R_omega_h", "xyzr_vxyzr_R_omega", "xyzr_vxyzr_R_omega_h",
              "xyz_vxyz_R_omega_acc_act", "xyz_vxyz_R_omega_act"]
@@ -62,7 +63,7 @@ class QsConfig(C.Structure):
                 ("noise_mode", C.c_int32), ("init_random_state", C.c_int32), ("auto_reset", C.c_int32),
                 ("dim_mode", C.c_int32), ("sim_steps", C.c_int32), ("ep_len", C.c_int32), ("per_env_goal", C.c_int32),
                 ("_pad", C.c_int32), ("dt", C.c_double), ("svd_period", C.c_double), ("goal", C.c_double * 3),
-                ("spawn_box", C.c_double), ("room_box", (C.c_double * 3) * 2), ("max_init_vel", C.c_double),
+                ("spawn_box", C.c_double), ("spawn_z_min", C.c_double), ("room_box", (C.c_double * 3) * 2), ("max_init_vel", C.c_double),
                 ("max_init_omega", C.c_double), ("collision_k", C.c_double), ("model", QsModel), ("reward", QsReward),
                 ("sense", QsSensorNoise)]
 

@@ -17,7 +17,7 @@ namespace qs {
 
 constexpr int BLOCK = 128;           // threads per CTA = envs per CTA
 constexpr int MAX_OBS = 25;
-constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 32;
+constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 48;
 
 enum Ctrl { CTRL_RAW = 0, CTRL_VERTICAL, CTRL_VERTPLANE, CTRL_SHIFTED, CTRL_OMEGA_THRUST, CTRL_VELOCITY_YAW, CTRL_MELLINGER };
 
@@ -78,7 +78,7 @@ struct Params {
   R ou_theta, ou_sigma, arm, omega_max, gravity, t2w;
   R jinv[4][4];
   R room_lo[3], room_hi[3];
-  R goal[3], spawn_box, max_init_vel, max_init_omega, coll_dist;
+  R goal[3], spawn_box, spawn_z_min, max_init_vel, max_init_omega, coll_dist;
   // reward
   R c_pos, c_effort, c_act_change, c_crash, c_orient, c_yaw, c_rot, c_attitude, c_spin, c_vel;
   R c_pos_offset, c_pos_log_w, c_pos_lin_w, c_collision;
@@ -684,32 +684,41 @@ __device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>&
 template <typename R, class T>
 __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, const R* a, const R* a_prev,
                                             bool crashed, bool collided, R* costs) {
+  const bool all = costs != nullptr;                                    // info buffer bound: every raw cost, as the reference
   R dx = s.gx - s.px, dy = s.gy - s.py, dz = s.gz - s.pz;
   R dist = q_sqrt<R, T::FASTM>(dx * dx + dy * dy + dz * dz);
-  R c_pos;
-  if (T::RARE && p.log_pos) c_pos = p.c_pos * (p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist);
-  else c_pos = p.c_pos * dist;                                          // :547-549
-  R c_eff = p.c_effort * q_sqrt<R, T::FASTM>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
-  R c_ac = R(0);
-  if (p.c_act_change != R(0)) {                                         // :556-558
+  R r_pos = dist;                                                       // :547-549
+  if (T::RARE && p.log_pos) r_pos = p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist;   // multi :554
+  R c_pos = p.c_pos * r_pos;
+  R r_eff = q_sqrt<R, T::FASTM>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
+  R c_eff = p.c_effort * r_eff;
+  R r_ac = R(0), c_ac = R(0);
+  if (all || p.c_act_change != R(0)) {                                  // :556-558
     R e0 = a[0] - a_prev[0], e1 = a[1] - a_prev[1], e2 = a[2] - a_prev[2], e3 = a[3] - a_prev[3];
-    c_ac = p.c_act_change * Mth<R>::sqrt(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+    r_ac = Mth<R>::sqrt(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+    c_ac = p.c_act_change * r_ac;
   }
-  R c_vel = R(0);
-  if (p.c_vel != R(0)) c_vel = p.c_vel * Mth<R>::sqrt(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);   // :562-563
+  R r_vel = R(0), c_vel = R(0);
+  if (all || p.c_vel != R(0)) { r_vel = Mth<R>::sqrt(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz); c_vel = p.c_vel * r_vel; }   // :562-563
   R c_or = p.c_orient * (-s.r[8]);                                      // :567-568
   R c_yaw = p.c_yaw * (-s.r[0]);                                        // :570-571
-  R c_rot = R(0), c_att = R(0);
-  if (p.c_rot != R(0)) c_rot = p.c_rot * Mth<R>::acos(clampr(((s.r[0] + s.r[4] + s.r[8]) - R(1)) / R(2), R(-1), R(1)));
-  if (p.c_attitude != R(0)) c_att = p.c_attitude * Mth<R>::acos(clampr(s.r[8], R(-1), R(1)));      // :580-581
-  R c_spin = p.c_spin * q_sqrt<R, T::FASTM>(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);              // :585-586
+  R r_rot = R(0), c_rot = R(0), r_att = R(0), c_att = R(0);
+  if (all || p.c_rot != R(0)) {                                         // :575-578
+    r_rot = Mth<R>::acos(clampr(((s.r[0] + s.r[4] + s.r[8]) - R(1)) / R(2), R(-1), R(1)));
+    c_rot = p.c_rot * r_rot;
+  }
+  if (all || p.c_attitude != R(0)) { r_att = Mth<R>::acos(clampr(s.r[8], R(-1), R(1))); c_att = p.c_attitude * r_att; }   // :580-581
+  R r_spin = q_sqrt<R, T::FASTM>(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);                         // :585-586
+  R c_spin = p.c_spin * r_spin;
   R c_crash = crashed ? p.c_crash : R(0);                               // :590-591
   R sum = ((c_pos + c_eff) + (c_crash + c_or)) + ((c_yaw + c_rot) + (c_att + c_spin));            // np.sum pairwise
   sum = (sum + c_ac) + c_vel;                                           // :593-604
   if (T::RARE) { if (collided) sum += p.c_collision; }
-  if (costs) {
+  if (costs) {                                                          // rew_info order (:607-631): weighted, then raw
     costs[0] = c_pos; costs[1] = c_eff; costs[2] = c_crash; costs[3] = c_or; costs[4] = c_yaw;
     costs[5] = c_rot; costs[6] = c_att; costs[7] = c_spin; costs[8] = c_ac; costs[9] = c_vel;
+    costs[10] = r_pos; costs[11] = r_eff; costs[12] = crashed ? R(1) : R(0); costs[13] = -s.r[8]; costs[14] = -s.r[0];
+    costs[15] = r_rot; costs[16] = r_att; costs[17] = r_spin; costs[18] = r_ac; costs[19] = r_vel;
   }
   return -p.dt * sum;
 }
@@ -908,7 +917,7 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
     if (p.dim_mode == 1) { x = s.gx; y = s.gy; }                        // :1089-1092
     else if (p.dim_mode == 2) { y = s.gy; }
   }
-  if (z < R(0.25)) z = R(0.25);                                         // :1094
+  if (z < p.spawn_z_min) z = p.spawn_z_min;                             // :1094 (0.25)
   s.px = x; s.py = y; s.pz = z;
   if (p.init_random) {                                                  // :1113-1115 -> :227-239
     R a[4], b[4], up[4], fw[4];
@@ -1060,7 +1069,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     if (T::RARE) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
     // ---- crash, reward, tick, done (:974-987) ----
     bool crashed = s.pz <= p.arm;                                       // :977
-    R costs[10];
+    R costs[20];
     R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::RARE && p.info) ? costs : nullptr);
     if (!Mth<R>::finite(rew) && active) atomicOr(p.status, 1);          // :633-636
     s.tick += R(1);                                                     // :986
@@ -1081,8 +1090,10 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
         inf[12] = cmd[0]; inf[13] = cmd[1]; inf[14] = cmd[2]; inf[15] = cmd[3];
         inf[16] = crashed ? R(1) : R(0); inf[17] = collided ? R(1) : R(0);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) inf[18 + k] = costs[k];
-        inf[28] = s.ret; inf[29] = s.tick; inf[30] = R(0); inf[31] = R(0);
+        for (int k = 0; k < 10; ++k) { inf[18 + k] = costs[k]; inf[32 + k] = costs[10 + k]; }
+        inf[28] = s.ret; inf[29] = s.tick; inf[30] = rew; inf[31] = done ? R(1) : R(0);
+#pragma unroll
+        for (int k = 42; k < INFO_DIM; ++k) inf[k] = R(0);
       }
     }
     // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----

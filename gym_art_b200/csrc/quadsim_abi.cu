@@ -181,7 +181,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.vel_damp = (R)m.vel_damp; p.damp_omega_q = (R)m.damp_omega_quadratic;
   p.ou_theta = (R)m.ou_theta; p.ou_sigma = (R)m.ou_sigma;
   p.arm = (R)m.arm; p.omega_max = (R)m.omega_max; p.gravity = (R)m.gravity; p.t2w = (R)m.thrust_to_weight;
-  p.spawn_box = (R)c.spawn_box; p.max_init_vel = (R)c.max_init_vel; p.max_init_omega = (R)c.max_init_omega;
+  p.spawn_box = (R)c.spawn_box; p.spawn_z_min = (R)c.spawn_z_min; p.max_init_vel = (R)c.max_init_vel; p.max_init_omega = (R)c.max_init_omega;
   p.coll_dist = (R)(c.collision_k * 2.0 * m.arm);
   const QsReward& r = c.reward;
   p.c_pos = (R)r.pos; p.c_effort = (R)r.effort; p.c_act_change = (R)r.action_change; p.c_crash = (R)r.crash;

@@ -66,7 +66,7 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
                 sim_steps=2, obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10, init_random_state=False,
                 rew_coeff=None, sense_noise=None, device_index=0, dtype="float32", seed=0, noise_mode="philox",
                 auto_reset=True, n_agents=1, per_env_goal=False, env_id_offset=0, multi_reward=False, collision_k=1.0,
-                goal=(0., 0., 2.), box=2.0):
+                goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi):
     """Pure host function (no GPU): ctor arguments -> QsConfig.  Raises the reference's ValueErrors."""
     cfg = _lib.QsConfig()
     cfg.abi_version = _lib.QS_ABI_VERSION
@@ -99,13 +99,14 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
     for k in range(3):
         cfg.goal[k] = float(goal[k])
     cfg.spawn_box = float(box)                                                        # quadrotor.py:728
+    cfg.spawn_z_min = float(spawn_z_min)                                              # quadrotor.py:1094
     lo = [-room_size, -room_size, 0.]
     hi = [room_size, room_size, room_size]                                            # quadrotor.py:723
     for k in range(3):
         cfg.room_box[0][k] = float(lo[k])
         cfg.room_box[1][k] = float(hi[k])
-    cfg.max_init_vel = 1.                                                             # quadrotor.py:717
-    cfg.max_init_omega = 2 * np.pi                                                    # quadrotor.py:718
+    cfg.max_init_vel = float(max_init_vel)                                            # quadrotor.py:717
+    cfg.max_init_omega = float(max_init_omega)                                        # quadrotor.py:718
     cfg.collision_k = float(collision_k)
     cfg.model = model.to_qs()
     rc = resolve_rew_coeff(rew_coeff, multi_reward)
@@ -139,7 +140,8 @@ class QuadVecEnv(object):
                  obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10, init_random_state=False, rew_coeff=None,
                  sense_noise=None, gravity=GRAV, device="cuda:0", dtype="float32", seed=0, noise_mode="philox",
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
-                 info=False):
+                 info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
+                 max_init_omega=2 * np.pi):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -164,7 +166,8 @@ class QuadVecEnv(object):
             room_size=room_size, init_random_state=init_random_state, rew_coeff=rew_coeff, sense_noise=sense_noise,
             device_index=dev_index, dtype=dtype, seed=seed, noise_mode=noise_mode, auto_reset=auto_reset,
             n_agents=n_agents, per_env_goal=goals is not None, env_id_offset=env_id_offset, multi_reward=multi_reward,
-            collision_k=collision_k)
+            collision_k=collision_k, goal=goal, box=box, spawn_z_min=spawn_z_min, max_init_vel=max_init_vel,
+            max_init_omega=max_init_omega)
         self.layout = _lib.state_layout(self.cfg)
         self.num_envs = int(num_envs)
         self.n_agents = int(n_agents)
@@ -174,14 +177,19 @@ class QuadVecEnv(object):
         self.goal = np.array([self.cfg.goal[0], self.cfg.goal[1], self.cfg.goal[2]])
         N = self.num_envs
         with torch.cuda.device(self.device):
-            self.state = torch.zeros((self.layout.rows, N, 4), dtype=self.tdtype, device=self.device)
+            if state is None:
+                self.state = torch.zeros((self.layout.rows, N, 4), dtype=self.tdtype, device=self.device)
+            else:       # a second handle over the same drones (e.g. another controller or dt): same layout required
+                assert tuple(state.shape) == (self.layout.rows, N, 4) and state.dtype == self.tdtype and state.is_contiguous()
+                self.state = state
             self.obs = torch.zeros((N, self.obs_dim), dtype=self.tdtype, device=self.device)
             self.rew = torch.zeros((N,), dtype=self.tdtype, device=self.device)
             self._done_u8 = torch.zeros((N,), dtype=torch.uint8, device=self.device)
             self.done = self._done_u8.view(torch.bool)      # zero-copy: the kernel writes 0 / 1
             self.info = torch.zeros((N, _lib.QS_INFO_DIM), dtype=self.tdtype, device=self.device) if info else None
-        self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.device).reshape(1, 9))
-        if goals is not None:
+        if state is None:
+            self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.device).reshape(1, 9))
+        if goals is not None and state is None:
             self.set_field("goals", np.asarray(goals, dtype=np.float64).reshape(N, 3))
         self._h = C.c_void_p()
         _lib.check(self.lib.qs_create(C.byref(self.cfg), C.byref(self._h)))

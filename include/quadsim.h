@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 4
+#define QS_ABI_VERSION 5
 
 typedef struct QsHandle QsHandle;
 typedef void* qs_stream_t; /* cudaStream_t */
@@ -101,7 +101,7 @@ typedef enum QsNoiseMode {
 /* ou_z   [n_envs][sim_steps][4] : OUNoise.noise() normals, one per substep (quad_utils.py:197-201) */
 
 /* Optional per-env diagnostics, info [n_envs][QS_INFO_DIM] (reference: info['obs_comp'], quadrotor.py:994-1006) */
-#define QS_INFO_DIM 32
+#define QS_INFO_DIM 48
 #define QS_INFO_ACC 0            /* world-frame acceleration, dynamics.acc */
 #define QS_INFO_ACCELEROMETER 3  /* dynamics.accelerometer */
 #define QS_INFO_TORQUE 6         /* dynamics.torque */
@@ -112,6 +112,9 @@ typedef enum QsNoiseMode {
 #define QS_INFO_COSTS 18         /* 10 weighted costs in the reference's summation order (quadrotor.py:593-604) */
 #define QS_INFO_EP_RETURN 28     /* running return of the episode the step belonged to */
 #define QS_INFO_TICK 29          /* tick after the step (before any auto-reset) */
+#define QS_INFO_REWARD 30        /* reward of the (last) step */
+#define QS_INFO_DONE 31          /* done flag of the (last) step */
+#define QS_INFO_COSTS_RAW 32     /* the same 10 costs before weighting: rew_info 'rewraw_*' (quadrotor.py:619-630) */
 
 /* QuadrotorDynamics constants (quadrotor.py:142-208) + the controllers' inverse Jacobian (quadrotor_control.py:192-211) */
 typedef struct QsModel {
@@ -175,6 +178,7 @@ typedef struct QsConfig {
   double svd_period;   /* since_last_svd_limit = 0.5 s (quadrotor.py:105) */
   double goal[3];      /* (0, 0, 2) (quadrotor.py:1081) */
   double spawn_box;    /* self.box = 2 (quadrotor.py:728) */
+  double spawn_z_min;  /* spawn height floor 0.25 (quadrotor.py:1094) */
   double room_box[2][3];
   double max_init_vel, max_init_omega; /* quadrotor.py:717-718 */
   double collision_k;  /* swarm: contact when |p_i - p_j| < collision_k * 2 * arm */

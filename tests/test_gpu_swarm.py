@@ -1,0 +1,105 @@
+"""GPU: the swarm env step (per-drone env step + pairwise contact in warp shuffles) against the NumPy oracle of the
+repo's own swarm specification (no reference semantics exist: parity is oracle parity)."""
+import numpy as np
+import pytest
+
+from oracle import quadsim_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(E, M, dtype, seed, **kw):
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
+    params = quad_models.defaultquad_params()
+    goals = np.tile(ring_goals(M, radius=0.3), (E, 1))          # tight ring: contacts happen within a few dozen steps
+    base = dict(ep_time=0.4, sim_steps=2, collision_k=1.5)
+    base.update(kw)
+    coll = base.pop("collision", 0.7)
+    oe = qo.OracleVecEnv(params, E * M, controller=qo.CTRL_RAW, auto_reset=True, n_agents=M, goals=goals, box=0.5,
+                         collision_coeff=coll, multi_reward=True, **base)
+    env = QuadVecEnv(E * M, dynamics_params=params, controller="raw", dtype=dtype, noise_mode="injected", auto_reset=True,
+                     n_agents=M, goals=goals, box=0.5, multi_reward=True, rew_coeff={"collision": coll}, info=True, seed=seed,
+                     **base)
+    return oe, env
+
+
+@pytest.mark.parametrize("M", [2, 8, 32])
+def test_swarm_step_matches_oracle_fp64(M):
+    E, T = 64 + 5, 100
+    rng = np.random.RandomState(M)
+    oe, env = _pair(E, M, "float64", 1)
+    n = E * M
+    rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+    env.set_noise(reset_z=rz)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), oe.reset(reset_z=rz), rtol=0, atol=1e-12)
+    hits = 0
+    for t in range(T):
+        a = rng.uniform(-0.2, 0.4, (n, 4))
+        ou_z = rng.standard_normal((n, 2, 4))
+        rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+        env.set_noise(ou_z=ou_z, reset_z=rz)
+        o, r, d = env.step(a)
+        oo, ro, do = oe.step(a, ou_z=ou_z, reset_z=rz)
+        assert np.array_equal(d.cpu().numpy(), do)
+        # free-running rollout: the device adds a drone's contact impulses in rotated partner order, the oracle in
+        # index order, and that last-bit difference grows with the (chaotic) contact dynamics
+        np.testing.assert_allclose(o.cpu().numpy(), oo, rtol=1e-8, atol=1e-8, err_msg="obs step %d" % t)
+        np.testing.assert_allclose(r.cpu().numpy(), ro, rtol=0, atol=1e-9)
+        coll = env.info[:, 17].cpu().numpy() != 0
+        assert np.array_equal(coll, oe.collided)
+        hits += int(coll.sum())
+    assert hits > 0, "the scenario must exercise the contact branch"
+    np.testing.assert_allclose(env.stats(), oe.stats, rtol=1e-9)
+
+
+def test_swarm_step_matches_oracle_fp32_per_step():
+    """fp32 build, state re-synchronised every step: 1e-5 relative on velocities / observations after contact."""
+    E, M, T = 128, 8, 60
+    rng = np.random.RandomState(11)
+    oe, env = _pair(E, M, "float32", 2, ep_time=5)
+    n = E * M
+    rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+    env.set_noise(reset_z=rz)
+    env.reset()
+    oe.reset(reset_z=rz)
+    hits = 0
+    for t in range(T):
+        for f, v in (("pos", oe.pos), ("vel", oe.vel), ("rot", oe.rot.reshape(n, 9)), ("omega", oe.omega),
+                     ("thrust_rot_damp", oe.rot_damp), ("thrust_cmds_damp", oe.cmds_damp), ("ou_state", oe.ou)):
+            env.set_field(f, v)
+        # the oracle continues from the fp32-rounded state the device holds
+        oe.pos, oe.vel, oe.omega = (env.get_field(k).double().cpu().numpy() for k in ("pos", "vel", "omega"))
+        oe.rot = env.get_field("rot").double().cpu().numpy()
+        oe.rot_damp, oe.cmds_damp, oe.ou = (env.get_field(k).double().cpu().numpy() for k in ("thrust_rot_damp", "thrust_cmds_damp", "ou_state"))
+        a = rng.uniform(-0.2, 0.4, (n, 4)).astype(np.float32).astype(np.float64)
+        ou_z = rng.standard_normal((n, 2, 4)).astype(np.float32).astype(np.float64)
+        env.set_noise(ou_z=ou_z)
+        o, r, d = env.step(a)
+        oo, ro, do = oe.step(a, ou_z=ou_z)
+        coll = env.info[:, 17].cpu().numpy() != 0
+        same = coll == oe.collided                      # a pair within 1 ulp of the contact distance may differ
+        assert same.mean() > 0.999
+        hits += int(coll.sum())
+        ok = np.repeat(same.reshape(E, M).all(axis=1), M)
+        err = np.abs(o.double().cpu().numpy() - oo)[ok] / np.maximum(np.abs(oo[ok]), 1.0)
+        assert err.max() < 1e-5, (t, err.max())
+        assert np.max(np.abs(r.double().cpu().numpy() - ro)[ok]) < 1e-6
+    assert hits > 0
+
+
+def test_swarm_facade_shapes_and_contact_flags():
+    import torch
+    from gym_art_b200.quadrotor_multi.quadrotor_multi import QuadrotorEnvMulti
+    env = QuadrotorEnvMulti(num_agents=8, num_envs=16, goal_radius=0.2, collision_k=2.0, info=True, seed=3)
+    o = env.reset()
+    assert tuple(o.shape) == (16, 8, 18)
+    seen = False
+    for t in range(200):
+        o, r, d, info = env.step(torch.zeros((16, 8, 4), device="cuda"))
+        seen = seen or bool(info["collided"].any())
+    assert tuple(r.shape) == (16, 8) and tuple(d.shape) == (16, 8) and seen
+    single = QuadrotorEnvMulti(num_agents=4, seed=1)
+    assert tuple(single.reset().shape) == (4, 18)
+    env.close(); single.close()
