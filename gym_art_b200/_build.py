@@ -2,7 +2,7 @@
 
     python -m gym_art_b200._build [--force] [--verbose]
 
-The three translation units compile in parallel; the shared object is git-ignored but travels to the GPU box
+The translation units compile in parallel; the shared object is git-ignored but travels to the GPU box
 with the repo snapshot.
 """
 import os
@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libquadsim.so")
-SOURCES = ["qs_kernels_f32.cu", "qs_kernels_f32_fast_philox.cu", "qs_kernels_f32_fast_inject.cu", "qs_kernels_f64.cu",
-           "quadsim_abi.cu"]
+FAST = ["qs_fast_%s_%s.cu" % (c, n) for c in ("raw", "omega", "mellinger") for n in ("philox", "inject")]
+SOURCES = ["qs_kernels_f32.cu", "qs_kernels_f64.cu", "quadsim_abi.cu"] + FAST
 DEPS = ["qs_device.cuh", "qs_kernels.inl", "qs_fast.inl", os.path.join("..", "..", "include", "quadsim.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # no --use_fast_math: parity with the float64 reference is part of the contract (fast intrinsics are used

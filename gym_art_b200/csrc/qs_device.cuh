@@ -69,7 +69,7 @@ struct Params {
   int inject, need_rare;              // variant selection (host)
   int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
   long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
-  int tile_sync;                      // TMA kernel: re-couple the CTA's warps with one barrier per tile (DRAM locality)
+  int pdl;                            // step kernel launched with programmatic dependent launch (see env_step_tma_kernel)
   // model
   R dt;
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
@@ -90,9 +90,11 @@ struct Params {
 };
 
 // compile-time specialisation knobs; -1 = decided at run time from Params
-template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_>
+template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_, int SIM_ = -1, bool PLAIN_ = false>
 struct Traits {
   static constexpr int CTRL = CTRL_;
+  static constexpr int SIM = SIM_;      // compile-time sim_steps (substep loop unrolled, OU draws hoisted), -1 = run time
+  static constexpr bool PLAIN = PLAIN_; // one env step per launch, 18-word observation, no previous-action row
   static constexpr int OU = OU_;
   static constexpr int SENSE = SENSE_;
   static constexpr bool INJECT = INJECT_;
@@ -128,18 +130,27 @@ __device__ __forceinline__ void finish_clock(const Params<R>& p, double svd_t_en
 }
 
 // same ticket scheme for launches that must not advance the clock (chunks of the host pipeline) but still have to
-// leave the work counter of the tile scheduler at zero
+// leave the work counter of the tile scheduler at zero.  Called by ONE thread of the CTA, after every thread of the
+// CTA has read the clock.
 template <typename R>
-__device__ __forceinline__ void finish_launch(const Params<R>& p, double svd_t_end, unsigned long long steps) {
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(p.launch_ticket, 1u);
-    if (t == gridDim.x - 1) {
-      *p.launch_ticket = 0u;
-      *p.tile_counter = 0u;
-      if (p.clock_advance) { p.clock->svd_timer = svd_t_end; p.clock->step += steps; }
-    }
+__device__ __forceinline__ void finish_launch_one(const Params<R>& p, double svd_t_end, unsigned long long steps) {
+  const unsigned int t = atomicAdd(p.launch_ticket, 1u);
+  if (t == gridDim.x - 1) {
+    *p.launch_ticket = 0u;
+    *p.tile_counter = 0u;
+    if (p.clock_advance) { p.clock->svd_timer = svd_t_end; p.clock->step += steps; }
   }
 }
+template <typename R>
+__device__ __forceinline__ void finish_launch(const Params<R>& p, double svd_t_end, unsigned long long steps) {
+  if (threadIdx.x == 0) finish_launch_one(p, svd_t_end, steps);
+}
+
+// Programmatic dependent launch (PDL): the step kernel lets the NEXT launch on the stream become resident and run
+// its prologue while this one is still computing, and itself waits for the PREVIOUS launch to complete (with its
+// memory flushed) before it touches global memory.  Both are no-ops for a launch made without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
 // scalar maths
@@ -373,7 +384,7 @@ __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long lo
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (active) {
     if (ou_on) { V4<R> q = ld4(p.state, p.n, p.row_ou, i); s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
-    if (p.row_act >= 0) { V4<R> q = ld4(p.state, p.n, p.row_act, i); s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+    if (!T::PLAIN && p.row_act >= 0) { V4<R> q = ld4(p.state, p.n, p.row_act, i); s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
     if (T::RARE) {
       if (p.row_gyro >= 0) { V4<R> q = ld4(p.state, p.n, p.row_gyro, i); s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; }
       if (p.row_goal >= 0) { V4<R> q = ld4(p.state, p.n, p.row_goal, i); s.gx = q.x; s.gy = q.y; s.gz = q.z; }
@@ -411,7 +422,7 @@ __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, 
 #endif
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (ou_on) st4(p.state, p.n, p.row_ou, i, s.ou[0], s.ou[1], s.ou[2], s.ou[3]);
-  if (p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
+  if (!T::PLAIN && p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
   if (T::RARE) {
     if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0));
     // the goal row is read-only for the step path
@@ -693,7 +704,7 @@ __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, 
   R r_eff = q_sqrt<R, T::FASTM>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
   R c_eff = p.c_effort * r_eff;
   R r_ac = R(0), c_ac = R(0);
-  if (all || p.c_act_change != R(0)) {                                  // :556-558
+  if (all || (!T::PLAIN && p.c_act_change != R(0))) {                   // :556-558
     R e0 = a[0] - a_prev[0], e1 = a[1] - a_prev[1], e2 = a[2] - a_prev[2], e3 = a[3] - a_prev[3];
     r_ac = Mth<R>::sqrt(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
     c_ac = p.c_act_change * r_ac;
@@ -789,28 +800,32 @@ __device__ __forceinline__ void rot2quat(const R* r, R* q) {            // senso
 
 template <typename R, class T>
 __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const NoiseSrc<R, T>& ns, bool reset_obs,
-                                          const R* act_prev, R* o) {
+                                          const R* act_prev, R* o, const R* zpre = nullptr) {
   const bool sense = T::SENSE >= 0 ? (T::SENSE != 0) : (p.sense_on != 0);
   R px = s.px, py = s.py, pz = s.pz, vx = s.vx, vy = s.vy, vz = s.vz, wx = s.wx, wy = s.wy, wz = s.wz;
   R rr[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) rr[k] = s.r[k];
   R acc[3] = {R(0), R(0), R(0)};
-  if (p.obs_acc) accelerometer(s, p, acc);
+  const bool obs_acc = !T::PLAIN && p.obs_acc, obs_rel = !T::PLAIN && p.obs_rel;
+  if (obs_acc) accelerometer(s, p, acc);
   if (sense) {
     R z[3];
+    if (zpre) { z[0] = zpre[0]; z[1] = zpre[1]; z[2] = zpre[2]; } else
     ns.obs3(reset_obs, 0, false, z);                                    // :116-118
     px += p.sn_pos_std * z[0]; py += p.sn_pos_std * z[1]; pz += p.sn_pos_std * z[2];
     if (T::RARE && p.sn_pos_unif != R(0)) {
       ns.obs3(reset_obs, 1, true, z);
       px += p.sn_pos_unif * z[0]; py += p.sn_pos_unif * z[1]; pz += p.sn_pos_unif * z[2];
     }
+    if (zpre) { z[0] = zpre[3]; z[1] = zpre[4]; z[2] = zpre[5]; } else
     ns.obs3(reset_obs, 2, false, z);                                    // :122-124
     vx += p.sn_vel_std * z[0]; vy += p.sn_vel_std * z[1]; vz += p.sn_vel_std * z[2];
     if (T::RARE && p.sn_vel_unif != R(0)) {
       ns.obs3(reset_obs, 3, true, z);
       vx += p.sn_vel_unif * z[0]; vy += p.sn_vel_unif * z[1]; vz += p.sn_vel_unif * z[2];
     }
+    if (zpre) { z[0] = zpre[6]; z[1] = zpre[7]; z[2] = zpre[8]; } else
     ns.obs3(reset_obs, 4, false, z);
     if (T::RARE && p.gyro_bias_mode) {                                  // :127-128, :162-170 (walk folded over the calls)
       R pi_ = reset_obs ? p.gb_pi1 : p.gb_pi3, sg = reset_obs ? p.gb_sig1 : p.gb_sig3;
@@ -847,7 +862,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     rr[0] = R(1) - R(2) * qy * qy - R(2) * qz * qz; rr[1] = R(2) * qx * qy - R(2) * qz * qw; rr[2] = R(2) * qx * qz + R(2) * qy * qw;
     rr[3] = R(2) * qx * qy + R(2) * qz * qw; rr[4] = R(1) - R(2) * qx * qx - R(2) * qz * qz; rr[5] = R(2) * qy * qz - R(2) * qx * qw;
     rr[6] = R(2) * qx * qz - R(2) * qy * qw; rr[7] = R(2) * qy * qz + R(2) * qx * qw; rr[8] = R(1) - R(2) * qx * qx - R(2) * qy * qy;
-    if (p.obs_acc) {                                                    // :156-157
+    if (obs_acc) {                                                      // :156-157
       R zs[3], zd[3];
       ns.obs3(reset_obs, 8, false, zs);
       ns.obs3(reset_obs, 9, false, zd);
@@ -856,7 +871,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     }
   }
   R ex = px - s.gx, ey = py - s.gy, ez = pz - s.gz;                     // get_state.py:15
-  if (p.obs_rel) {                                                      // get_state.py:159-160 (true R)
+  if (obs_rel) {                                                        // get_state.py:159-160 (true R)
     R tx = s.r[0] * ex + s.r[3] * ey + s.r[6] * ez, ty = s.r[1] * ex + s.r[4] * ey + s.r[7] * ez;
     R tz = s.r[2] * ex + s.r[5] * ey + s.r[8] * ez;
     ex = tx; ey = ty; ez = tz;
@@ -875,10 +890,11 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
 }
 
 // writes one env's observation row into the CTA's shared tile in final [obs_dim] order
-template <typename R>
+template <typename R, bool PLAIN = false>
 __device__ __forceinline__ void obs_to_tile(const Params<R>& p, const R* o, R* row) {
 #pragma unroll
   for (int k = 0; k < 18; ++k) row[k] = o[k];
+  if (PLAIN) return;
   int n = 18;
   if (p.obs_h) row[n++] = o[18];
   if (p.obs_acc) { row[n] = o[19]; row[n + 1] = o[20]; row[n + 2] = o[21]; n += 3; }
@@ -1038,9 +1054,25 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
   bool done_any = false;
   double st_ret = 0.0, st_ret2 = 0.0, st_n = 0.0;
 
+  const int k_steps = T::PLAIN ? 1 : p.k_steps;
+  const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+  const bool sense = T::SENSE >= 0 ? (T::SENSE != 0) : (p.sense_on != 0);
 #pragma unroll 1
-  for (int ks = 0; ks < p.k_steps; ++ks) {
+  for (int ks = 0; ks < k_steps; ++ks) {
     ns.begin_step(step0 + (unsigned long long)ks);
+    // Known sim_steps: every draw of the step depends only on (env id, step index), so generate them up front - the
+    // Philox / Box-Muller chains then overlap the state loads still in flight and each other instead of sitting on
+    // the dynamics' critical path.
+    constexpr int NPRE = T::SIM > 0 ? T::SIM : 1;
+    R zou[NPRE][4];
+    R zobs[9];
+    if (T::SIM > 0) {
+      if (ou_on) {
+#pragma unroll
+        for (int sub = 0; sub < NPRE; ++sub) ns.ou(sub, zou[sub]);
+      }
+      if (T::PLAIN && sense) { ns.obs3(false, 0, false, zobs); ns.obs3(false, 2, false, zobs + 3); ns.obs3(false, 4, false, zobs + 6); }
+    }
     // ---- action (:943-944) ----
     R a[4] = {R(0), R(0), R(0), R(0)};
     if (a_first != nullptr && ks == 0) {
@@ -1057,13 +1089,20 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // ---- controller + dynamics (:966-970, :261-262) ----
     R cmd[4];
     controller_cmds<R, T>(s, p, ctrl, a, cmd);
+    if (T::SIM > 0) {
+#pragma unroll
+      for (int sub = 0; sub < NPRE; ++sub) {
+        const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);        // :381-386
+        substep<R, T>(s, cmd, p, zou[sub], fire);
+      }
+    } else {
 #pragma unroll 1
-    for (int sub = 0; sub < p.sim_steps; ++sub) {
-      const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);          // :381-386
-      R z[4] = {R(0), R(0), R(0), R(0)};
-      const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
-      if (ou_on) ns.ou(sub, z);
-      substep<R, T>(s, cmd, p, z, fire);
+      for (int sub = 0; sub < p.sim_steps; ++sub) {
+        const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);        // :381-386
+        R z[4] = {R(0), R(0), R(0), R(0)};
+        if (ou_on) ns.ou(sub, z);
+        substep<R, T>(s, cmd, p, z, fire);
+      }
     }
     bool collided = false;
     if (T::RARE) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
@@ -1079,7 +1118,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     done_any = done_any || done;
 #pragma unroll
     for (int k = 0; k < 4; ++k) s.pa[k] = a[k];                         // becomes actions[1] of the next step
-    const bool last = (ks == p.k_steps - 1);
+    const bool last = (ks == k_steps - 1);
     if (T::RARE) {
       if (p.info != nullptr && last && active) {
         R* inf = p.info + i * INFO_DIM;
@@ -1099,7 +1138,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----
     const bool walk = T::RARE && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
     const bool resetting = done && p.auto_reset;
-    if ((last && !resetting) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o);
+    if ((last && !resetting) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o, (T::SIM > 0 && T::PLAIN && sense) ? zobs : nullptr);
     if (done) {
       if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
       if (resetting) {
@@ -1246,16 +1285,67 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
   const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
   const bool has_act = p.actions != nullptr;
   const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
-  const int obs_tile_floats = BLOCK * p.obs_dim;                         // per stage
+  const int obs_dim = T::PLAIN ? 18 : p.obs_dim;
+  const int obs_tile_floats = BLOCK * obs_dim;                           // per stage
   float4* in = reinterpret_cast<float4*>(smem_raw);
   float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4));
   const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
   const long long G = gridDim.x;
   const bool multi = n_tiles > G;                                        // more tiles than resident CTAs
 
+  __shared__ unsigned int warps_done;
+  if (!multi) {
+    if (tid == 0) warps_done = 0u;
+    __syncthreads();
+  }
+  pdl_launch_dependents();                       // the next launch may start its prologue; it waits below for our completion
+  pdl_wait();                                    // everything before this line touched no global memory
+
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
   double svd_end = svd_t0;
+
+  if (!multi) {
+    // ---- one-wave launch (small N): latency-bound, so no CTA barrier anywhere: direct vector loads, every warp
+    // transposes and ships its own 32 observation rows, the last warp to finish takes the CTA's launch ticket ----
+    const long long i = p.begin + (long long)blockIdx.x * BLOCK + tid;
+    const bool active = i < p.end;
+    St<R> s;
+    R a0[4] = {0.f, 0.f, 0.f, 0.f};
+    load_state<R, T>(s, p, i, active);
+    if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
+    R o[26];
+    StepOut<R> out;
+    run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out);
+    if (active) {
+      store_state<R, T>(s, p, i);
+      p.rew[i] = out.rew_sum;
+      p.done[i] = out.done_any ? 1 : 0;
+    }
+    float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
+    obs_to_tile<R, T::PLAIN>(p, o, wtile + lane * obs_dim);
+    __syncwarp();
+    const long long warp_first = i - lane;
+    long long rows = p.end - warp_first;
+    if (rows > 32) rows = 32;
+    if (rows > 0) {
+      const int total = (int)rows * obs_dim;
+      float* dst = p.obs + warp_first * obs_dim;               // 128 * obs_dim bytes per full warp: 16-byte aligned
+      if ((total & 3) == 0) {
+        const float4* t4 = reinterpret_cast<const float4*>(wtile);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int k = lane; k < (total >> 2); k += 32) d4[k] = t4[k];
+      } else {
+        for (int k = lane; k < total; k += 32) dst[k] = wtile[k];
+      }
+    }
+    if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&warps_done, 1u) == WARPS - 1) finish_launch_one(p, out.svd_t, (unsigned long long)p.k_steps);
+    }
+    return;
+  }
 
   auto issue_load = [&](long long tile, int stage) {
     const long long first = p.begin + tile * BLOCK;
@@ -1315,7 +1405,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       init_optional(s, p);
       const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
       if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
-      if (p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+      if (!T::PLAIN && p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
       if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
       finish_load(s);
       __syncwarp();
@@ -1342,7 +1432,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     }
     // observation rows: registers -> shared tile -> one bulk store per CTA
     float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
-    obs_to_tile(p, o, tile_obs + tid * p.obs_dim);
+    obs_to_tile<R, T::PLAIN>(p, o, tile_obs + tid * obs_dim);
     if (multi) {
       fence_proxy_async();                       // generic-proxy tile writes -> async proxy
       if (tid == 0) bulk_wait_read0();           // last tile's store has drained the OTHER stage (it had a whole tile)
@@ -1350,9 +1440,9 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     __syncthreads();                             // tile complete; also keeps the warps' 512-byte row segments adjacent in time
     long long rows = p.end - block_first;
     if (rows > BLOCK) rows = BLOCK;
-    const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)p.obs_dim * 4u;
+    const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)obs_dim * 4u;
     if (multi && (obs_bytes & 15u) == 0u) {
-      if (tid == 0) { bulk_s2g(p.obs + block_first * p.obs_dim, tile_obs, obs_bytes); bulk_commit(); }
+      if (tid == 0) { bulk_s2g(p.obs + block_first * obs_dim, tile_obs, obs_bytes); bulk_commit(); }
     } else {
       flush_tile(p, tile_obs, block_first, nullptr);                     // one-wave launch, or ragged last tile
     }
@@ -1454,8 +1544,14 @@ template <typename R> cudaError_t launch_step(const Params<R>& p, cudaStream_t s
 template <typename R> cudaError_t launch_reset(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_dynamics(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_clock_advance(const Params<R>& p, cudaStream_t st);
-// fp32 fast subset (qs_fast.inl)
-cudaError_t launch_fast_philox(const Params<float>& p, cudaStream_t st, const char** variant_name);
-cudaError_t launch_fast_inject(const Params<float>& p, cudaStream_t st, const char** variant_name);
+// fp32 fast subset (qs_fast.inl, one translation unit per controller x noise source)
+#define QS_DECL_FAST(name) cudaError_t name(const Params<float>& p, cudaStream_t st, const char** variant_name)
+QS_DECL_FAST(launch_fast_raw_philox);
+QS_DECL_FAST(launch_fast_raw_inject);
+QS_DECL_FAST(launch_fast_omega_philox);
+QS_DECL_FAST(launch_fast_omega_inject);
+QS_DECL_FAST(launch_fast_mellinger_philox);
+QS_DECL_FAST(launch_fast_mellinger_inject);
+#undef QS_DECL_FAST
 
 }  // namespace qs

@@ -30,26 +30,41 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   long long slots = (long long)sm_count() * per_sm;
   const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-  env_step_tma_kernel<T><<<grid, BLOCK, smem, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(BLOCK);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T>, p);
 }
 
+template <int C, int SIM, bool PLAIN>
+static cudaError_t launch_fast_cs(const Params<float>& p, cudaStream_t st) {
+  if (p.ou_on) {
+    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
+    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
+  }
+  if (p.sense_on) return launch_tma_t<Traits<C, 0, 1, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
+  return launch_tma_t<Traits<C, 0, 0, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
+}
+
+// the common shape (sim_steps = 2, one env step per launch, plain 18-word observation, no previous-action row) gets
+// fully specialised kernels; everything else in the fast subset takes the run-time-parameterised twins
 template <int C>
 static cudaError_t launch_fast_c(const Params<float>& p, cudaStream_t st) {
-  if (p.ou_on) {
-    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, false> >(p, st);
-    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, false> >(p, st);
-  }
-  if (p.sense_on) return launch_tma_t<Traits<C, 0, 1, QS_FAST_INJECT != 0, false> >(p, st);
-  return launch_tma_t<Traits<C, 0, 0, QS_FAST_INJECT != 0, false> >(p, st);
+  const bool plain = p.sim_steps == 2 && p.k_steps == 1 && p.obs_dim == 18 && !p.obs_rel && p.row_act < 0;
+  if (plain) return launch_fast_cs<C, 2, true>(p, st);
+  return launch_fast_cs<C, -1, false>(p, st);
 }
 
 cudaError_t QS_FAST_NAME(const Params<float>& p, cudaStream_t st, const char** name) {
-  switch (p.controller) {
-    case CTRL_RAW: if (name) *name = "tma-raw" QS_FAST_SUFFIX; return launch_fast_c<CTRL_RAW>(p, st);
-    case CTRL_OMEGA_THRUST: if (name) *name = "tma-omega-thrust" QS_FAST_SUFFIX; return launch_fast_c<CTRL_OMEGA_THRUST>(p, st);
-    default: if (name) *name = "tma-mellinger" QS_FAST_SUFFIX; return launch_fast_c<CTRL_MELLINGER>(p, st);
-  }
+  if (name) *name = QS_FAST_LABEL QS_FAST_SUFFIX;
+  return launch_fast_c<QS_FAST_CTRL>(p, st);
 }
 
 }  // namespace qs

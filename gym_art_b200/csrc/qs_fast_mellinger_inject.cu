@@ -1,0 +1,7 @@
+// fp32 fast subset, controller mellinger, inject noise (one translation unit per controller x noise source: they compile in parallel)
+#define QS_FAST_INJECT 1
+#define QS_FAST_CTRL qs::CTRL_MELLINGER
+#define QS_FAST_LABEL "tma-mellinger"
+#define QS_FAST_NAME launch_fast_mellinger_inject
+#define QS_FAST_SUFFIX "-injected"
+#include "qs_fast.inl"

@@ -21,7 +21,9 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
 #ifdef QS_FAST_VARIANTS
   if (!p.need_rare && p.act_dim == 4 &&
       (p.controller == CTRL_RAW || p.controller == CTRL_OMEGA_THRUST || p.controller == CTRL_MELLINGER)) {
-    return p.inject ? launch_fast_inject(p, st, name) : launch_fast_philox(p, st, name);
+    if (p.controller == CTRL_RAW) return p.inject ? launch_fast_raw_inject(p, st, name) : launch_fast_raw_philox(p, st, name);
+    if (p.controller == CTRL_OMEGA_THRUST) return p.inject ? launch_fast_omega_inject(p, st, name) : launch_fast_omega_philox(p, st, name);
+    return p.inject ? launch_fast_mellinger_inject(p, st, name) : launch_fast_mellinger_philox(p, st, name);
   }
 #endif
   if (p.inject) { if (name) *name = "generic-injected"; return launch_step_t<R, TGenInject>(p, st); }

@@ -35,7 +35,7 @@ struct QsHandle {
   qs::Clock* d_clock;        // device-resident {svd_timer, step}: steps stay CUDA-graph capturable
   unsigned int* d_ticket;    // [0]: clock ticket; [1 + 2k], [2 + 2k]: launch ticket and tile counter of launch slot k
   uint64_t launches;
-  int tile_sync;
+  int pdl;
   std::string err;
   const char* last_variant;
   // qs_step_host scratch (library-owned)
@@ -153,7 +153,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.need_rare = need_rare(h) ? 1 : 0;
   p.tma_rows = h->lay.rows;
   p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
-  p.tile_sync = h->tile_sync;
+  p.pdl = h->pdl;
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
@@ -211,6 +211,7 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
   fill_params<R>(h, &p);
   p.k_steps = k;
   p.clock_advance = advance;
+  if (!advance) p.pdl = 0;                       // chunk launches of the host pipeline follow copies on side streams
   p.launch_ticket = h->d_ticket + 1 + 2 * slot;
   p.tile_counter = h->d_ticket + 2 + 2 * slot;
   p.actions = (const R*)actions; p.obs = (R*)obs; p.rew = (R*)rew; p.done = done;
@@ -257,7 +258,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->ou_z = h->obs_z = h->reset_z = nullptr;
   h->d_stats = nullptr; h->d_status = nullptr; h->d_clock = nullptr; h->d_ticket = nullptr;
   h->launches = 0;
-  { const char* e = getenv("QUADSIM_TILE_SYNC"); h->tile_sync = e ? atoi(e) : 1; }   // tuning knob, default on
+  { const char* e = getenv("QUADSIM_PDL"); h->pdl = e ? atoi(e) : 1; }   // A/B knob: programmatic dependent launch, default on
   h->last_variant = "";
   h->host_ready = false;
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
