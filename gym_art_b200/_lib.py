@@ -64,7 +64,8 @@ class QsConfig(C.Structure):
                 ("dim_mode", C.c_int32), ("sim_steps", C.c_int32), ("ep_len", C.c_int32), ("per_env_goal", C.c_int32),
                 ("_pad", C.c_int32), ("dt", C.c_double), ("svd_period", C.c_double), ("goal", C.c_double * 3),
                 ("spawn_box", C.c_double), ("spawn_z_min", C.c_double), ("room_box", (C.c_double * 3) * 2), ("max_init_vel", C.c_double),
-                ("max_init_omega", C.c_double), ("collision_k", C.c_double), ("model", QsModel), ("reward", QsReward),
+                ("max_init_omega", C.c_double), ("collision_k", C.c_double), ("use_formation", C.c_int32), ("_pad2", C.c_int32),
+                ("formation", (C.c_double * 3) * 32), ("model", QsModel), ("reward", QsReward),
                 ("sense", QsSensorNoise)]
 
 

@@ -79,6 +79,8 @@ struct Params {
   R jinv[4][4];
   R room_lo[3], room_hi[3];
   R goal[3], spawn_box, spawn_z_min, max_init_vel, max_init_omega, coll_dist;
+  int formation_on;
+  R formation[32][3];                  // swarm: goal of drone a of every swarm
   // reward
   R c_pos, c_effort, c_act_change, c_crash, c_orient, c_yaw, c_rot, c_attitude, c_spin, c_vel;
   R c_pos_offset, c_pos_log_w, c_pos_lin_w, c_collision;
@@ -90,8 +92,9 @@ struct Params {
 };
 
 // compile-time specialisation knobs; -1 = decided at run time from Params
-template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_, int SIM_ = -1, bool PLAIN_ = false>
+template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_, int SIM_ = -1, bool PLAIN_ = false, bool SWARM_ = false>
 struct Traits {
+  static constexpr bool SWARM = SWARM_ || RARE_;   // n_agents > 1 handled: contact stage, formation goals, log-distance reward
   static constexpr int CTRL = CTRL_;
   static constexpr int SIM = SIM_;      // compile-time sim_steps (substep loop unrolled, OU draws hoisted), -1 = run time
   static constexpr bool PLAIN = PLAIN_; // one env step per launch, 18-word observation, no previous-action row
@@ -346,12 +349,18 @@ __device__ __forceinline__ void default_core(St<R>& s) {   // lanes beyond the l
   s.tick = R(0); s.ret = R(0);
 }
 
-template <typename R>
+template <typename R, bool SWARM = true>
 __device__ __forceinline__ void init_optional(St<R>& s, const Params<R>& p) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) { s.ou[k] = R(0); s.pa[k] = R(0); }
   s.gb[0] = s.gb[1] = s.gb[2] = R(0);
   s.gx = p.goal[0]; s.gy = p.goal[1]; s.gz = p.goal[2];
+  if (SWARM) {
+    if (p.formation_on) {                     // launches start on a multiple of BLOCK, and n_agents divides 32
+      const int a = (int)threadIdx.x & (p.n_agents - 1);
+      s.gx = p.formation[a][0]; s.gy = p.formation[a][1]; s.gz = p.formation[a][2];
+    }
+  }
 }
 
 template <typename R>
@@ -380,7 +389,7 @@ __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long lo
   } else {
     default_core(s);
   }
-  init_optional(s, p);
+  init_optional<R, T::SWARM>(s, p);
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (active) {
     if (ou_on) { V4<R> q = ld4(p.state, p.n, p.row_ou, i); s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
@@ -699,7 +708,7 @@ __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, 
   R dx = s.gx - s.px, dy = s.gy - s.py, dz = s.gz - s.pz;
   R dist = q_sqrt<R, T::FASTM>(dx * dx + dy * dy + dz * dz);
   R r_pos = dist;                                                       // :547-549
-  if (T::RARE && p.log_pos) r_pos = p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist;   // multi :554
+  if (T::SWARM && p.log_pos) r_pos = p.c_pos_log_w * Mth<R>::log(dist + p.c_pos_offset) + p.c_pos_lin_w * dist;   // multi :554
   R c_pos = p.c_pos * r_pos;
   R r_eff = q_sqrt<R, T::FASTM>(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3]);   // :553-554
   R c_eff = p.c_effort * r_eff;
@@ -724,7 +733,7 @@ __device__ __forceinline__ R compute_reward(const St<R>& s, const Params<R>& p, 
   R c_crash = crashed ? p.c_crash : R(0);                               // :590-591
   R sum = ((c_pos + c_eff) + (c_crash + c_or)) + ((c_yaw + c_rot) + (c_att + c_spin));            // np.sum pairwise
   sum = (sum + c_ac) + c_vel;                                           // :593-604
-  if (T::RARE) { if (collided) sum += p.c_collision; }
+  if (T::SWARM) { if (collided) sum += p.c_collision; }
   if (costs) {                                                          // rew_info order (:607-631): weighted, then raw
     costs[0] = c_pos; costs[1] = c_eff; costs[2] = c_crash; costs[3] = c_or; costs[4] = c_yaw;
     costs[5] = c_rot; costs[6] = c_att; costs[7] = c_spin; costs[8] = c_ac; costs[9] = c_vel;
@@ -1105,7 +1114,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
       }
     }
     bool collided = false;
-    if (T::RARE) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
+    if (T::SWARM) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
     // ---- crash, reward, tick, done (:974-987) ----
     bool crashed = s.pz <= p.arm;                                       // :977
     R costs[20];
@@ -1402,7 +1411,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       // lanes beyond the last env of a ragged tile read stale shared memory: harmless, nothing of theirs is stored
       const float4* buf = in + (size_t)stage * stage_vecs + tid;
       unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
-      init_optional(s, p);
+      init_optional<R, T::SWARM>(s, p);
       const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
       if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
       if (!T::PLAIN && p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }

@@ -43,14 +43,14 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T>, p);
 }
 
-template <int C, int SIM, bool PLAIN>
+template <int C, int SIM, bool PLAIN, bool SWARM>
 static cudaError_t launch_fast_cs(const Params<float>& p, cudaStream_t st) {
   if (p.ou_on) {
-    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
-    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
+    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, false, SIM, PLAIN, SWARM> >(p, st);
+    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, false, SIM, PLAIN, SWARM> >(p, st);
   }
-  if (p.sense_on) return launch_tma_t<Traits<C, 0, 1, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
-  return launch_tma_t<Traits<C, 0, 0, QS_FAST_INJECT != 0, false, SIM, PLAIN> >(p, st);
+  if (p.sense_on) return launch_tma_t<Traits<C, 0, 1, QS_FAST_INJECT != 0, false, SIM, PLAIN, SWARM> >(p, st);
+  return launch_tma_t<Traits<C, 0, 0, QS_FAST_INJECT != 0, false, SIM, PLAIN, SWARM> >(p, st);
 }
 
 // the common shape (sim_steps = 2, one env step per launch, plain 18-word observation, no previous-action row) gets
@@ -58,8 +58,13 @@ static cudaError_t launch_fast_cs(const Params<float>& p, cudaStream_t st) {
 template <int C>
 static cudaError_t launch_fast_c(const Params<float>& p, cudaStream_t st) {
   const bool plain = p.sim_steps == 2 && p.k_steps == 1 && p.obs_dim == 18 && !p.obs_rel && p.row_act < 0;
-  if (plain) return launch_fast_cs<C, 2, true>(p, st);
-  return launch_fast_cs<C, -1, false>(p, st);
+  const bool swarm = p.n_agents > 1 || p.log_pos;      // the host only routes these here when k_steps == 1 and plain
+  if (swarm) {
+    if (!plain) return cudaErrorInvalidValue;
+    return launch_fast_cs<C, 2, true, true>(p, st);
+  }
+  if (plain) return launch_fast_cs<C, 2, true, false>(p, st);
+  return launch_fast_cs<C, -1, false, false>(p, st);
 }
 
 cudaError_t QS_FAST_NAME(const Params<float>& p, cudaStream_t st, const char** name) {

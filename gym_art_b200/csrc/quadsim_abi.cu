@@ -80,6 +80,7 @@ int validate(const QsConfig* c, std::string* why) {
   if (!(c->dt > 0.0)) { *why = "dt must be positive"; return QS_EINVAL; }
   if (c->n_agents < 1 || c->n_agents > 32 || !is_pow2(c->n_agents)) { *why = "n_agents must be 1, 2, 4, 8, 16 or 32"; return QS_EINVAL; }
   if (c->n_envs % c->n_agents != 0) { *why = "n_envs must be a multiple of n_agents"; return QS_EINVAL; }
+  if (c->use_formation && c->per_env_goal) { *why = "use_formation and per_env_goal are mutually exclusive"; return QS_EINVAL; }
   if (!(c->model.mass > 0.0) || !(c->model.inertia[0] > 0.0) || !(c->model.inertia[1] > 0.0) || !(c->model.inertia[2] > 0.0)) {
     *why = "model mass/inertia must be positive"; return QS_EINVAL;
   }
@@ -110,7 +111,11 @@ bool need_rare(const QsHandle* h) {
   if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) return true;
   if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
                     s.gyro_norm_std != 0.0)) return true;
-  if (c.reward.log_pos || c.n_agents > 1 || c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
+  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
+  // swarms (and the log-distance reward that comes with them) have specialised kernels for the common step shape only
+  const bool plain = c.sim_steps == 2 && h->lay.obs_dim == 18 && h->lay.row_prev_action < 0 &&
+                     c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA;
+  if ((c.n_agents > 1 || c.reward.log_pos) && !plain) return true;
   return false;
 }
 
@@ -183,6 +188,9 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.arm = (R)m.arm; p.omega_max = (R)m.omega_max; p.gravity = (R)m.gravity; p.t2w = (R)m.thrust_to_weight;
   p.spawn_box = (R)c.spawn_box; p.spawn_z_min = (R)c.spawn_z_min; p.max_init_vel = (R)c.max_init_vel; p.max_init_omega = (R)c.max_init_omega;
   p.coll_dist = (R)(c.collision_k * 2.0 * m.arm);
+  p.formation_on = (c.use_formation && c.n_agents > 1) ? 1 : 0;
+  for (int a = 0; a < 32; ++a)
+    for (int k = 0; k < 3; ++k) p.formation[a][k] = (R)c.formation[a][k];
   const QsReward& r = c.reward;
   p.c_pos = (R)r.pos; p.c_effort = (R)r.effort; p.c_act_change = (R)r.action_change; p.c_crash = (R)r.crash;
   p.c_orient = (R)r.orient; p.c_yaw = (R)r.yaw; p.c_rot = (R)r.rot; p.c_attitude = (R)r.attitude; p.c_spin = (R)r.spin;
@@ -211,6 +219,7 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
   fill_params<R>(h, &p);
   p.k_steps = k;
   p.clock_advance = advance;
+  if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos)) p.need_rare = 1;   // specialised swarm kernels: k == 1 only
   if (!advance) p.pdl = 0;                       // chunk launches of the host pipeline follow copies on side streams
   p.launch_ticket = h->d_ticket + 1 + 2 * slot;
   p.tile_counter = h->d_ticket + 2 + 2 * slot;

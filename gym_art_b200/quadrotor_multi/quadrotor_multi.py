@@ -61,14 +61,18 @@ class QuadrotorEnvMulti(object):
         E, M = self.num_envs, self.num_agents
         if goals is None:
             goals = ring_goals(M, goal_radius)
-        goals = np.broadcast_to(np.asarray(goals, dtype=np.float64).reshape(-1, M, 3), (E, M, 3)).reshape(E * M, 3).copy()
+        goals = np.asarray(goals, dtype=np.float64)
+        # one formation shared by every swarm lives in the kernel's constant block; per-swarm goals need a state row
+        formation = goals.reshape(M, 3) if goals.size == M * 3 else None
+        goals = np.broadcast_to(goals.reshape(-1, M, 3), (E, M, 3)).reshape(E * M, 3).copy()
         if isinstance(dynamics_params, str):
             dynamics_params = _ALIASES.get(dynamics_params, dynamics_params)
         self.vec = QuadVecEnv(E * M, dynamics_params=dynamics_params, raw_control=raw_control,
                               raw_control_zero_middle=raw_control_zero_middle, sim_freq=sim_freq, sim_steps=sim_steps,
                               obs_repr=obs_repr, ep_time=ep_time, room_size=room_size, init_random_state=init_random_state,
                               rew_coeff=rew_coeff, sense_noise=sense_noise, device=device, dtype=dtype, seed=seed,
-                              noise_mode=noise_mode, auto_reset=auto_reset, n_agents=M, goals=goals,
+                              noise_mode=noise_mode, auto_reset=auto_reset, n_agents=M,
+                              goals=None if formation is not None else goals, formation=formation,
                               multi_reward=multi_reward, collision_k=collision_k, info=info)
         self.goals = goals.reshape(E, M, 3)
         self.obs_dim, self.act_dim, self.ep_len, self.dt = self.vec.obs_dim, self.vec.act_dim, self.vec.ep_len, self.vec.dt

@@ -66,7 +66,7 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
                 sim_steps=2, obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10, init_random_state=False,
                 rew_coeff=None, sense_noise=None, device_index=0, dtype="float32", seed=0, noise_mode="philox",
                 auto_reset=True, n_agents=1, per_env_goal=False, env_id_offset=0, multi_reward=False, collision_k=1.0,
-                goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi):
+                goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi, formation=None):
     """Pure host function (no GPU): ctor arguments -> QsConfig.  Raises the reference's ValueErrors."""
     cfg = _lib.QsConfig()
     cfg.abi_version = _lib.QS_ABI_VERSION
@@ -108,6 +108,14 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
     cfg.max_init_vel = float(max_init_vel)                                            # quadrotor.py:717
     cfg.max_init_omega = float(max_init_omega)                                        # quadrotor.py:718
     cfg.collision_k = float(collision_k)
+    if formation is not None:                                                         # swarm: goal of drone a = formation[a]
+        f = np.asarray(formation, dtype=np.float64).reshape(-1, 3)
+        if f.shape[0] != int(n_agents) or per_env_goal:
+            raise ValueError("formation must have one goal per agent and excludes per-env goals")
+        cfg.use_formation = 1
+        for a in range(f.shape[0]):
+            for k in range(3):
+                cfg.formation[a][k] = float(f[a, k])
     cfg.model = model.to_qs()
     rc = resolve_rew_coeff(rew_coeff, multi_reward)
     for k in ("pos", "effort", "action_change", "crash", "orient", "yaw", "rot", "attitude", "spin", "vel"):
@@ -141,7 +149,7 @@ class QuadVecEnv(object):
                  sense_noise=None, gravity=GRAV, device="cuda:0", dtype="float32", seed=0, noise_mode="philox",
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
-                 max_init_omega=2 * np.pi):
+                 max_init_omega=2 * np.pi, formation=None):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -167,7 +175,7 @@ class QuadVecEnv(object):
             device_index=dev_index, dtype=dtype, seed=seed, noise_mode=noise_mode, auto_reset=auto_reset,
             n_agents=n_agents, per_env_goal=goals is not None, env_id_offset=env_id_offset, multi_reward=multi_reward,
             collision_k=collision_k, goal=goal, box=box, spawn_z_min=spawn_z_min, max_init_vel=max_init_vel,
-            max_init_omega=max_init_omega)
+            max_init_omega=max_init_omega, formation=formation)
         self.layout = _lib.state_layout(self.cfg)
         self.num_envs = int(num_envs)
         self.n_agents = int(n_agents)

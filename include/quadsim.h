@@ -182,6 +182,9 @@ typedef struct QsConfig {
   double room_box[2][3];
   double max_init_vel, max_init_omega; /* quadrotor.py:717-718 */
   double collision_k;  /* swarm: contact when |p_i - p_j| < collision_k * 2 * arm */
+  int32_t use_formation; /* swarm: drone a of every swarm flies to formation[a] (no goal row in the state buffer) */
+  int32_t _pad2;
+  double formation[32][3];
   QsModel model;
   QsReward reward;
   QsSensorNoise sense;

@@ -8,7 +8,7 @@ from oracle import quadsim_oracle as qo
 pytestmark = pytest.mark.gpu
 
 
-def _pair(E, M, dtype, seed, **kw):
+def _pair(E, M, dtype, seed, info=True, formation=False, **kw):
     from gym_art_b200 import QuadVecEnv
     from gym_art_b200.quadrotor import quad_models
     from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
@@ -19,9 +19,10 @@ def _pair(E, M, dtype, seed, **kw):
     coll = base.pop("collision", 0.7)
     oe = qo.OracleVecEnv(params, E * M, controller=qo.CTRL_RAW, auto_reset=True, n_agents=M, goals=goals, box=0.5,
                          collision_coeff=coll, multi_reward=True, **base)
+    gk = dict(formation=ring_goals(M, radius=0.3)) if formation else dict(goals=goals)
     env = QuadVecEnv(E * M, dynamics_params=params, controller="raw", dtype=dtype, noise_mode="injected", auto_reset=True,
-                     n_agents=M, goals=goals, box=0.5, multi_reward=True, rew_coeff={"collision": coll}, info=True, seed=seed,
-                     **base)
+                     n_agents=M, box=0.5, multi_reward=True, rew_coeff={"collision": coll}, info=info, seed=seed,
+                     **gk, **base)
     return oe, env
 
 
@@ -87,6 +88,40 @@ def test_swarm_step_matches_oracle_fp32_per_step():
         assert err.max() < 1e-5, (t, err.max())
         assert np.max(np.abs(r.double().cpu().numpy() - ro)[ok]) < 1e-6
     assert hits > 0
+
+
+@pytest.mark.parametrize("M", [4, 8])
+def test_swarm_fast_kernel_matches_oracle_fp32(M):
+    """The specialised swarm variant of the TMA kernel (formation goals, no info buffer), per-step against the oracle;
+    E is large enough for the multi-tile (mbarrier pipeline) path of the persistent kernel."""
+    E, T = (148 * 4 * 128 * 2) // M + 3, 40
+    rng = np.random.RandomState(13 + M)
+    oe, env = _pair(E, M, "float32", 3, info=False, formation=True, ep_time=5)
+    n = E * M
+    rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+    env.set_noise(reset_z=rz)
+    env.reset()
+    oe.reset(reset_z=rz)
+    contacts = 0
+    for t in range(T):
+        for f, v in (("pos", oe.pos), ("vel", oe.vel), ("rot", oe.rot.reshape(n, 9)), ("omega", oe.omega),
+                     ("thrust_rot_damp", oe.rot_damp), ("thrust_cmds_damp", oe.cmds_damp), ("ou_state", oe.ou)):
+            env.set_field(f, v)
+        oe.pos, oe.vel, oe.omega = (env.get_field(k).double().cpu().numpy() for k in ("pos", "vel", "omega"))
+        oe.rot = env.get_field("rot").double().cpu().numpy()
+        oe.rot_damp, oe.cmds_damp, oe.ou = (env.get_field(k).double().cpu().numpy() for k in ("thrust_rot_damp", "thrust_cmds_damp", "ou_state"))
+        a = rng.uniform(-0.2, 0.4, (n, 4)).astype(np.float32).astype(np.float64)
+        ou_z = rng.standard_normal((n, 2, 4)).astype(np.float32).astype(np.float64)
+        env.set_noise(ou_z=ou_z)
+        o, r, d = env.step(a)
+        assert env.kernel_variant == "tma-raw-injected"
+        oo, ro, do = oe.step(a, ou_z=ou_z)
+        contacts += int(oe.collided.sum())
+        err = (np.abs(o.double().cpu().numpy() - oo) / np.maximum(np.abs(oo), 1.0)).max(axis=1)
+        rerr = np.abs(r.double().cpu().numpy() - ro)
+        bad = (err > 1e-5) | (rerr > 1e-6)              # only pairs within an ulp of the contact distance may differ
+        assert bad.mean() < 1e-4, (t, bad.sum(), err.max())
+    assert contacts > 100
 
 
 def test_swarm_facade_shapes_and_contact_flags():

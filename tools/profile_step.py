@@ -27,7 +27,9 @@ def main():
     elif a.config == "cfg5":
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="mellinger", **kw)
     else:
-        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", n_agents=8, **kw)
+        from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", n_agents=8, formation=ring_goals(8),
+                         **kw)
     # same-run yardstick: STREAM-style copy bandwidth of this very GPU (method of MEASURED_PEAKS.json)
     if a.copy:
         x = torch.empty(1 << 30, dtype=torch.bfloat16, device="cuda:0")
