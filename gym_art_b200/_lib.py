@@ -30,7 +30,7 @@ STATUS_NAMES = {QS_EINVAL: "QS_EINVAL", QS_ECUDA: "QS_ECUDA", QS_ENONFINITE: "QS
 # every symbol include/quadsim.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = ["qs_abi_version", "qs_state_layout", "qs_create", "qs_destroy", "qs_last_error", "qs_bind_state", "qs_bind_info",
            "qs_set_noise_injection", "qs_reset", "qs_step", "qs_step_k", "qs_dynamics_step", "qs_step_host", "qs_get_stats",
-           "qs_stats_device_ptr", "qs_check", "qs_get_clock", "qs_set_clock", "qs_launch_count", "qs_last_variant"]
+           "qs_stats_device_ptr", "qs_check", "qs_get_clock", "qs_set_clock", "qs_launch_count", "qs_last_variant", "qs_last_host_path"]
 
 
 class QsModel(C.Structure):
@@ -115,6 +115,7 @@ def load():
         "qs_set_clock": (C.c_int, [H, C.c_double, C.c_uint64, P]),
         "qs_launch_count": (C.c_int, [H, C.POINTER(C.c_uint64)]),
         "qs_last_variant": (C.c_char_p, [H]),
+        "qs_last_host_path": (C.c_char_p, [H]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

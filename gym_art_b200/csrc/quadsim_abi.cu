@@ -42,6 +42,9 @@ struct QsHandle {
   cudaStream_t hs[kHostStreams];
   cudaEvent_t hev[kHostStreams];
   bool host_ready;
+  int host_zero_copy;        // A/B knob QUADSIM_HOST_ZEROCOPY (default 1)
+  cudaStream_t zc_stream;
+  const char* last_host_path;
   void *h_act, *h_obs, *h_rew;
   uint8_t* h_done;
 };
@@ -62,6 +65,16 @@ int fail(QsHandle* h, int code, const char* fmt, const char* a = "") {
   } while (0)
 
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// device-side alias of a pinned host pointer (false for pageable memory)
+bool device_alias(const void* host, void** dev) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+  if (((uintptr_t)a.devicePointer) % 16 != 0) return false;
+  *dev = a.devicePointer;
+  return true;
+}
 
 int validate(const QsConfig* c, std::string* why) {
   if (!c) { *why = "cfg is NULL"; return QS_EINVAL; }
@@ -270,6 +283,9 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   { const char* e = getenv("QUADSIM_PDL"); h->pdl = e ? atoi(e) : 1; }   // A/B knob: programmatic dependent launch, default on
   h->last_variant = "";
   h->host_ready = false;
+  { const char* e = getenv("QUADSIM_HOST_ZEROCOPY"); h->host_zero_copy = e ? atoi(e) : 1; }
+  h->zc_stream = nullptr;
+  h->last_host_path = "";
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stats, 3 * sizeof(double));
@@ -296,6 +312,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
 int qs_destroy(QsHandle* h) {
   if (!h) return QS_EINVAL;
   cudaSetDevice(h->cfg.device);
+  if (h->zc_stream) cudaStreamDestroy(h->zc_stream);
   if (h->host_ready) {
     for (int k = 0; k < kHostStreams; ++k) { cudaStreamDestroy(h->hs[k]); cudaEventDestroy(h->hev[k]); }
     cudaFree(h->h_act); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
@@ -399,6 +416,23 @@ int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* re
   const long long n = h->cfg.n_envs;
   const size_t rs = h->cfg.dtype == QS_F32 ? sizeof(float) : sizeof(double);
   const int od = h->lay.obs_dim, ad = h->lay.act_dim;
+  // Pinned (cudaHostAlloc / cudaHostRegister) buffers are addressable from the device: one launch reads the actions
+  // and writes obs / reward / done straight across PCIe (coalesced 16-byte vectors and bulk stores), so there is no
+  // staging copy, no copy-engine hand-off and a single stream synchronisation per step.
+  if (h->host_zero_copy) {
+    void* d_act = nullptr; void* d_obs = nullptr; void* d_rew = nullptr; void* d_done = nullptr;
+    if ((!actions_host || device_alias(actions_host, &d_act)) && device_alias(obs_host, &d_obs) &&
+        device_alias(rew_host, &d_rew) && device_alias(done_host, &d_done)) {
+      if (!h->zc_stream) QS_CUDA(h, cudaStreamCreateWithFlags(&h->zc_stream, cudaStreamNonBlocking));
+      if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, d_act, d_obs, d_rew, (uint8_t*)d_done, h->zc_stream, 0, n, 1);
+      else rc = do_step<double>(h, 1, d_act, d_obs, d_rew, (uint8_t*)d_done, h->zc_stream, 0, n, 1);
+      if (rc != QS_OK) return rc;
+      QS_CUDA(h, cudaStreamSynchronize(h->zc_stream));
+      h->last_host_path = "zero-copy";
+      return QS_OK;
+    }
+  }
+  h->last_host_path = "staged";
   if (!h->host_ready) {
     for (int k = 0; k < kHostStreams; ++k) {
       QS_CUDA(h, cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
@@ -498,5 +532,7 @@ int qs_launch_count(const QsHandle* h, uint64_t* out) {
 }
 
 const char* qs_last_variant(const QsHandle* h) { return h ? h->last_variant : ""; }
+
+const char* qs_last_host_path(const QsHandle* h) { return h ? h->last_host_path : ""; }
 
 }  // extern "C"

@@ -388,6 +388,10 @@ class QuadVecEnv(object):
     def kernel_variant(self):
         return self.lib.qs_last_variant(self._h).decode()
 
+    @property
+    def host_path(self):
+        return self.lib.qs_last_host_path(self._h).decode()
+
     def state_dict(self):
         """Checkpoint: the state tensor plus the global clocks (SURVEY.md section 5 "Checkpoint / resume")."""
         t, s = self.clock

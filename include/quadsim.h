@@ -240,9 +240,9 @@ int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uin
  * reward/obs/tick.  controller = -1 passes `actions` straight through as normalized motor commands. */
 int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_substeps, qs_stream_t stream);
 
-/* Same contract as qs_step but with HOST buffers: H2D of the actions, the fused step, D2H of obs/rew/done,
- * pipelined in chunks over internal streams; returns after the results are in host memory.  Pinned host
- * memory gives full PCIe bandwidth; pageable memory works but is slower. */
+/* Same contract as qs_step but with HOST buffers; returns after the results are in host memory.  Pinned buffers
+ * (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()) are read and written by the step kernel directly
+ * across PCIe in one launch; pageable buffers go through a chunked H2D / kernel / D2H pipeline over internal streams. */
 int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* rew_host, uint8_t* done_host);
 
 /* Finished-episode statistics accumulated on the device: {sum of returns, sum of squared returns, episodes}.
@@ -264,6 +264,9 @@ int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count, qs_stream_t
 int qs_launch_count(const QsHandle* h, uint64_t* out);
 /* Name of the kernel variant the last step launched ("fast-raw", "generic-philox", ...): diagnostics. */
 const char* qs_last_variant(const QsHandle* h);
+/* How the last qs_step_host moved its data: "zero-copy" (pinned buffers, read / written by the kernel itself across
+ * PCIe) or "staged" (pageable buffers: chunked cudaMemcpyAsync pipeline). */
+const char* qs_last_host_path(const QsHandle* h);
 
 #ifdef __cplusplus
 }

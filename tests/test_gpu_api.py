@@ -137,18 +137,22 @@ def test_step_k_equals_k_steps():
         assert torch.equal(e1.state, e2.state) and e1.clock == e2.clock
 
 
-def test_step_host_equals_step():
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_equals_step(pinned):
+    """qs_step_host == qs_step: pinned buffers take the zero-copy launch, pageable ones the staged chunk pipeline."""
     import torch
-    n = 70000 + 5            # several chunks, ragged tail
+    n = 70000 + 5            # several chunks / tiles, ragged tail
     e1, e2 = _env(n, sense_noise="default"), _env(n, sense_noise="default")
     e1.reset(), e2.reset()
-    a_h = (torch.rand((n, 4)) * 2 - 1).pin_memory()
-    o_h = torch.empty((n, 18)).pin_memory()
-    r_h, d_h = torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    a_h = pin(torch.rand((n, 4)) * 2 - 1)
+    o_h = pin(torch.empty((n, 18)))
+    r_h, d_h = pin(torch.empty(n)), pin(torch.empty(n, dtype=torch.uint8))
     a_d = a_h.cuda()
     for _ in range(4):
         o, r, d = e1.step(a_d)
         e2.step_host(a_h, o_h, r_h, d_h)
+        assert e2.host_path == ("zero-copy" if pinned else "staged")
         assert torch.equal(o.cpu(), o_h) and torch.equal(r.cpu(), r_h) and torch.equal(d.cpu(), d_h.bool())
     assert e1.clock == e2.clock and torch.equal(e1.state, e2.state)
 
