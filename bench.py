@@ -155,11 +155,27 @@ def cpu_baseline(seconds=6.0, cores=None):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
-def make_env(n, device, seed, env_id_offset=0):
+def make_env(n, device, seed, env_id_offset=0, cfg="cfg2"):
     from gym_art_b200 import QuadVecEnv
-    return QuadVecEnv(n, dynamics_params="DefaultQuad", controller="raw", raw_control_zero_middle=True, sense_noise=None,
-                      obs_repr="xyz_vxyz_R_omega", ep_time=EP_TIME, sim_steps=SIM_STEPS, device=device, dtype="float32",
-                      seed=seed, noise_mode="philox", auto_reset=True, env_id_offset=env_id_offset)
+    kw = dict(obs_repr="xyz_vxyz_R_omega", ep_time=EP_TIME, sim_steps=SIM_STEPS, device=device, dtype="float32", seed=seed,
+              noise_mode="philox", auto_reset=True, env_id_offset=env_id_offset)
+    if cfg == "cfg2":      # Hummingbird RawControl, no sensor noise
+        return QuadVecEnv(n, dynamics_params="DefaultQuad", controller="raw", raw_control_zero_middle=True, sense_noise=None, **kw)
+    if cfg == "cfg3":      # CrazyFlie OmegaThrustControl + SensorNoise + random init
+        return QuadVecEnv(n, dynamics_params="Crazyflie", controller="omega_thrust", sense_noise="default",
+                          init_random_state=True, **kw)
+    if cfg == "cfg4":      # swarms of 8 Hummingbirds on a ring formation, pairwise contact
+        from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
+        return QuadVecEnv(n, dynamics_params="DefaultQuad", controller="raw", n_agents=8, formation=ring_goals(8), **kw)
+    if cfg == "cfg5":      # Hummingbird Mellinger closed loop (no action input)
+        return QuadVecEnv(n, dynamics_params="DefaultQuad", controller="mellinger", **kw)
+    raise ValueError(cfg)
+
+
+# (config, envs per GPU, algorithmic bytes per env step): the other BASELINE.json configs, timed briefly for context
+OTHER = (("cfg3", 1 << 20, 349), ("cfg4", 262144 * 8, 349), ("cfg5", 8 << 20, 333))
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/r1_ncu_*.txt)
+NCU_TRAFFIC = {N_BATCH: 9.5e6, N_LARGE: 1406.5e6}
 
 
 def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, per_chunk_hook=None, chunk=501):
@@ -282,6 +298,30 @@ def run_ours(args):
     big_achieved = N_LARGE * BYTES_PER_ENV_STEP / (ms_l * 1e-3 / KL) / 1e9
     variant = big.kernel_variant
     big.check_finite()
+    big.close()
+    del big, big_act
+    others = {}
+    for cfg, n_o, bytes_o in OTHER:
+        e = make_env(n_o, device, seed=3, env_id_offset=rank * n_o, cfg=cfg)
+        e.reset()
+        a_o = None
+        if cfg != "cfg5":
+            a_o = torch.rand((n_o, 4), device=device, generator=gen) * 2 - 1
+            if cfg == "cfg3":
+                a_o[:, 0] *= 0.2
+        RING_PERIOD[0] = 1
+        KO = 40
+        ms_o = time_graph(torch, lambda i: e.step(a_o), KO, 5, device, dist if multi else None, None)
+        to = torch.tensor([ms_o], device=device, dtype=torch.float64)
+        if multi:
+            dist.all_reduce(to, op=dist.ReduceOp.MAX)
+        ms_o = float(to.item())
+        e.check_finite()
+        others[cfg] = {"n_envs_per_gpu_step": n_o, "value": world * n_o * KO / (ms_o * 1e-3), "unit": "env-steps/s",
+                       "ms_per_step": ms_o / KO, "kernel_variant": e.kernel_variant, "bytes_per_env_step": bytes_o,
+                       "roofline_frac": n_o * bytes_o / (ms_o * 1e-3 / KO) / 1e9 / hbm_peak}
+        e.close()
+        del e, a_o
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through qs_step_host -------------------------------------------------------------------
@@ -316,19 +356,25 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_envs_per_gpu_step": N_BATCH, "sim_steps": SIM_STEPS, "substeps_per_s": value * SIM_STEPS,
                        "l2": "ring of %d independent batches, %.0f MB footprint > 126 MB L2, cycled" % (ring, ring_bytes / 1e6),
-                       "launch": "CUDA graph of qs_step launches (device-resident clock), one kernel per step",
+                       "launch": "CUDA graph of qs_step launches (device-resident clock, programmatic dependent launch), "
+                                 "one kernel per step",
                        "kernel_variant": variant, "parallelism": "env-index sharding x%d, no data-path collective" % world},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N_BATCH * 16,
                     "d2h_bytes_per_step": N_BATCH * (72 + 4 + 1), "steps": KE,
-                    "api": "qs_step_host (pinned host buffers, 4-chunk H2D/kernel/D2H pipeline)"},
+                    "api": "qs_step_host on pinned host tensors: the step kernel reads the actions and writes obs/reward/done "
+                           "across PCIe itself (%s)" % e0.host_path},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "traffic": NCU_TRAFFIC[N_BATCH], "traffic_source": "profiles/r1_ncu_cfg2_65536.txt (ncu replays a "
+                         "cold-L2 launch: the 23 MB working set is written back to L2 only, so DRAM sees the reads)",
+                         "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "note": "65,536-env launches are launch/latency-bound (23 MB per launch); see hbm_resident"},
             "hbm_resident": {"n_envs_per_gpu_step": N_LARGE, "steps": KL, "value": big_value, "unit": "env-steps/s",
                              "ms_per_step": ms_l / KL,
                              "roofline": {"bound": "hbm", "achieved": big_achieved, "peak": hbm_peak, "unit": "GB/s",
-                                          "frac": big_achieved / hbm_peak}},
+                                          "frac": big_achieved / hbm_peak, "traffic": NCU_TRAFFIC[N_LARGE],
+                                          "traffic_source": "profiles/r1_ncu_cfg2_4194304.txt"}},
+            "other_workloads": others,
             "clocks": clocks,
             "cpu_baseline": cpu,
         }

@@ -1349,8 +1349,8 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       }
     }
     if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
+    // (the clock was read at the top of every thread, and run_steps depended on the values: no fence needed here)
     if (lane == 0) {
-      __threadfence_block();
       if (atomicAdd(&warps_done, 1u) == WARPS - 1) finish_launch_one(p, out.svd_t, (unsigned long long)p.k_steps);
     }
     return;
