@@ -62,10 +62,20 @@ class QuadLink(object):
         arm_yaw = np.array([-1., 1., -1., 1.]) * self.arm_angle
         payload_z = np.sign(params["payload_pos"]["z_sign"]) * (body["h"] + payload["h"]) / 2
 
+        # a link gives its mass directly ("m") or through its material density (inertia.py:75-82, :98-99, :160-161):
+        # RandomQuad samples densities (quadrotor_randomization.py:155-164)
+        def box(d):
+            m = d["m"] if d.get("m") is not None else d["density"] * d["l"] * d["w"] * d["h"]
+            return m, box_inertia(d["l"], d["w"], d["h"], m)
+
+        def cyl(d):
+            m = d["m"] if d.get("m") is not None else d["density"] * np.pi * d["h"] * d["r"] ** 2
+            return m, cylinder_inertia(d["h"], d["r"], m)
+
+        parts = [box(body), box(payload)] + [box(arms)] * 4 + [cyl(motors)] * 4 + [cyl(props)] * 4
         # link table: mass, principal inertia, yaw, position
-        mass = [body["m"], payload["m"]] + [arms["m"]] * 4 + [motors["m"]] * 4 + [props["m"]] * 4
-        diag = [box_inertia(**body), box_inertia(**payload)] + [box_inertia(**arms)] * 4 + \
-               [cylinder_inertia(**motors)] * 4 + [cylinder_inertia(**props)] * 4
+        mass = [m for m, _ in parts]
+        diag = [I for _, I in parts]
         yaw = [0., 0.] + list(arm_yaw) + [0.] * 8
         pos = [np.zeros(3), np.array(list(params["payload_pos"]["xy"]) + [payload_z], dtype=np.float64)] + \
               list(arms_xyz) + list(motors_xyz) + list(props_xyz)

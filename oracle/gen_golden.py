@@ -9,6 +9,7 @@ noise tape (oracle/ref_shim.NoiseTape): configuration, the unit noise draws regr
 injected-noise slot layout of include/quadsim.h, the actions, and everything the reference
 returned or held after every step.  The fixtures travel to the GPU box; the reference does not.
 """
+import copy
 import json
 import os
 import sys
@@ -175,6 +176,36 @@ def model_answers():
     return out
 
 
+def random_models():
+    """Dynamics randomisation: parameter dicts and derived constants the live
+    reference produces under fixed np.random seeds - RandomQuad samples, RelativeSampler perturbations of the
+    CrazyFlie (normal and uniform), and the sample_* helpers."""
+    ref = rh.ref_shim.import_reference()
+    qr = ref.quad_rand
+    out, cases = {}, []
+    for seed in range(6):
+        np.random.seed(100 + seed)
+        cases.append(("randomquad_%d" % seed, qr.RandomQuad().sample()))
+    base = ref.quad_models.crazyflie_params()
+    for seed, (ratio, sampler) in enumerate(((0.2, "normal"), (0.3, "uniform"), (0.1, "normal"))):
+        np.random.seed(200 + seed)
+        rs = qr.RelativeSampler(params=copy.deepcopy(base), noise_ratio=ratio, sampler=sampler,
+                                noise_ratio_custom={"motor": {"linearity": 0.0}} if seed == 2 else None)
+        cases.append(("relative_%d" % seed, rs.sample(copy.deepcopy(base))))
+    np.random.seed(300)
+    p = qr.sample_t2w_t2t(qr.sample_linearity(qr.sample_nodelay(ref.quad_models.defaultquad_params())), 1.8, 2.5)
+    cases.append(("helpers_0", p))
+    for name, params in cases:
+        d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2)
+        ctrl = ref.control.OmegaThrustControl(d)
+        out[name + "_params_json"] = np.array(json.dumps(_plain(params)))
+        for k in ("mass", "inertia", "prop_pos", "thrust_max", "torque_max", "arm"):
+            out["%s_%s" % (name, k)] = np.array(getattr(d, k), dtype=np.float64)
+        out[name + "_Jinv"] = ctrl.Jinv
+    out["names"] = np.array([n for n, _ in cases])
+    return out
+
+
 def main(argv):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     names = argv[1:] or list(CASES)
@@ -185,7 +216,8 @@ def main(argv):
     if not argv[1:]:
         np.savez_compressed(os.path.join(GOLDEN_DIR, "known_answer.npz"), **known_answer())
         np.savez_compressed(os.path.join(GOLDEN_DIR, "model_answers.npz"), **model_answers())
-        print("wrote known_answer, model_answers")
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "random_models.npz"), **random_models())
+        print("wrote known_answer, model_answers, random_models")
 
 
 if __name__ == "__main__":

@@ -99,16 +99,22 @@ def quadlink_constants(geom):
         else:
             rots.append(np.eye(3))
 
-    add(body["m"], _box_I(body["l"], body["w"], body["h"], body["m"]), [0.0, 0.0, 0.0])
+    def box_m(d, l):             # BoxLink.__init__/compute_m, inertia.py:75-82, :98-99
+        return d["m"] if d.get("m") is not None else d["density"] * l * d["w"] * d["h"]
+
+    def cyl_m(d):                # CylinderLink.__init__/compute_m, inertia.py:139-146, :160-161
+        return d["m"] if d.get("m") is not None else d["density"] * np.pi * d["h"] * d["r"] ** 2
+
+    mb, mp, ma, mm, mr = box_m(body, body["l"]), box_m(payload, payload["l"]), box_m(arms, arm_l), cyl_m(motors), cyl_m(props)
+    add(mb, _box_I(body["l"], body["w"], body["h"], mb), [0.0, 0.0, 0.0])
     pz = np.sign(geom["payload_pos"]["z_sign"]) * (body["h"] + payload["h"]) / 2       # :268
-    add(payload["m"], _box_I(payload["l"], payload["w"], payload["h"], payload["m"]),
-        list(geom["payload_pos"]["xy"]) + [pz])
+    add(mp, _box_I(payload["l"], payload["w"], payload["h"], mp), list(geom["payload_pos"]["xy"]) + [pz])
     for i in range(4):
-        add(arms["m"], _box_I(arm_l, arms["w"], arms["h"], arms["m"]), arms_coord[:, i], alpha=arm_angles[i])
+        add(ma, _box_I(arm_l, arms["w"], arms["h"], ma), arms_coord[:, i], alpha=arm_angles[i])
     for i in range(4):
-        add(motors["m"], _cyl_I(motors["h"], motors["r"], motors["m"]), motors_coord[:, i])
+        add(mm, _cyl_I(motors["h"], motors["r"], mm), motors_coord[:, i])
     for i in range(4):
-        add(props["m"], _cyl_I(props["h"], props["r"], props["m"]), props_coord[:, i])
+        add(mr, _cyl_I(props["h"], props["r"], mr), props_coord[:, i])
 
     m_total = np.sum(masses)                                              # :308-310
     com = sum(masses[i] * xyzs[i] for i in range(len(masses))) / m_total  # :281-282

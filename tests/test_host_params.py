@@ -63,3 +63,80 @@ def test_config_derived_values():
     assert cfg.reward.log_pos == 1 and cfg.reward.effort == 0.01 and cfg.reward.spin == 0.0 and cfg.reward.pos_offset == 0.1
     assert cfg.model.ou_sigma == pytest.approx(0.01) and cfg.model.omega_max == 40.0
     assert [cfg.room_box[0][k] for k in range(3)] == [-10., -10., 0.] and [cfg.room_box[1][k] for k in range(3)] == [10.] * 3
+
+
+# ---- dynamics randomisation: same np.random draws as the reference -------------------
+def _random_cases():
+    import copy
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    cases = []
+    for seed in range(6):
+        np.random.seed(100 + seed)
+        cases.append(("randomquad_%d" % seed, qr.RandomQuad().sample()))
+    base = quad_models.crazyflie_params()
+    for seed, (ratio, sampler) in enumerate(((0.2, "normal"), (0.3, "uniform"), (0.1, "normal"))):
+        np.random.seed(200 + seed)
+        rs = qr.RelativeSampler(params=copy.deepcopy(base), noise_ratio=ratio, sampler=sampler,
+                                noise_ratio_custom={"motor": {"linearity": 0.0}} if seed == 2 else None)
+        cases.append(("relative_%d" % seed, rs.sample(copy.deepcopy(base))))
+    np.random.seed(300)
+    p = qr.sample_t2w_t2t(qr.sample_linearity(qr.sample_nodelay(quad_models.defaultquad_params())), 1.8, 2.5)
+    cases.append(("helpers_0", p))
+    return cases
+
+
+def test_randomisation_reproduces_reference_draw_for_draw():
+    """RandomQuad / RelativeSampler / sample_* under fixed seeds give the parameter dicts AND derived constants
+    recorded from the live reference (tests/golden/random_models.npz, oracle/gen_golden.py random_models)."""
+    rm = load_npz("random_models")
+    cases = _random_cases()
+    assert [n for n, _ in cases] == [str(n) for n in rm["names"]]
+    for name, params in cases:
+        ref_params = json.loads(str(rm[name + "_params_json"]))
+        m = ModelConstants(params)                           # like the reference's QuadLink, fills in geom.arms.l
+        _assert_tree_close(_plain(params), _plain(ref_params), name)
+        for key in ("mass", "inertia", "prop_pos", "thrust_max", "torque_max", "arm", "Jinv"):
+            np.testing.assert_allclose(getattr(m, key), rm["%s_%s" % (name, key)], rtol=1e-12, atol=1e-18,
+                                       err_msg="%s %s" % (name, key))
+        om = qo.model_constants(params)                      # the oracle's independent restatement agrees too
+        np.testing.assert_allclose(om["mass"], m.mass, rtol=1e-13)
+        np.testing.assert_allclose(om["inertia"], m.inertia, rtol=1e-12)
+        np.testing.assert_allclose(om["Jinv"], m.Jinv, rtol=1e-10)
+
+
+def _assert_tree_close(a, b, path):
+    if isinstance(a, dict):
+        assert set(a) == set(b), path
+        for k in a:
+            _assert_tree_close(a[k], b[k], path + "." + k)
+    elif isinstance(a, list):
+        np.testing.assert_allclose(np.array(a, dtype=float), np.array(b, dtype=float), rtol=1e-13, atol=0, err_msg=path)
+    elif isinstance(a, float):
+        assert a == pytest.approx(b, rel=1e-13, abs=0), path
+    else:
+        assert a == b, path
+
+
+def test_randomquad_respects_limits_and_is_flyable():
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    np.random.seed(7)
+    for _ in range(50):
+        p = qr.RandomQuad().sample()
+        m = ModelConstants(p)
+        assert 1.2 <= p["motor"]["thrust_to_weight"] <= 3.5 and np.all(m.inertia > 0) and m.mass > 0
+        assert np.all(p["motor"]["assymetry"] >= 0.9) and np.all(p["motor"]["assymetry"] <= 1.1)
+        assert np.isfinite(m.Jinv).all() and abs(np.sum(m.thrust_max) / (9.81 * m.mass) - p["motor"]["thrust_to_weight"]) < 1e-9
+
+
+def test_absolute_sampler_ranges():
+    import copy
+    import types
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    base = quad_models.crazyflie_params()
+    rng = lambda lo, hi: types.SimpleNamespace(min=lo, max=hi)
+    noise = copy.deepcopy(base)
+    qr._walk(noise, lambda k, v: rng(np.min(v) * 0.9, np.max(v) * 1.1 + 1e-9) if not isinstance(v, str) else v)
+    np.random.seed(1)
+    p = qr.AbsoluteSampler(base, noise, sampler="uniform").sample(copy.deepcopy(base))
+    assert 0.9 * 1.9 - 1e-9 <= p["motor"]["thrust_to_weight"] <= 1.1 * 1.9 + 1e-9
+    assert p["motor"]["thrust_to_weight"] != base["motor"]["thrust_to_weight"]
