@@ -17,7 +17,7 @@ namespace qs {
 
 constexpr int BLOCK = 128;           // threads per CTA = envs per CTA
 constexpr int MAX_OBS = 25;
-constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 48;
+constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 48, MODEL_ROWS = 14;
 
 enum Ctrl { CTRL_RAW = 0, CTRL_VERTICAL, CTRL_VERTPLANE, CTRL_SHIFTED, CTRL_OMEGA_THRUST, CTRL_VELOCITY_YAW, CTRL_MELLINGER };
 
@@ -41,6 +41,7 @@ struct Params {
   R* rew;                   // [n]
   uint8_t* done;            // [n]
   R* info;                  // [n][INFO_DIM] or null
+  const R* models;          // per-env model constants [MODEL_ROWS][n][4] or null (quadsim.h "Per-env model buffer")
   const uint8_t* reset_mask;
   const R* ou_z;            // injected: [n][sim_steps][4]
   const R* obs_z;           // injected: [n][OBS_Z]
@@ -92,8 +93,10 @@ struct Params {
 };
 
 // compile-time specialisation knobs; -1 = decided at run time from Params
-template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_, int SIM_ = -1, bool PLAIN_ = false, bool SWARM_ = false>
+template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_, int SIM_ = -1, bool PLAIN_ = false, bool SWARM_ = false,
+          bool PEM_ = false>
 struct Traits {
+  static constexpr bool PEM = PEM_;     // per-env model constants (dynamics randomisation), read from the model buffer
   static constexpr bool SWARM = SWARM_ || RARE_;   // n_agents > 1 handled: contact stage, formation goals, log-distance reward
   static constexpr int CTRL = CTRL_;
   static constexpr int SIM = SIM_;      // compile-time sim_steps (substep loop unrolled, OU draws hoisted), -1 = run time
@@ -298,6 +301,67 @@ struct Rng {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// Model constants as one thread sees them.  One model per handle: straight out of the constant bank (Params).
+// Per-env models (dynamics randomisation, quadrotor_randomization.py): read-only loads from the model buffer, row
+// layout in quadsim.h; nothing is cached in registers (the fp64 build has none to spare), L1 serves the re-reads.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, bool PEM> struct Mdl;
+template <typename R> struct Mdl<R, false> {
+  const Params<R>& p;
+  __device__ __forceinline__ Mdl(const Params<R>& p_, long long) : p(p_) {}
+  __device__ __forceinline__ R thrust_max(int k) const { return p.thrust_max[k]; }
+  __device__ __forceinline__ R tz(int k) const { return p.tz[k]; }
+  __device__ __forceinline__ R pcx(int k) const { return p.pcx[k]; }
+  __device__ __forceinline__ R pcy(int k) const { return p.pcy[k]; }
+  __device__ __forceinline__ R ppx(int k) const { return p.ppx[k]; }
+  __device__ __forceinline__ R ppy(int k) const { return p.ppy[k]; }
+  __device__ __forceinline__ R ppz(int k) const { return p.ppz[k]; }
+  __device__ __forceinline__ R inertia(int k) const { return p.inertia[k]; }
+  __device__ __forceinline__ R inv_inertia(int k) const { return p.inv_inertia[k]; }
+  __device__ __forceinline__ R mass() const { return p.mass; }
+  __device__ __forceinline__ R inv_mass() const { return p.inv_mass; }
+  __device__ __forceinline__ R tau_up() const { return p.tau_up; }
+  __device__ __forceinline__ R tau_down() const { return p.tau_down; }
+  __device__ __forceinline__ R ou_sigma() const { return p.ou_sigma; }
+  __device__ __forceinline__ R arm() const { return p.arm; }
+  __device__ __forceinline__ R lin() const { return p.lin; }
+  __device__ __forceinline__ R c_drag() const { return p.c_drag; }
+  __device__ __forceinline__ R c_roll() const { return p.c_roll; }
+  __device__ __forceinline__ R t2w() const { return p.t2w; }
+  __device__ __forceinline__ R vel_damp() const { return p.vel_damp; }
+  __device__ __forceinline__ R damp_omega_q() const { return p.damp_omega_q; }
+  __device__ __forceinline__ R jinv(int r, int c) const { return p.jinv[r][c]; }
+};
+template <typename R> struct Mdl<R, true> {
+  const R* base;          // element 0 of this env's vector in row 0
+  long long stride;       // elements between rows
+  __device__ __forceinline__ Mdl(const Params<R>& p, long long i) : base(p.models + i * 4), stride(p.n * 4) {}
+  __device__ __forceinline__ R at(int row, int c) const { return __ldg(base + row * stride + c); }
+  __device__ __forceinline__ R thrust_max(int k) const { return at(0, k); }
+  __device__ __forceinline__ R tz(int k) const { return at(1, k); }
+  __device__ __forceinline__ R pcx(int k) const { return at(2, k); }
+  __device__ __forceinline__ R pcy(int k) const { return at(3, k); }
+  __device__ __forceinline__ R ppx(int k) const { return -at(3, k); }
+  __device__ __forceinline__ R ppy(int k) const { return at(2, k); }
+  __device__ __forceinline__ R ppz(int k) const { return at(4, k); }
+  __device__ __forceinline__ R inertia(int k) const { return at(5, k); }
+  __device__ __forceinline__ R inv_inertia(int k) const { return at(6, k); }
+  __device__ __forceinline__ R mass() const { return at(5, 3); }
+  __device__ __forceinline__ R inv_mass() const { return at(6, 3); }
+  __device__ __forceinline__ R tau_up() const { return at(7, 0); }
+  __device__ __forceinline__ R tau_down() const { return at(7, 1); }
+  __device__ __forceinline__ R ou_sigma() const { return at(7, 2); }
+  __device__ __forceinline__ R arm() const { return at(7, 3); }
+  __device__ __forceinline__ R lin() const { return at(8, 0); }
+  __device__ __forceinline__ R c_drag() const { return at(8, 1); }
+  __device__ __forceinline__ R c_roll() const { return at(8, 2); }
+  __device__ __forceinline__ R t2w() const { return at(8, 3); }
+  __device__ __forceinline__ R vel_damp() const { return at(9, 0); }
+  __device__ __forceinline__ R damp_omega_q() const { return at(9, 1); }
+  __device__ __forceinline__ R jinv(int r, int c) const { return at(10 + r, c); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // per-env state in registers
 // ---------------------------------------------------------------------------------------------------------
 template <typename R>
@@ -462,58 +526,59 @@ __device__ __forceinline__ void polar_orthonormalize(R* r) {
 // QuadrotorDynamics.step1 (quadrotor.py:273-436).  z: 4 unit normals for the OU thrust noise.
 // ---------------------------------------------------------------------------------------------------------
 template <typename R, class T>
-__device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>& p, const R* z, bool fire_svd) {
+__device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>& p, const Mdl<R, T::PEM>& m, const R* z,
+                                        bool fire_svd) {
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   const R dt = p.dt;
   R tsum = R(0), tqx = R(0), tqy = R(0), tqz = R(0);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     R c = clampr(cmd[k], R(0), R(1));                                   // :279
-    R tau = (c < s.cd[k]) ? p.tau_down : p.tau_up;                      // :284-288 (tau pre-clipped to 1 on the host)
+    R tau = (c < s.cd[k]) ? m.tau_down() : m.tau_up();                      // :284-288 (tau pre-clipped to 1 on the host)
     R rt = q_sqrt<R, T::FASTM>(c);                                      // :294
     s.rd[k] = tau * (rt - s.rd[k]) + s.rd[k];                           // :295
     R cd = s.rd[k] * s.rd[k];                                           // :296
     if (ou_on) {
-      s.ou[k] = s.ou[k] + (p.ou_theta * (-s.ou[k]) + p.ou_sigma * z[k]);   // quad_utils.py:197-201 (mu = 0)
+      s.ou[k] = s.ou[k] + (p.ou_theta * (-s.ou[k]) + m.ou_sigma() * z[k]);   // quad_utils.py:197-201 (mu = 0)
       cd = cd + c * s.ou[k];                                            // :299
     }
     cd = clampr(cd, R(0), R(1));                                        // :300
     s.cd[k] = cd;
     R t;
-    if (T::RARE) t = p.thrust_max[k] * ((R(1) - p.lin) * cd * cd + p.lin * cd);   // :302, :140
-    else t = p.thrust_max[k] * cd;                                      // linearity == 1
-    tqx += p.pcx[k] * t;                                                // :304, :310
-    tqy += p.pcy[k] * t;
-    tqz += p.tz[k] * cd;                                                // :307
+    if (T::RARE) t = m.thrust_max(k) * ((R(1) - m.lin()) * cd * cd + m.lin() * cd);   // :302, :140
+    else t = m.thrust_max(k) * cd;                                      // linearity == 1
+    tqx += m.pcx(k) * t;                                                // :304, :310
+    tqy += m.pcy(k) * t;
+    tqz += m.tz(k) * cd;                                                // :307
     tsum += t;                                                          // :362
   }
   R fdx = R(0), fdy = R(0), fdz = R(0);                                 // rotor drag force (body frame)
   if (T::RARE) {
-    if (p.c_drag != R(0) || p.c_roll != R(0)) {                         // :318-349
+    if (m.c_drag() != R(0) || m.c_roll() != R(0)) {                         // :318-349
       R vbx = s.r[0] * s.vx + s.r[3] * s.vy + s.r[6] * s.vz;            // rot.T @ vel
       R vby = s.r[1] * s.vx + s.r[4] * s.vy + s.r[7] * s.vz;
       R vbz = s.r[2] * s.vx + s.r[5] * s.vy + s.r[8] * s.vz;
       R dtx = R(0), dty = R(0), dtz = R(0), rtx = R(0), rty = R(0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        R vrx = vbx + (s.wy * p.ppz[k] - s.wz * p.ppy[k]);              // :323 omega x prop_pos
-        R vry = vby + (s.wz * p.ppx[k] - s.wx * p.ppz[k]);              // z component projected out (:325)
+        R vrx = vbx + (s.wy * m.ppz(k) - s.wz * m.ppy(k));              // :323 omega x prop_pos
+        R vry = vby + (s.wz * m.ppx(k) - s.wx * m.ppz(k));              // z component projected out (:325)
         R sq = Mth<R>::sqrt(s.cd[k]);
-        R fx = -p.c_drag * sq * vrx, fy = -p.c_drag * sq * vry;         // :328
+        R fx = -m.c_drag() * sq * vrx, fy = -m.c_drag() * sq * vry;         // :328
         fdx += fx; fdy += fy;
-        dtx += fy * p.ppz[k];                                           // :331 f x prop_pos (f.z = 0)
-        dty += -fx * p.ppz[k];
-        dtz += fx * p.ppy[k] - fy * p.ppx[k];
-        rtx += -p.c_roll * p.ccw[k] * sq * vrx;                         // :334
-        rty += -p.c_roll * p.ccw[k] * sq * vry;
+        dtx += fy * m.ppz(k);                                           // :331 f x prop_pos (f.z = 0)
+        dty += -fx * m.ppz(k);
+        dtz += fx * m.ppy(k) - fy * m.ppx(k);
+        rtx += -m.c_roll() * p.ccw[k] * sq * vrx;                         // :334
+        rty += -m.c_roll() * p.ccw[k] * sq * vry;
       }
       R vtx = dtx + rtx, vty = dty + rty, vtz = dtz;                    // :336
       R vel_norm = Mth<R>::sqrt(vbx * vbx + vby * vby + vbz * vbz);     // :339
       R rdf = Mth<R>::sqrt(fdx * fdx + fdy * fdy);                      // :340
-      R rdf_clip = clampr(rdf, R(0), vel_norm * p.mass / (R(2) * dt));  // :341
+      R rdf_clip = clampr(rdf, R(0), vel_norm * m.mass() / (R(2) * dt));  // :341
       if (rdf > R(1e-6)) { R sc = rdf_clip; fdx = (fdx / rdf) * sc; fdy = (fdy / rdf) * sc; }   // :342-343
       R rvt = Mth<R>::sqrt(vtx * vtx + vty * vty + vtz * vtz);          // :346
-      R iwx = s.wx * p.inertia[0], iwy = s.wy * p.inertia[1], iwz = s.wz * p.inertia[2];
+      R iwx = s.wx * m.inertia(0), iwy = s.wy * m.inertia(1), iwz = s.wz * m.inertia(2);
       R rvt_clip = clampr(rvt, R(0), Mth<R>::sqrt(iwx * iwx + iwy * iwy + iwz * iwz) / (R(2) * dt));   // :347
       if (rvt > R(1e-6)) { vtx = (vtx / rvt) * rvt_clip; vty = (vty / rvt) * rvt_clip; vtz = (vtz / rvt) * rvt_clip; }
       tqx += vtx; tqy += vty; tqz += vtz;                               // :361
@@ -553,22 +618,22 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
   if (fire_svd) polar_orthonormalize(s.r);                              // :381-386 (uniform across the grid)
   // ---- body rates (:398-405): old omega in the gyroscopic term ----
   {
-    R iwx = p.inertia[0] * s.wx, iwy = p.inertia[1] * s.wy, iwz = p.inertia[2] * s.wz;
+    R iwx = m.inertia(0) * s.wx, iwy = m.inertia(1) * s.wy, iwz = m.inertia(2) * s.wz;
     R gx = (-s.wy) * iwz - (-s.wz) * iwy;                               // cross(-omega, I omega)
     R gy = (-s.wz) * iwx - (-s.wx) * iwz;
     R gz = (-s.wx) * iwy - (-s.wy) * iwx;
-    s.odx = p.inv_inertia[0] * (gx + tqx);
-    s.ody = p.inv_inertia[1] * (gy + tqy);
-    s.odz = p.inv_inertia[2] * (gz + tqz);
+    s.odx = m.inv_inertia(0) * (gx + tqx);
+    s.ody = m.inv_inertia(1) * (gy + tqy);
+    s.odz = m.inv_inertia(2) * (gz + tqz);
     R fx = dt, fy = dt, fz = dt;
     if (T::RARE) {
       R w2x = s.wx * s.wx, w2y = s.wy * s.wy, w2z = s.wz * s.wz;
       if (sizeof(R) == 8 && s.w_is_f32) {   // omega ** 2 on the float32 array set_state left behind (:223, :403)
         w2x = (R)((float)s.wx * (float)s.wx); w2y = (R)((float)s.wy * (float)s.wy); w2z = (R)((float)s.wz * (float)s.wz);
       }
-      fx = (R(1) - clampr(p.damp_omega_q * w2x, R(0), R(1))) * dt;      // :403-404
-      fy = (R(1) - clampr(p.damp_omega_q * w2y, R(0), R(1))) * dt;
-      fz = (R(1) - clampr(p.damp_omega_q * w2z, R(0), R(1))) * dt;
+      fx = (R(1) - clampr(m.damp_omega_q() * w2x, R(0), R(1))) * dt;      // :403-404
+      fy = (R(1) - clampr(m.damp_omega_q() * w2y, R(0), R(1))) * dt;
+      fz = (R(1) - clampr(m.damp_omega_q() * w2z, R(0), R(1))) * dt;
     }
     s.wx = clampr(s.wx + fx * s.odx, -p.omega_max, p.omega_max);        // :404-405
     s.wy = clampr(s.wy + fy * s.ody, -p.omega_max, p.omega_max);
@@ -582,17 +647,17 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
   R bx = fdx, by = fdy, bz = tsum + fdz;                                // thrust + rotor_drag_force (body)
   R ax, ay, az;
   if (T::RARE) {
-    ax = p.inv_mass * (s.r[0] * bx + s.r[1] * by + s.r[2] * bz);
-    ay = p.inv_mass * (s.r[3] * bx + s.r[4] * by + s.r[5] * bz);
-    az = p.inv_mass * (s.r[6] * bx + s.r[7] * by + s.r[8] * bz) - R(9.81);
+    ax = m.inv_mass() * (s.r[0] * bx + s.r[1] * by + s.r[2] * bz);
+    ay = m.inv_mass() * (s.r[3] * bx + s.r[4] * by + s.r[5] * bz);
+    az = m.inv_mass() * (s.r[6] * bx + s.r[7] * by + s.r[8] * bz) - R(9.81);
   } else {
-    ax = p.inv_mass * (s.r[2] * bz);
-    ay = p.inv_mass * (s.r[5] * bz);
-    az = p.inv_mass * (s.r[8] * bz) - R(9.81);                          // GRAV constant, not self.gravity (:426)
+    ax = m.inv_mass() * (s.r[2] * bz);
+    ay = m.inv_mass() * (s.r[5] * bz);
+    az = m.inv_mass() * (s.r[8] * bz) - R(9.81);                          // GRAV constant, not self.gravity (:426)
   }
   s.ax = ax; s.ay = ay; s.az = az;
   if (T::RARE) {
-    R vd = R(1) - p.vel_damp;
+    R vd = R(1) - m.vel_damp();
     s.vx = vd * s.vx + dt * ax; s.vy = vd * s.vy + dt * ay; s.vz = vd * s.vz + dt * az;   // :431
   } else {
     s.vx = s.vx + dt * ax; s.vy = s.vy + dt * ay; s.vz = s.vz + dt * az;
@@ -623,15 +688,16 @@ template <typename R, bool FAST = false> __device__ __forceinline__ void normali
   if (!(n < R(0.00001))) { x = x / n; y = y / n; z = z / n; }
 }
 
-template <typename R>
-__device__ __forceinline__ void jinv_mix(const Params<R>& p, R d0, R d1, R d2, R d3, R* cmd) {
+template <typename R, class M>
+__device__ __forceinline__ void jinv_mix(const M& m, R d0, R d1, R d2, R d3, R* cmd) {
 #pragma unroll
   for (int k = 0; k < 4; ++k)
-    cmd[k] = clampr(p.jinv[k][0] * d0 + p.jinv[k][1] * d1 + p.jinv[k][2] * d2 + p.jinv[k][3] * d3, R(0), R(1));
+    cmd[k] = clampr(m.jinv(k, 0) * d0 + m.jinv(k, 1) * d1 + m.jinv(k, 2) * d2 + m.jinv(k, 3) * d3, R(0), R(1));
 }
 
-template <typename R, bool FAST>
-__device__ __forceinline__ void attitude_controller(const St<R>& s, const Params<R>& p, bool mellinger, const R* a, R* cmd) {
+template <typename R, bool FAST, class M>
+__device__ __forceinline__ void attitude_controller(const St<R>& s, const Params<R>& p, const M& m, bool mellinger, const R* a,
+                                                    R* cmd) {
   R adx, ady, adz, xcx, xcy, xcz, ewx, ewy, ewz, kp_a, kd_a, yaw_scale;
   if (mellinger) {                                                      // :315-362
     R tx = s.gx - s.px, ty = s.gy - s.py, tz = s.gz - s.pz;
@@ -670,11 +736,12 @@ __device__ __forceinline__ void attitude_controller(const St<R>& s, const Params
   }
   R dwx = -kp_a * erx - kwx, dwy = -kp_a * ery - kwy, dwz = -kp_a * erz - kwz;       // :350
   R thrust_mag = adx * s.r[2] + ady * s.r[5] + adz * s.r[8];            // :352
-  jinv_mix(p, thrust_mag, dwx, dwy, dwz, cmd);                          // :357-359
+  jinv_mix<R>(m, thrust_mag, dwx, dwy, dwz, cmd);                          // :357-359
 }
 
 template <typename R, class T>
-__device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>& p, int ctrl, const R* a, R* cmd) {
+__device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>& p, const Mdl<R, T::PEM>& m, int ctrl, const R* a,
+                                                R* cmd) {
   if (ctrl == CTRL_RAW || ctrl == CTRL_VERTICAL || ctrl == CTRL_VERTPLANE) {   // :72-99, :116-136, :159-179
     R lo = p.zero_middle ? R(-1) : R(0);
     R b[4];
@@ -688,13 +755,13 @@ __device__ __forceinline__ void controller_cmds(const St<R>& s, const Params<R>&
     else { cmd[0] = cmd[1] = b[0]; cmd[2] = cmd[3] = b[1]; }
   } else if (ctrl == CTRL_SHIFTED) {                                    // :23-27
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cmd[k] = clampr((a[k] + R(1)) / p.t2w, R(0), R(1));
+    for (int k = 0; k < 4; ++k) cmd[k] = clampr((a[k] + R(1)) / m.t2w(), R(0), R(1));
   } else if (ctrl == CTRL_OMEGA_THRUST) {                               // :225-234
     R dwx = R(-5) * (s.wx - a[1]), dwy = R(-5) * (s.wy - a[2]), dwz = R(-5) * (s.wz - a[3]);
     R acc_des = R(9.81) * (a[0] + R(1));
-    jinv_mix(p, acc_des, dwx, dwy, dwz, cmd);
+    jinv_mix<R>(m, acc_des, dwx, dwy, dwz, cmd);
   } else {
-    attitude_controller<R, T::FASTM>(s, p, ctrl == CTRL_MELLINGER, a, cmd);
+    attitude_controller<R, T::FASTM>(s, p, m, ctrl == CTRL_MELLINGER, a, cmd);
   }
 }
 
@@ -1058,6 +1125,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
                                           double svd_t0, unsigned long long step0, R* o, StepOut<R>& out) {
   const int ctrl = T::CTRL >= 0 ? T::CTRL : p.controller;
   NoiseSrc<R, T> ns(p, active ? i : 0);
+  const Mdl<R, T::PEM> m(p, active ? i : p.begin);
   double svd_t = svd_t0;
   R rew_sum = R(0);
   bool done_any = false;
@@ -1097,12 +1165,12 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     R a_prev[4] = {s.pa[0], s.pa[1], s.pa[2], s.pa[3]};                 // actions[1]
     // ---- controller + dynamics (:966-970, :261-262) ----
     R cmd[4];
-    controller_cmds<R, T>(s, p, ctrl, a, cmd);
+    controller_cmds<R, T>(s, p, m, ctrl, a, cmd);
     if (T::SIM > 0) {
 #pragma unroll
       for (int sub = 0; sub < NPRE; ++sub) {
         const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);        // :381-386
-        substep<R, T>(s, cmd, p, zou[sub], fire);
+        substep<R, T>(s, cmd, p, m, zou[sub], fire);
       }
     } else {
 #pragma unroll 1
@@ -1110,13 +1178,13 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
         const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);        // :381-386
         R z[4] = {R(0), R(0), R(0), R(0)};
         if (ou_on) ns.ou(sub, z);
-        substep<R, T>(s, cmd, p, z, fire);
+        substep<R, T>(s, cmd, p, m, z, fire);
       }
     }
     bool collided = false;
     if (T::SWARM) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
     // ---- crash, reward, tick, done (:974-987) ----
-    bool crashed = s.pz <= p.arm;                                       // :977
+    bool crashed = s.pz <= m.arm();                                     // :977
     R costs[20];
     R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::RARE && p.info) ? costs : nullptr);
     if (!Mth<R>::finite(rew) && active) atomicOr(p.status, 1);          // :633-636
@@ -1512,15 +1580,16 @@ __global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_const
     for (int k = 0; k < 4; ++k) if (k < adim) a[k] = p.actions[i * adim + k];
   }
   R cmd[4];
+  const Mdl<R, T::PEM> m(p, active ? i : p.begin);
   if (p.dyn_controller < 0) { cmd[0] = a[0]; cmd[1] = a[1]; cmd[2] = a[2]; cmd[3] = a[3]; }
-  else controller_cmds<R, T>(s, p, p.dyn_controller, a, cmd);
+  else controller_cmds<R, T>(s, p, m, p.dyn_controller, a, cmd);
   double svd_t = p.clock->svd_timer;
 #pragma unroll 1
   for (int sub = 0; sub < p.dyn_substeps; ++sub) {
     const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);
     R z[4] = {R(0), R(0), R(0), R(0)};
     if (p.ou_on) ns.ou(sub, z);
-    substep<R, T>(s, cmd, p, z, fire);
+    substep<R, T>(s, cmd, p, m, z, fire);
   }
   if (active) {
     store_state<R, T>(s, p, i);

@@ -14,6 +14,8 @@ static cudaError_t launch_step_t(const Params<R>& p, cudaStream_t st) {
 
 typedef Traits<-1, -1, -1, true, true> TGenInject;
 typedef Traits<-1, -1, -1, false, true> TGenPhilox;
+typedef Traits<-1, -1, -1, true, true, -1, false, false, true> TGenInjectPEM;     // per-env model constants
+typedef Traits<-1, -1, -1, false, true, -1, false, false, true> TGenPhiloxPEM;
 
 template <>
 cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, const char** name) {
@@ -26,6 +28,11 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
     return p.inject ? launch_fast_mellinger_inject(p, st, name) : launch_fast_mellinger_philox(p, st, name);
   }
 #endif
+  if (p.models != nullptr) {
+    if (p.inject) { if (name) *name = "generic-permodel-injected"; return launch_step_t<R, TGenInjectPEM>(p, st); }
+    if (name) *name = "generic-permodel-philox";
+    return launch_step_t<R, TGenPhiloxPEM>(p, st);
+  }
   if (p.inject) { if (name) *name = "generic-injected"; return launch_step_t<R, TGenInject>(p, st); }
   if (name) *name = "generic-philox";
   return launch_step_t<R, TGenPhilox>(p, st);
@@ -45,7 +52,10 @@ template <>
 cudaError_t launch_dynamics<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) {
   typedef QS_REAL R;
   const unsigned grid = (unsigned)((p.end - p.begin + BLOCK - 1) / BLOCK);
-  if (p.inject) dynamics_step_kernel<R, TGenInject><<<grid, BLOCK, 0, st>>>(p);
+  if (p.models != nullptr) {
+    if (p.inject) dynamics_step_kernel<R, TGenInjectPEM><<<grid, BLOCK, 0, st>>>(p);
+    else dynamics_step_kernel<R, TGenPhiloxPEM><<<grid, BLOCK, 0, st>>>(p);
+  } else if (p.inject) dynamics_step_kernel<R, TGenInject><<<grid, BLOCK, 0, st>>>(p);
   else dynamics_step_kernel<R, TGenPhilox><<<grid, BLOCK, 0, st>>>(p);
   return cudaGetLastError();
 }

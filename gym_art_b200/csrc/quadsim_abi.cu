@@ -27,6 +27,7 @@ struct QsHandle {
   QsStateLayout lay;
   void* state;
   void* info;
+  const void* models;
   const void* ou_z;
   const void* obs_z;
   const void* reset_z;
@@ -93,6 +94,7 @@ int validate(const QsConfig* c, std::string* why) {
   if (!(c->dt > 0.0)) { *why = "dt must be positive"; return QS_EINVAL; }
   if (c->n_agents < 1 || c->n_agents > 32 || !is_pow2(c->n_agents)) { *why = "n_agents must be 1, 2, 4, 8, 16 or 32"; return QS_EINVAL; }
   if (c->n_envs % c->n_agents != 0) { *why = "n_envs must be a multiple of n_agents"; return QS_EINVAL; }
+  if (c->per_env_model && c->n_agents > 1) { *why = "per-env models are not built for swarms"; return QS_EUNSUPPORTED; }
   if (c->use_formation && c->per_env_goal) { *why = "use_formation and per_env_goal are mutually exclusive"; return QS_EINVAL; }
   if (!(c->model.mass > 0.0) || !(c->model.inertia[0] > 0.0) || !(c->model.inertia[1] > 0.0) || !(c->model.inertia[2] > 0.0)) {
     *why = "model mass/inertia must be positive"; return QS_EINVAL;
@@ -107,7 +109,7 @@ bool needs_prev_action(const QsConfig* c) {
 
 void layout_of(const QsConfig* c, QsStateLayout* o) {
   int rows = 7;
-  o->row_ou = (c->model.ou_sigma > 0.0) ? rows++ : -1;
+  o->row_ou = (c->model.ou_sigma > 0.0 || c->per_env_model) ? rows++ : -1;
   o->row_prev_action = needs_prev_action(c) ? rows++ : -1;
   o->row_gyro_bias = (c->sense.enabled && c->sense.gyro_norm_std != 0.0) ? rows++ : -1;
   o->row_goal = c->per_env_goal ? rows++ : -1;
@@ -124,7 +126,7 @@ bool need_rare(const QsHandle* h) {
   if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) return true;
   if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
                     s.gyro_norm_std != 0.0)) return true;
-  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
+  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr || c.per_env_model) return true;
   // swarms (and the log-distance reward that comes with them) have specialised kernels for the common step shape only
   const bool plain = c.sim_steps == 2 && h->lay.obs_dim == 18 && h->lay.row_prev_action < 0 &&
                      c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA;
@@ -140,6 +142,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   const QsModel& m = c.model;
   p.state = (R*)h->state;
   p.info = (R*)h->info;
+  p.models = (const R*)h->models;
   p.ou_z = (const R*)h->ou_z;
   p.obs_z = (const R*)h->obs_z;
   p.reset_z = (const R*)h->reset_z;
@@ -164,7 +167,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.obs_act = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT || c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACT);
   p.init_random = c.init_random_state; p.auto_reset = c.auto_reset;
   p.sense_on = c.sense.enabled ? 1 : 0;
-  p.ou_on = (m.ou_sigma > 0.0) ? 1 : 0;
+  p.ou_on = (m.ou_sigma > 0.0 || c.per_env_model) ? 1 : 0;
   p.gyro_bias_mode = (c.sense.enabled && c.sense.gyro_norm_std != 0.0) ? 1 : 0;
   p.dyn_controller = -1; p.dyn_substeps = c.sim_steps;
   p.inject = (c.noise_mode == QS_NOISE_INJECTED) ? 1 : 0;
@@ -247,6 +250,7 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
 int check_ready(QsHandle* h, bool need_actions, const void* actions) {
   if (!h) return QS_EINVAL;
   if (!h->state) return fail(h, QS_ESTATE, "state buffer not bound (qs_bind_state)");
+  if (h->cfg.per_env_model && !h->models) return fail(h, QS_ESTATE, "model buffer not bound (qs_bind_models)");
   if (need_actions && !actions && h->cfg.controller != QS_CTRL_MELLINGER)
     return fail(h, QS_EINVAL, "actions may be NULL only for QS_CTRL_MELLINGER");
   return QS_OK;
@@ -277,6 +281,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->cfg = *cfg;
   layout_of(cfg, &h->lay);
   h->state = h->info = nullptr;
+  h->models = nullptr;
   h->ou_z = h->obs_z = h->reset_z = nullptr;
   h->d_stats = nullptr; h->d_status = nullptr; h->d_clock = nullptr; h->d_ticket = nullptr;
   h->launches = 0;
@@ -332,6 +337,15 @@ int qs_bind_state(QsHandle* h, void* state) {
   if (!state) return fail(h, QS_EINVAL, "state is NULL");
   if (((uintptr_t)state) % 32 != 0) return fail(h, QS_EINVAL, "state must be 32-byte aligned");
   h->state = state;
+  return QS_OK;
+}
+
+int qs_bind_models(QsHandle* h, const void* models) {
+  if (!h) return QS_EINVAL;
+  if (!h->cfg.per_env_model) return fail(h, QS_EINVAL, "handle was not created with per_env_model");
+  if (!models) return fail(h, QS_EINVAL, "models is NULL");
+  if (((uintptr_t)models) % 32 != 0) return fail(h, QS_EINVAL, "models must be 32-byte aligned");
+  h->models = models;
   return QS_OK;
 }
 

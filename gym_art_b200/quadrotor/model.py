@@ -58,6 +58,23 @@ class ModelConstants(object):
         self.G_omega = (1.0 / self.inertia)[:, None] * (self.thrust_max * self.prop_crossproducts.T + self.torque_max * ccw_mx)
         self.torque_to_inertia = np.sum(self.G_omega @ np.array([[0, 0, 0], [0, 1, 1], [1, 1, 0], [1, 0, 1]]), axis=1)
 
+    def rows(self, dt):
+        """This model as one column of the per-env model buffer: float64 [QS_MODEL_ROWS, 4] (layout in quadsim.h)."""
+        r = np.zeros((_lib.QS_MODEL_ROWS, 4))
+        r[0] = self.thrust_max
+        r[1] = self.torque_max * self.prop_ccw
+        r[2] = self.prop_pos[:, 1]
+        r[3] = -self.prop_pos[:, 0]
+        r[4] = self.prop_pos[:, 2]
+        r[5, :3], r[5, 3] = self.inertia, self.mass
+        r[6, :3], r[6, 3] = 1.0 / self.inertia, 1.0 / self.mass
+        r[7] = [min(1.0, 4.0 * dt / (self.motor_damp_time_up + EPS)), min(1.0, 4.0 * dt / (self.motor_damp_time_down + EPS)),
+                self.ou_sigma, self.arm]                                                   # quadrotor.py:284-288
+        r[8] = [self.motor_linearity, self.C_rot_drag, self.C_rot_roll, self.thrust_to_weight]
+        r[9, :2] = [self.vel_damp, self.damp_omega_quadratic]
+        r[10:14] = self.Jinv
+        return r
+
     def to_qs(self):
         m = _lib.QsModel()
         m.mass = self.mass

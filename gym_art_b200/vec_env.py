@@ -25,7 +25,7 @@ REW_COEFF_MULTI_DEFAULT = {"pos": 1., "pos_offset": 0.1, "pos_log_weight": 1., "
                            "attitude": 0., "spin": 0., "vel": 0.}                     # quadrotor_multi.py:810-818
 
 
-def resolve_dynamics_params(dynamics_params, dynamics_change=None):
+def resolve_dynamics_params(dynamics_params, dynamics_change=None, check=True):
     """quadrotor.py:738-744 + :1030-1056: sampler name (or dict) -> checked parameter dict."""
     if isinstance(dynamics_params, str):
         params = getattr(quad_rand, dynamics_params)().sample()
@@ -34,7 +34,7 @@ def resolve_dynamics_params(dynamics_params, dynamics_change=None):
         params = copy.deepcopy(dynamics_params)
     if dynamics_change is not None:
         quad_rand._update_existing(params, dynamics_change)
-    return quad_rand.check_quad_param_limits(params)
+    return quad_rand.check_quad_param_limits(params) if check else params
 
 
 def resolve_sense_noise(sense_noise):
@@ -66,7 +66,8 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
                 sim_steps=2, obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10, init_random_state=False,
                 rew_coeff=None, sense_noise=None, device_index=0, dtype="float32", seed=0, noise_mode="philox",
                 auto_reset=True, n_agents=1, per_env_goal=False, env_id_offset=0, multi_reward=False, collision_k=1.0,
-                goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi, formation=None):
+                goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi, formation=None,
+                per_env_model=False):
     """Pure host function (no GPU): ctor arguments -> QsConfig.  Raises the reference's ValueErrors."""
     cfg = _lib.QsConfig()
     cfg.abi_version = _lib.QS_ABI_VERSION
@@ -108,6 +109,7 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
     cfg.max_init_vel = float(max_init_vel)                                            # quadrotor.py:717
     cfg.max_init_omega = float(max_init_omega)                                        # quadrotor.py:718
     cfg.collision_k = float(collision_k)
+    cfg.per_env_model = int(bool(per_env_model))
     if formation is not None:                                                         # swarm: goal of drone a = formation[a]
         f = np.asarray(formation, dtype=np.float64).reshape(-1, 3)
         if f.shape[0] != int(n_agents) or per_env_goal:
@@ -149,7 +151,7 @@ class QuadVecEnv(object):
                  sense_noise=None, gravity=GRAV, device="cuda:0", dtype="float32", seed=0, noise_mode="philox",
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
-                 max_init_omega=2 * np.pi, formation=None):
+                 max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -175,7 +177,7 @@ class QuadVecEnv(object):
             device_index=dev_index, dtype=dtype, seed=seed, noise_mode=noise_mode, auto_reset=auto_reset,
             n_agents=n_agents, per_env_goal=goals is not None, env_id_offset=env_id_offset, multi_reward=multi_reward,
             collision_k=collision_k, goal=goal, box=box, spawn_z_min=spawn_z_min, max_init_vel=max_init_vel,
-            max_init_omega=max_init_omega, formation=formation)
+            max_init_omega=max_init_omega, formation=formation, per_env_model=per_env_dynamics is not None)
         self.layout = _lib.state_layout(self.cfg)
         self.num_envs = int(num_envs)
         self.n_agents = int(n_agents)
@@ -205,6 +207,12 @@ class QuadVecEnv(object):
         if info:
             _lib.check(self.lib.qs_bind_info(self._h, self.info.data_ptr()), self._h)
         self._noise_refs = None
+        self.models, self.model_params, self.model_index = None, None, None
+        if per_env_dynamics is not None:
+            # dynamics randomisation (quadrotor.py:738-763, :1030-1056): `per_env_dynamics` independently sampled models
+            # (base sampler -> dynamics_change -> sampler 1 -> sampler 2 -> limits), dealt to the envs at random
+            self._dyn_spec = (dynamics_params, dynamics_change, dyn_sampler_1, dyn_sampler_2, gravity)
+            self.resample_dynamics(n_models=int(per_env_dynamics))
 
     # ------------------------------------------------------------------------------------------------
     def close(self):
@@ -280,6 +288,46 @@ class QuadVecEnv(object):
         self.set_field("omega", om, mask)
         self.set_field("thrust_rot_damp", [0., 0., 0., 0.], mask)
         self.set_field("thrust_cmds_damp", [0., 0., 0., 0.], mask)
+
+    # ---- per-env dynamics ------------------------------------------------------
+    def set_models(self, params_list, index=None):
+        """Per-env model constants: `params_list` = K parameter dicts, `index` [N] = model of every env (default: env i
+        flies model i % K).  Host cost is O(K) (QuadLink + Jacobian per model); the [rows, N, 4] buffer is gathered
+        on the device."""
+        t = self.torch
+        if not self.cfg.per_env_model:
+            raise RuntimeError("create the env with per_env_dynamics=... to use per-env models")
+        from .quadrotor.model import ModelConstants
+        consts = [p if isinstance(p, ModelConstants) else ModelConstants(p, gravity=self.model.gravity) for p in params_list]
+        table = np.stack([m.rows(self.dt) for m in consts], axis=1)                       # [rows, K, 4]
+        K = len(consts)
+        if index is None:
+            index = np.arange(self.num_envs) % K
+        idx = t.as_tensor(np.asarray(index), device=self.device, dtype=t.long)
+        tab = t.as_tensor(table, dtype=self.tdtype, device=self.device)
+        self.models = tab[:, idx, :].contiguous()
+        self.model_params, self.model_consts, self.model_index = list(params_list), consts, idx
+        _lib.check(self.lib.qs_bind_models(self._h, self.models.data_ptr()), self._h)
+
+    def resample_dynamics(self, n_models=None, seed=None):
+        """Draw a fresh set of models with the reference's sampler chain and deal them to the envs (call between
+        episodes, like the reference's resample_dynamics: a model change mid-episode is not meaningful)."""
+        import copy
+        dynamics_params, dynamics_change, s1, s2, _ = self._dyn_spec
+        K = int(n_models or len(self.model_params))
+        if seed is not None:
+            np.random.seed(seed)
+        out = []
+        for _ in range(K):
+            p = resolve_dynamics_params(dynamics_params, dynamics_change, check=False)
+            for spec in (s1, s2):
+                if spec is not None:
+                    kw = copy.deepcopy(spec)
+                    cls = kw.pop("class") if "class" in kw else kw.pop("type")
+                    p = getattr(quad_rand, cls)(params=p, **kw).sample(p)
+            out.append(quad_rand.check_quad_param_limits(p))
+        self.set_models(out, index=np.random.randint(0, K, size=self.num_envs))
+        return out
 
     # ---- noise injection (test mode) -----------------------------------------------------------------
     def set_noise(self, ou_z=None, obs_z=None, reset_z=None):

@@ -116,6 +116,15 @@ typedef enum QsNoiseMode {
 #define QS_INFO_DONE 31          /* done flag of the (last) step */
 #define QS_INFO_COSTS_RAW 32     /* the same 10 costs before weighting: rew_info 'rewraw_*' (quadrotor.py:619-630) */
 
+/* Per-env model buffer (dynamics randomisation, quadrotor_randomization.py + quadrotor.py:1030-1056 resample_dynamics):
+ * real[QS_MODEL_ROWS][n_envs][4], read-only for the kernels, one 16-byte vector per env per row:
+ *   0 thrust_max[4]            1 torque_max[k] * prop_ccw[k]     2 prop_pos[k].y     3 -prop_pos[k].x     4 prop_pos[k].z
+ *   5 inertia.xyz, mass        6 1/inertia.xyz, 1/mass
+ *   7 tau_up, tau_down (= min(1, 4 dt / (damp_time + 1e-6)), quadrotor.py:284-288), ou_sigma, arm
+ *   8 linearity, C_drag, C_roll, thrust_to_weight      9 vel_damp, damp_omega_quadratic, 0, 0
+ *   10..13 rows of the inverse Jacobian (quadrotor_control.py:192-211) */
+#define QS_MODEL_ROWS 14
+
 /* QuadrotorDynamics constants (quadrotor.py:142-208) + the controllers' inverse Jacobian (quadrotor_control.py:192-211) */
 typedef struct QsModel {
   double mass;
@@ -183,7 +192,7 @@ typedef struct QsConfig {
   double max_init_vel, max_init_omega; /* quadrotor.py:717-718 */
   double collision_k;  /* swarm: contact when |p_i - p_j| < collision_k * 2 * arm */
   int32_t use_formation; /* swarm: drone a of every swarm flies to formation[a] (no goal row in the state buffer) */
-  int32_t _pad2;
+  int32_t per_env_model; /* dynamics randomisation: model constants come from qs_bind_models, not from `model` */
   double formation[32][3];
   QsModel model;
   QsReward reward;
@@ -215,6 +224,9 @@ const char* qs_last_error(const QsHandle* h); /* h may be NULL: error of the las
 
 /* state: device buffer real[rows][n_envs][4]; the library never frees it */
 int qs_bind_state(QsHandle* h, void* state);
+/* QsConfig.per_env_model handles: device buffer real[QS_MODEL_ROWS][n_envs][4]; may be re-bound or rewritten between
+ * steps (the reference resamples dynamics between episodes); the library never frees it */
+int qs_bind_models(QsHandle* h, const void* models);
 /* optional diagnostics buffer real[n_envs][QS_INFO_DIM] (NULL to disable) */
 int qs_bind_info(QsHandle* h, void* info);
 /* QS_NOISE_INJECTED: device buffers of unit draws consumed by the next reset/step calls (any may be NULL = zeros) */

@@ -11,7 +11,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 ROLLOUT_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                       if os.path.basename(p) not in ("known_answer.npz", "model_answers.npz"))
+                       if os.path.basename(p) not in ("known_answer.npz", "model_answers.npz", "random_models.npz"))
 
 
 class Golden(object):

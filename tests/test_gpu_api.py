@@ -253,3 +253,87 @@ def test_errors_without_state_or_actions():
     assert lib.qs_step(h, None, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == _lib.QS_EINVAL   # raw needs actions
     assert lib.qs_set_noise_injection(h, None, None, None) == _lib.QS_EINVAL                            # Philox handle
     assert lib.qs_destroy(h) == _lib.QS_OK
+
+
+# ---- per-env dynamics ------------------------------------------------------------
+def _model_zoo():
+    import copy
+    from gym_art_b200.quadrotor import quad_models
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    np.random.seed(42)
+    zoo = [qr.RandomQuad().sample(), qr.RandomQuad().sample(), quad_models.crazyflie_params(), quad_models.defaultquad_params()]
+    drag = quad_models.crazyflie_params()
+    qr._update_existing(drag, {"motor": {"C_drag": 0.0028, "C_roll": 0.003, "linearity": 0.424, "damp_time_up": 0.1,
+                                          "damp_time_down": 0.3}, "damp": {"vel": 0.001, "omega_quadratic": 0.015}})
+    zoo.append(drag)
+    zoo.append(qr.RelativeSampler(copy.deepcopy(zoo[2]), noise_ratio=0.2).sample(copy.deepcopy(zoo[2])))
+    return zoo
+
+
+@pytest.mark.parametrize("ctrl,oc", [("raw", 0), ("omega_thrust", 4), ("mellinger", 6)])
+def test_per_env_models_match_oracle_fp64(ctrl, oc):
+    """Every env flies its own model (RandomQuad samples, CrazyFlie, Hummingbird, a drag/linearity variant, a
+    perturbed CrazyFlie): the device result equals the oracle run model by model, fp64, injected noise."""
+    from gym_art_b200 import QuadVecEnv
+    from oracle import quadsim_oracle as qo
+    zoo = _model_zoo()
+    K, per, T = len(zoo), 7, 60
+    n = K * per
+    index = np.arange(n) % K
+    rng = np.random.RandomState(3)
+    kw = dict(sim_steps=2, ep_time=0.25, sense_noise="default", obs_repr="xyz_vxyz_R_omega_acc_act", init_random_state=True)
+    env = QuadVecEnv(n, dynamics_params=zoo[3], controller=ctrl, dtype="float64", noise_mode="injected", auto_reset=True,
+                     per_env_dynamics=K, **kw)
+    env.set_models(zoo, index=index)
+    assert env.layout.row_ou >= 0
+    oes = [qo.OracleVecEnv(zoo[k], per, controller=oc, auto_reset=True, **kw) for k in range(K)]
+    sel = [np.where(index == k)[0] for k in range(K)]
+
+    def draws():
+        rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+        rz[:, qo.RZ_NUP:] = rng.standard_normal((n, qo.RESET_Z - qo.RZ_NUP))
+        return rz
+
+    rz = draws()
+    env.set_noise(reset_z=rz)
+    o = env.reset().cpu().numpy()
+    for k in range(K):
+        np.testing.assert_allclose(o[sel[k]], oes[k].reset(reset_z=rz[sel[k]]), rtol=0, atol=1e-12)
+    for t in range(T):
+        a = np.concatenate([rng.uniform(-0.2, 0.2, (n, 1)), rng.uniform(-1, 1, (n, 3))], axis=1) if ctrl == "omega_thrust" \
+            else rng.uniform(-1, 1, (n, 4))
+        ou_z, obs_z, rz = rng.standard_normal((n, 2, 4)), rng.standard_normal((n, qo.OBS_Z)), draws()
+        env.set_noise(ou_z=ou_z, obs_z=obs_z, reset_z=rz)
+        o, r, d = env.step(a)
+        assert env.kernel_variant == "generic-permodel-injected"
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for k in range(K):
+            s = sel[k]
+            oo, ro, do = oes[k].step(a[s], ou_z=ou_z[s], obs_z=obs_z[s], reset_z=rz[s])
+            assert np.array_equal(d[s], do)
+            np.testing.assert_allclose(o[s], oo, rtol=1e-9, atol=1e-9, err_msg="model %d step %d" % (k, t))
+            np.testing.assert_allclose(r[s], ro, rtol=0, atol=1e-10)
+    env.close()
+
+
+def test_per_env_dynamics_sampler_chain_fp32():
+    """per_env_dynamics=K with the reference's sampler chain (RandomQuad base + ConstValueSampler): models differ
+    between envs, the env flies (Mellinger keeps RandomQuads near the goal), resampling changes the buffer."""
+    import torch
+    n = 4096
+    env = _env(n, dynamics_params="RandomQuad", controller="mellinger", per_env_dynamics=64, ep_time=7,
+               dyn_sampler_1={"class": "ConstValueSampler", "params_change": {"noise": {"thrust_noise_ratio": 0.02}}})
+    assert len(env.model_params) == 64 and tuple(env.models.shape) == (14, n, 4)
+    masses = env.models[5, :, 3]
+    assert masses.unique().numel() == 64 and float(env.models[7, :, 2].max()) == pytest.approx(0.004)
+    env.reset()
+    for t in range(400):            # 2 s of flight (the oracle shows a median distance of ~0.03 m by then)
+        o, r, d = env.step(None)
+    env.check_finite()
+    dist = o[:, :3].norm(dim=1)
+    # (a few of the 64 random models are not stabilised by the fixed Mellinger gains; most hover at their goal)
+    assert float(dist.median()) < 0.2 and float(dist.quantile(0.75)) < 0.5, "RandomQuads under Mellinger should hover near the goal"
+    before = env.models.clone()
+    env.resample_dynamics(seed=5)
+    assert not torch.equal(before, env.models)
+    env.close()
