@@ -126,11 +126,13 @@ bool need_rare(const QsHandle* h) {
   if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) return true;
   if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
                     s.gyro_norm_std != 0.0)) return true;
-  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr || c.per_env_model) return true;
-  // swarms (and the log-distance reward that comes with them) have specialised kernels for the common step shape only
+  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
+  // swarms (and the log-distance reward that comes with them) and per-env models have specialised kernels for the
+  // common step shape only
   const bool plain = c.sim_steps == 2 && h->lay.obs_dim == 18 && h->lay.row_prev_action < 0 &&
                      c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA;
-  if ((c.n_agents > 1 || c.reward.log_pos) && !plain) return true;
+  if ((c.n_agents > 1 || c.reward.log_pos || c.per_env_model) && !plain) return true;
+  if (c.per_env_model && c.reward.log_pos) return true;
   return false;
 }
 
@@ -235,7 +237,7 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
   fill_params<R>(h, &p);
   p.k_steps = k;
   p.clock_advance = advance;
-  if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos)) p.need_rare = 1;   // specialised swarm kernels: k == 1 only
+  if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos || h->cfg.per_env_model)) p.need_rare = 1;   // specialised kernels: k == 1 only
   if (!advance) p.pdl = 0;                       // chunk launches of the host pipeline follow copies on side streams
   p.launch_ticket = h->d_ticket + 1 + 2 * slot;
   p.tile_counter = h->d_ticket + 2 + 2 * slot;

@@ -76,6 +76,14 @@ CASES = {
     "hb_xyzr_h_noise": (qo.CTRL_RAW, None, _uni(-1, 1, 4), 300, 14, False,
                         dict(dynamics_params="DefaultQuad", ep_time=1, sense_noise="default",
                              obs_repr="xyzr_vxyzr_R_omega_h")),
+    # dynamics randomisation: the reference samples a RandomQuad / perturbs the CrazyFlie itself
+    "rq_raw_noise": (qo.CTRL_RAW, None, _uni(-0.6, 1.0, 4), 300, 16, False,
+                     dict(dynamics_params="RandomQuad", ep_time=1, sense_noise="default")),
+    "rq_mellinger": (qo.CTRL_MELLINGER, None, _uni(0, 0, 4), 450, 17, False,
+                     dict(dynamics_params="RandomQuad", raw_control=False, ep_time=2, init_random_state=True)),
+    "cf_relative_omegathrust": (qo.CTRL_OMEGA_THRUST, "omega_thrust", _act_omega_thrust, 300, 18, False,
+                                dict(dynamics_params="Crazyflie", ep_time=1,
+                                     dyn_sampler_1={"class": "RelativeSampler", "noise_ratio": 0.2, "sampler": "normal"})),
     "mq_raw_simsteps4": (qo.CTRL_RAW, None, _uni(-0.5, 0.8, 4), 300, 15, False,
                          dict(dynamics_params="MediumQuad", ep_time=2, sim_steps=4, sim_freq=100.0)),
 }

@@ -337,3 +337,47 @@ def test_per_env_dynamics_sampler_chain_fp32():
     env.resample_dynamics(seed=5)
     assert not torch.equal(before, env.models)
     env.close()
+
+
+@pytest.mark.parametrize("ctrl,oc", [("raw", 0), ("mellinger", 6)])
+def test_per_env_models_fast_kernel_fp32(ctrl, oc):
+    """The specialised per-env-model variant of the TMA kernel (multi-tile persistent path), fp32, per step from a
+    re-synchronised state against the oracle run model by model: 1e-5 relative."""
+    from gym_art_b200 import QuadVecEnv
+    from oracle import quadsim_oracle as qo
+    zoo = [z for i, z in enumerate(_model_zoo()) if i != 4]      # the drag/linearity model belongs to the generic kernel
+    K, per, T = len(zoo), 15400, 12
+    n = K * per                                                   # 77,000 envs > 148 x 4 resident tiles of 128
+    index = np.arange(n) % K
+    rng = np.random.RandomState(9)
+    kw = dict(sim_steps=2, ep_time=5, sense_noise="default")
+    env = QuadVecEnv(n, dynamics_params=zoo[3], controller=ctrl, noise_mode="injected", auto_reset=True, per_env_dynamics=K, **kw)
+    env.set_models(zoo, index=index)
+    oes = [qo.OracleVecEnv(zoo[k], per, controller=oc, auto_reset=True, **kw) for k in range(K)]
+    sel = [np.where(index == k)[0] for k in range(K)]
+    rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+    env.set_noise(reset_z=rz)
+    env.reset()
+    for k in range(K):
+        oes[k].reset(reset_z=rz[sel[k]])
+    fields = (("pos", "pos"), ("vel", "vel"), ("rot", "rot"), ("omega", "omega"), ("thrust_rot_damp", "rot_damp"),
+              ("thrust_cmds_damp", "cmds_damp"), ("ou_state", "ou"))
+    for t in range(T):
+        dev = {f: env.get_field(f).double().cpu().numpy() for f, _ in fields}
+        for k in range(K):                                        # the oracle continues from the device's fp32 state
+            for f, of in fields:
+                setattr(oes[k], of, dev[f][sel[k]].copy())
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32).astype(np.float64)
+        ou_z = rng.standard_normal((n, 2, 4)).astype(np.float32).astype(np.float64)
+        obs_z = rng.standard_normal((n, qo.OBS_Z)).astype(np.float32).astype(np.float64)
+        env.set_noise(ou_z=ou_z, obs_z=obs_z)
+        o, r, d = env.step(a)
+        assert env.kernel_variant == "tma-%s-injected" % ctrl
+        o, r = o.double().cpu().numpy(), r.double().cpu().numpy()
+        for k in range(K):
+            s = sel[k]
+            oo, ro, do = oes[k].step(a[s], ou_z=ou_z[s], obs_z=obs_z[s])
+            err = np.max(np.abs(o[s] - oo) / np.maximum(np.abs(oo), 1.0))
+            assert err < 1e-5, (k, t, err)
+            assert np.max(np.abs(r[s] - ro)) < 1e-6
+    env.close()
