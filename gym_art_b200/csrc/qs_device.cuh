@@ -1120,9 +1120,32 @@ struct StepOut {
   double svd_t;                   // value of the global re-orthonormalisation timer after the last substep
 };
 
+// Draws of one env step that depend only on (global env id, step index): generated BEFORE the state is needed so
+// that the Philox / Box-Muller chains overlap the loads in flight (kernels with compile-time sim_steps, k_steps == 1)
+template <typename R, class T>
+struct Pre {
+  static constexpr int N = T::SIM > 0 ? T::SIM : 1;
+  R zou[N][4];
+  R zobs[9];
+};
+
+template <typename R, class T>
+__device__ __forceinline__ void predraw(const Params<R>& p, long long i, bool active, unsigned long long step0, Pre<R, T>& pre) {
+  NoiseSrc<R, T> ns(p, active ? i : 0);
+  ns.begin_step(step0);
+  const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+  const bool sense = T::SENSE >= 0 ? (T::SENSE != 0) : (p.sense_on != 0);
+  if (ou_on) {
+#pragma unroll
+    for (int sub = 0; sub < Pre<R, T>::N; ++sub) ns.ou(sub, pre.zou[sub]);
+  }
+  if (sense) { ns.obs3(false, 0, false, pre.zobs); ns.obs3(false, 2, false, pre.zobs + 3); ns.obs3(false, 4, false, pre.zobs + 6); }
+}
+
 template <typename R, class T>
 __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long long i, bool active, const R* a_first,
-                                          double svd_t0, unsigned long long step0, R* o, StepOut<R>& out) {
+                                          double svd_t0, unsigned long long step0, R* o, StepOut<R>& out,
+                                          const Pre<R, T>* pre = nullptr) {
   const int ctrl = T::CTRL >= 0 ? T::CTRL : p.controller;
   NoiseSrc<R, T> ns(p, active ? i : 0);
   const Mdl<R, T::PEM> m(p, active ? i : p.begin);
@@ -1141,15 +1164,13 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // Philox / Box-Muller chains then overlap the state loads still in flight and each other instead of sitting on
     // the dynamics' critical path.
     constexpr int NPRE = T::SIM > 0 ? T::SIM : 1;
-    R zou[NPRE][4];
-    R zobs[9];
-    if (T::SIM > 0) {
-      if (ou_on) {
+    constexpr bool PRE = T::SIM > 0 && T::PLAIN;                        // k_steps == 1: the caller drew everything already
+    Pre<R, T> own;
+    if (T::SIM > 0 && !PRE && ou_on) {
 #pragma unroll
-        for (int sub = 0; sub < NPRE; ++sub) ns.ou(sub, zou[sub]);
-      }
-      if (T::PLAIN && sense) { ns.obs3(false, 0, false, zobs); ns.obs3(false, 2, false, zobs + 3); ns.obs3(false, 4, false, zobs + 6); }
+      for (int sub = 0; sub < NPRE; ++sub) ns.ou(sub, own.zou[sub]);
     }
+    const Pre<R, T>& dr = PRE ? *pre : own;
     // ---- action (:943-944) ----
     R a[4] = {R(0), R(0), R(0), R(0)};
     if (a_first != nullptr && ks == 0) {
@@ -1170,7 +1191,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
 #pragma unroll
       for (int sub = 0; sub < NPRE; ++sub) {
         const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);        // :381-386
-        substep<R, T>(s, cmd, p, m, zou[sub], fire);
+        substep<R, T>(s, cmd, p, m, dr.zou[sub], fire);
       }
     } else {
 #pragma unroll 1
@@ -1215,7 +1236,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----
     const bool walk = T::RARE && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
     const bool resetting = done && p.auto_reset;
-    if ((last && !resetting) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o, (T::SIM > 0 && T::PLAIN && sense) ? zobs : nullptr);
+    if ((last && !resetting) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o, (PRE && sense) ? dr.zobs : nullptr);
     if (done) {
       if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
       if (resetting) {
@@ -1314,6 +1335,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -1351,7 +1377,10 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 //   * a launch that fits in one wave (small N) skips the async machinery and uses plain vector loads;
 //   * the state goes back to HBM straight from registers (coalesced 16-byte stores); the CTA transposes its 128
 //     observation rows through shared memory and ships them as one cp.async.bulk store.
-template <class T>
+// ONEWAVE: the launch has no more tiles than resident CTA slots (small N).  That case is latency-bound, so it gets its
+// own instantiation with the ring, the mbarriers and every CTA barrier compiled out: direct vector loads, per-warp
+// observation flush.  (tests/test_gpu_fullsize.py holds both instantiations to bit-identical results.)
+template <class T, bool ONEWAVE>
 __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   typedef float R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1365,10 +1394,11 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
   const int obs_dim = T::PLAIN ? 18 : p.obs_dim;
   const int obs_tile_floats = BLOCK * obs_dim;                           // per stage
   float4* in = reinterpret_cast<float4*>(smem_raw);
-  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (size_t)2 * stage_vecs * sizeof(float4));
+  // (a one-wave launch allocates only the observation tile)
+  float* obs_tiles = reinterpret_cast<float*>(smem_raw + (ONEWAVE ? (size_t)0 : (size_t)2 * stage_vecs * sizeof(float4)));
   const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
   const long long G = gridDim.x;
-  const bool multi = n_tiles > G;                                        // more tiles than resident CTAs
+  constexpr bool multi = !ONEWAVE;                                       // more tiles than resident CTAs
 
   __shared__ unsigned int warps_done;
   if (!multi) {
@@ -1381,48 +1411,6 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
   double svd_end = svd_t0;
-
-  if (!multi) {
-    // ---- one-wave launch (small N): latency-bound, so no CTA barrier anywhere: direct vector loads, every warp
-    // transposes and ships its own 32 observation rows, the last warp to finish takes the CTA's launch ticket ----
-    const long long i = p.begin + (long long)blockIdx.x * BLOCK + tid;
-    const bool active = i < p.end;
-    St<R> s;
-    R a0[4] = {0.f, 0.f, 0.f, 0.f};
-    load_state<R, T>(s, p, i, active);
-    if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
-    R o[26];
-    StepOut<R> out;
-    run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out);
-    if (active) {
-      store_state<R, T>(s, p, i);
-      p.rew[i] = out.rew_sum;
-      p.done[i] = out.done_any ? 1 : 0;
-    }
-    float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
-    obs_to_tile<R, T::PLAIN>(p, o, wtile + lane * obs_dim);
-    __syncwarp();
-    const long long warp_first = i - lane;
-    long long rows = p.end - warp_first;
-    if (rows > 32) rows = 32;
-    if (rows > 0) {
-      const int total = (int)rows * obs_dim;
-      float* dst = p.obs + warp_first * obs_dim;               // 128 * obs_dim bytes per full warp: 16-byte aligned
-      if ((total & 3) == 0) {
-        const float4* t4 = reinterpret_cast<const float4*>(wtile);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int k = lane; k < (total >> 2); k += 32) d4[k] = t4[k];
-      } else {
-        for (int k = lane; k < total; k += 32) dst[k] = wtile[k];
-      }
-    }
-    if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
-    // (the clock was read at the top of every thread, and run_steps depended on the values: no fence needed here)
-    if (lane == 0) {
-      if (atomicAdd(&warps_done, 1u) == WARPS - 1) finish_launch_one(p, out.svd_t, (unsigned long long)p.k_steps);
-    }
-    return;
-  }
 
   auto issue_load = [&](long long tile, int stage) {
     const long long first = p.begin + tile * BLOCK;
@@ -1446,13 +1434,11 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
       mbar_init(&empty_bar[0], WARPS); mbar_init(&empty_bar[1], WARPS);
       fence_mbar_init();
-      // tile j of this CTA lives in stage j & 1 (tile 0 is read directly): prefetch the next two right away
+      // tile j of this CTA lives in stage j & 1.  Tile 0 is copied into stage 0 by the threads themselves (below);
+      // the producer prefetches tile 1 now and refills a stage whenever the four warps have drained it.
       const long long t1 = fetch_tile();
       tile_slot[1] = t1;
       if (t1 >= 0) issue_load(t1, 1);
-      const long long t2 = t1 >= 0 ? fetch_tile() : -1;
-      tile_slot[0] = t2;
-      if (t2 >= 0) issue_load(t2, 0);
     }
     __syncthreads();
   }
@@ -1467,24 +1453,41 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
     const long long i = block_first + tid;
     const bool active = i < p.end;
 
+    // ---- tile data.  First tile of the CTA: every thread copies its own nine 16-byte vectors into stage 0 with
+    // cp.async (no register scoreboard is held, so the draws below are generated while the copies are in flight);
+    // later tiles were put into the ring by the producer's bulk copies.
+    const bool ou_row = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
+    const bool act_row = !T::PLAIN && p.row_act >= 0;
+    float4* buf = in + (size_t)stage * stage_vecs + tid;
     St<R> s;
     R a0[4] = {0.f, 0.f, 0.f, 0.f};
-    if (j == 0) {
-      // first tile of the CTA: direct loads (nothing was prefetched yet)
+    if (ONEWAVE) {
       load_state<R, T>(s, p, i, active);
       if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
-    } else {
-      mbar_wait(&full_bar[stage], (full_phase >> stage) & 1u);
-      full_phase ^= (1u << stage);
+    } else if (j == 0) {
+      const long long il = active ? i : p.end - 1;                       // lanes beyond the last env: any valid env
+      const char* ptr = reinterpret_cast<const char*>(p.state + il * 4);
+      for (int r = 0; r < rows_in; ++r) cp_async16(buf + r * BLOCK, ptr + r * p.row_bytes);
+      if (has_act) cp_async16(buf + rows_in * BLOCK, p.actions + il * 4);
+      cp_async_commit();
+    }
+    Pre<R, T> pre;
+    if (T::SIM > 0 && T::PLAIN) predraw<R, T>(p, i, active, step0, pre);
+    if (multi) {
+      if (j == 0) {
+        cp_async_wait_all();                                             // a thread reads back only what it copied itself
+      } else {
+        mbar_wait(&full_bar[stage], (full_phase >> stage) & 1u);
+        full_phase ^= (1u << stage);
+      }
       // lanes beyond the last env of a ragged tile read stale shared memory: harmless, nothing of theirs is stored
-      const float4* buf = in + (size_t)stage * stage_vecs + tid;
       unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
       init_optional<R, T::SWARM>(s, p);
-      const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
-      if (ou_on) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
-      if (!T::PLAIN && p.row_act >= 0) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
+      if (ou_row) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
+      if (act_row) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
       if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
       finish_load(s);
+
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);                     // this warp is done with the stage
       if (tid == 0) {
@@ -1499,13 +1502,41 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
 
     R o[26];
     StepOut<R> out;
-    run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out);
+    run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out, &pre);
     svd_end = out.svd_t;
 
     if (active) {
       store_state<R, T>(s, p, i);
       p.rew[i] = out.rew_sum;
       p.done[i] = out.done_any ? 1 : 0;
+    }
+    if (!multi) {
+      // ---- one-wave launch (small N): latency-bound, so no CTA barrier anywhere - every warp transposes and ships
+      // its own 32 observation rows, the last warp to finish takes the CTA's launch ticket.  (Same run_steps
+      // instance as the pipelined path: results do not depend on which path a batch size selects.)
+      float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
+      obs_to_tile<R, T::PLAIN>(p, o, wtile + lane * obs_dim);
+      __syncwarp();
+      const long long warp_first = i - lane;
+      long long wrows = p.end - warp_first;
+      if (wrows > 32) wrows = 32;
+      if (wrows > 0) {
+        const int total = (int)wrows * obs_dim;
+        float* dst = p.obs + warp_first * obs_dim;             // 128 * obs_dim bytes per full warp: 16-byte aligned
+        if ((total & 3) == 0) {
+          const float4* t4 = reinterpret_cast<const float4*>(wtile);
+          float4* d4 = reinterpret_cast<float4*>(dst);
+          for (int k = lane; k < (total >> 2); k += 32) d4[k] = t4[k];
+        } else {
+          for (int k = lane; k < total; k += 32) dst[k] = wtile[k];
+        }
+      }
+      if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
+      // (the clock was read at the top of every thread, and run_steps depended on the values: no fence needed here)
+      if (lane == 0) {
+        if (atomicAdd(&warps_done, 1u) == WARPS - 1) finish_launch_one(p, out.svd_t, (unsigned long long)p.k_steps);
+      }
+      return;
     }
     // observation rows: registers -> shared tile -> one bulk store per CTA
     float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;

@@ -15,21 +15,14 @@ static int sm_count() {
   return n;
 }
 
-template <class T>
-static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
-  const long long tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
-  const size_t smem = (size_t)2 * (p.tma_rows + 1) * BLOCK * sizeof(float4) + (size_t)2 * BLOCK * p.obs_dim * sizeof(float);
+template <class T, bool ONEWAVE>
+static cudaError_t launch_tma_w(const Params<float>& p, cudaStream_t st, unsigned grid, size_t smem) {
   static bool attr_set = false;   // one flag per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(env_step_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(env_step_tma_kernel<T, ONEWAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  int per_sm = (int)((227 * 1024) / (smem + 1024 + 128));
-  if (per_sm > TMA_MIN_CTAS) per_sm = TMA_MIN_CTAS;
-  if (per_sm < 1) per_sm = 1;
-  long long slots = (long long)sm_count() * per_sm;
-  const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(BLOCK);
@@ -40,7 +33,20 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T>, p);
+  return cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T, ONEWAVE>, p);
+}
+
+template <class T>
+static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
+  const long long tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
+  const size_t smem = (size_t)2 * (p.tma_rows + 1) * BLOCK * sizeof(float4) + (size_t)2 * BLOCK * p.obs_dim * sizeof(float);
+  int per_sm = (int)((227 * 1024) / (smem + 1024 + 128));
+  if (per_sm > TMA_MIN_CTAS) per_sm = TMA_MIN_CTAS;
+  if (per_sm < 1) per_sm = 1;
+  const long long slots = (long long)sm_count() * per_sm;
+  if (tiles <= slots)                                                                 // one wave: one tile per CTA
+    return launch_tma_w<T, true>(p, st, (unsigned)tiles, (size_t)BLOCK * p.obs_dim * sizeof(float));
+  return launch_tma_w<T, false>(p, st, (unsigned)slots, smem);                        // persistent CTAs, tile ring
 }
 
 template <int C, int SIM, bool PLAIN, bool SWARM>

@@ -133,8 +133,11 @@ def test_step_k_equals_k_steps():
             rsum += r1
             dany |= d1
         o2, r2, d2 = e2.step_k(K, a)
-        assert torch.equal(o1, o2) and torch.equal(dany, d2) and torch.allclose(rsum, r2, rtol=0, atol=1e-6)
-        assert torch.equal(e1.state, e2.state) and e1.clock == e2.clock
+        # same draws, same episode bookkeeping; the K-step kernel is a different template instantiation, so its
+        # floating-point contraction may differ in the last bit per step
+        assert torch.equal(dany, d2) and torch.allclose(rsum, r2, rtol=0, atol=1e-6) and e1.clock == e2.clock
+        assert torch.allclose(o1, o2, rtol=1e-5, atol=1e-5) and torch.allclose(e1.state, e2.state, rtol=1e-5, atol=1e-5)
+        assert torch.equal(e1.tick, e2.tick)
 
 
 @pytest.mark.parametrize("pinned", [True, False])
