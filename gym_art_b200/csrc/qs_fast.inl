@@ -44,8 +44,9 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
   if (per_sm > TMA_MIN_CTAS) per_sm = TMA_MIN_CTAS;
   if (per_sm < 1) per_sm = 1;
   const long long slots = (long long)sm_count() * per_sm;
-  if (tiles <= slots)                                                                 // one wave: one tile per CTA
-    return launch_tma_w<T, true>(p, st, (unsigned)tiles, (size_t)BLOCK * p.obs_dim * sizeof(float));
+  // one wave: one tile per CTA.  The kernel needs only the observation tile, but it is given the full allocation so
+  // that at most per_sm CTAs share an SM: the launch is latency-bound and its time is set by the fullest SM.
+  if (tiles <= slots) return launch_tma_w<T, true>(p, st, (unsigned)tiles, smem);
   return launch_tma_w<T, false>(p, st, (unsigned)slots, smem);                        // persistent CTAs, tile ring
 }
 
