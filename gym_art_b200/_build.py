@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libquadsim.so")
-FAST = ["qs_fast_%s_%s.cu" % (c, n) for c in ("raw", "omega", "mellinger") for n in ("philox", "inject")]
+FAST = ["qs_fast_%s_%s.cu" % (c, n) for c in ("raw", "omega", "mellinger", "shifted", "velyaw") for n in ("philox", "inject")]
 SOURCES = ["qs_kernels_f32.cu", "qs_kernels_f64.cu", "quadsim_abi.cu"] + FAST
 DEPS = ["qs_device.cuh", "qs_kernels.inl", "qs_fast.inl", os.path.join("..", "..", "include", "quadsim.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

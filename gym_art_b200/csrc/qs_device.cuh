@@ -1661,6 +1661,10 @@ QS_DECL_FAST(launch_fast_omega_philox);
 QS_DECL_FAST(launch_fast_omega_inject);
 QS_DECL_FAST(launch_fast_mellinger_philox);
 QS_DECL_FAST(launch_fast_mellinger_inject);
+QS_DECL_FAST(launch_fast_shifted_philox);
+QS_DECL_FAST(launch_fast_shifted_inject);
+QS_DECL_FAST(launch_fast_velyaw_philox);
+QS_DECL_FAST(launch_fast_velyaw_inject);
 #undef QS_DECL_FAST
 
 }  // namespace qs

@@ -1,0 +1,7 @@
+// fp32 fast subset, controller shifted, philox noise (one translation unit per controller x noise source: they compile in parallel)
+#define QS_FAST_INJECT 0
+#define QS_FAST_CTRL qs::CTRL_SHIFTED
+#define QS_FAST_LABEL "tma-shifted"
+#define QS_FAST_NAME launch_fast_shifted_philox
+#define QS_FAST_SUFFIX ""
+#include "qs_fast.inl"

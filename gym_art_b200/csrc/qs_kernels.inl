@@ -22,9 +22,12 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
   typedef QS_REAL R;
 #ifdef QS_FAST_VARIANTS
   if (!p.need_rare && p.act_dim == 4 &&
-      (p.controller == CTRL_RAW || p.controller == CTRL_OMEGA_THRUST || p.controller == CTRL_MELLINGER)) {
+      (p.controller == CTRL_RAW || p.controller == CTRL_OMEGA_THRUST || p.controller == CTRL_MELLINGER ||
+       p.controller == CTRL_SHIFTED || p.controller == CTRL_VELOCITY_YAW)) {
     if (p.controller == CTRL_RAW) return p.inject ? launch_fast_raw_inject(p, st, name) : launch_fast_raw_philox(p, st, name);
     if (p.controller == CTRL_OMEGA_THRUST) return p.inject ? launch_fast_omega_inject(p, st, name) : launch_fast_omega_philox(p, st, name);
+    if (p.controller == CTRL_SHIFTED) return p.inject ? launch_fast_shifted_inject(p, st, name) : launch_fast_shifted_philox(p, st, name);
+    if (p.controller == CTRL_VELOCITY_YAW) return p.inject ? launch_fast_velyaw_inject(p, st, name) : launch_fast_velyaw_philox(p, st, name);
     return p.inject ? launch_fast_mellinger_inject(p, st, name) : launch_fast_mellinger_philox(p, st, name);
   }
 #endif
