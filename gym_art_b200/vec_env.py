@@ -207,12 +207,38 @@ class QuadVecEnv(object):
         if info:
             _lib.check(self.lib.qs_bind_info(self._h, self.info.data_ptr()), self._h)
         self._noise_refs = None
+        # spaces of ONE env, as the reference's controller / env report them (quadrotor.py:890, :898-936)
+        from .quadrotor.spaces import Box
+        lo, hi = self._action_bounds()
+        self.action_space = Box(lo, hi, dtype=np.float32)
+        rb = np.array([[-room_size, -room_size, 0.], [room_size, room_size, room_size]], dtype=np.float64)
+        comp = {"xyz": (-(rb[1] - rb[0]), rb[1] - rb[0]), "vxyz": (-3. * np.ones(3), 3. * np.ones(3)), "R": (-np.ones(9), np.ones(9)),
+                "omega": (-40. * np.ones(3), 40. * np.ones(3)), "h": (np.zeros(1), rb[1][2] * np.ones(1)),
+                "acc": (-3. * GRAV * np.ones(3), 3. * GRAV * np.ones(3)), "act": (np.zeros(4), np.ones(4))}
+        comp["xyzr"], comp["vxyzr"] = comp["xyz"], comp["vxyz"]
+        names = obs_repr.split("_")
+        self.observation_space = Box(np.concatenate([comp[c][0] for c in names]), np.concatenate([comp[c][1] for c in names]),
+                                     dtype=np.float32)
         self.models, self.model_params, self.model_index = None, None, None
         if per_env_dynamics is not None:
             # dynamics randomisation (quadrotor.py:738-763, :1030-1056): `per_env_dynamics` independently sampled models
             # (base sampler -> dynamics_change -> sampler 1 -> sampler 2 -> limits), dealt to the envs at random
             self._dyn_spec = (dynamics_params, dynamics_change, dyn_sampler_1, dyn_sampler_2, gravity)
             self.resample_dynamics(n_models=int(per_env_dynamics))
+
+    def _action_bounds(self):
+        """quadrotor_control.py action_space() of the selected controller."""
+        c, t2w = self.controller_name, self.model.thrust_to_weight
+        if c in ("raw", "vertical", "vertplane"):
+            d = {"raw": 4, "vertical": 1, "vertplane": 2}[c]
+            return (-np.ones(d) if self.cfg.zero_middle else np.zeros(d)), np.ones(d)
+        if c == "shifted":
+            return -np.ones(4), (t2w - 1.0) * np.ones(4)
+        if c == "velocity_yaw":
+            hi = np.array([20., 20., 20., 4 * np.pi])
+            return -hi, hi
+        hi = np.array([t2w - 1.0, 10 * np.pi, 10 * np.pi, 2 * np.pi])       # omega_thrust / mellinger :213-221, :514-522
+        return np.array([-1.0, -hi[1], -hi[2], -hi[3]]), hi
 
     # ------------------------------------------------------------------------------------------------
     def close(self):
@@ -369,6 +395,25 @@ class QuadVecEnv(object):
         _lib.check(self.lib.qs_step(self._h, None if a is None else a.data_ptr(), self.obs.data_ptr(), self.rew.data_ptr(),
                                     self._done_u8.data_ptr(), self._stream()), self._h)
         return self.obs, self.rew, self.done
+
+    def capture_steps(self, n_steps, actions=None):
+        """CUDA graph of `n_steps` consecutive env steps reading `actions` ([N, A] device tensor the caller refills
+        between replays, or None for the in-kernel Mellinger controller).  The clock lives on the device, so every
+        replay continues the simulation with fresh noise; launches carry the PDL attribute, so consecutive steps
+        overlap launch latency (the caller loop of quadrotor.py:1278-1305 without per-step host work).
+        Returns the torch.cuda.CUDAGraph; outputs land in self.obs / self.rew / self.done."""
+        t = self.torch
+        a = self._actions(actions)
+        stream = t.cuda.Stream(device=self.device)
+        stream.wait_stream(t.cuda.current_stream(self.device))
+        with t.cuda.stream(stream):
+            self.step(a)                                  # warm-up outside the capture (lazy module loading)
+        stream.synchronize()
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g, stream=stream):
+            for _ in range(int(n_steps)):
+                self.step(a)
+        return g
 
     def step_k(self, k, actions=None):
         """k fused env steps in one launch; returns (last obs, summed reward, any-done)."""

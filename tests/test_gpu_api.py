@@ -384,3 +384,24 @@ def test_per_env_models_fast_kernel_fp32(ctrl, oc):
             assert err < 1e-5, (k, t, err)
             assert np.max(np.abs(r[s] - ro)) < 1e-6
     env.close()
+
+
+def test_capture_steps_graph_and_spaces():
+    import torch
+    n = 2048
+    e1, e2 = _env(n, sense_noise="default"), _env(n, sense_noise="default")
+    assert e1.action_space.shape == (4,) and e1.observation_space.shape == (18,) and float(e1.action_space.low[0]) == -1.0
+    e1.reset(), e2.reset()
+    a = torch.rand((n, 4), device="cuda") * 2 - 1
+    g = e2.capture_steps(5, a)              # runs one warm-up step, then captures five
+    e1.step(a)
+    for rep in range(3):
+        a.uniform_(-1, 1)                   # the graph reads the caller's action tensor at replay time
+        for _ in range(5):
+            e1.step(a)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(e1.obs, e2.obs) and torch.equal(e1.rew, e2.rew) and torch.equal(e1.state, e2.state)
+    assert e1.clock == e2.clock and e2.clock[1] == 1 + 16
+    m = _env(64, controller="omega_thrust", dynamics_params="Crazyflie")
+    assert m.action_space.high[0] == pytest.approx(0.9) and m.action_space.low[1] == pytest.approx(-10 * np.pi)
