@@ -912,7 +912,10 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     } else {
       wx += p.sn_gyro_density * z[0]; wy += p.sn_gyro_density * z[1]; wz += p.sn_gyro_density * z[2];   // :130-131
     }
-    // rotation: R -> quaternion -> (x small-angle quaternion) -> R (:134-147); a pure round trip by default
+    // rotation: R -> quaternion -> (x small-angle quaternion) -> R (:134-147).  Without quaternion noise (the default,
+    // and the only case in the fast subset) the float64 reference's round trip returns R to 1e-15; an fp32 round trip
+    // would only add rounding, so the fast kernels pass R through.
+    if (!T::FASTM) {
     R q[4];
     rot2quat<R, T::FASTM>(s.r, q);
     if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) {
@@ -938,6 +941,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     rr[0] = R(1) - R(2) * qy * qy - R(2) * qz * qz; rr[1] = R(2) * qx * qy - R(2) * qz * qw; rr[2] = R(2) * qx * qz + R(2) * qy * qw;
     rr[3] = R(2) * qx * qy + R(2) * qz * qw; rr[4] = R(1) - R(2) * qx * qx - R(2) * qz * qz; rr[5] = R(2) * qy * qz - R(2) * qx * qw;
     rr[6] = R(2) * qx * qz - R(2) * qy * qw; rr[7] = R(2) * qy * qz + R(2) * qx * qw; rr[8] = R(1) - R(2) * qx * qx - R(2) * qy * qy;
+    }
     if (obs_acc) {                                                      // :156-157
       R zs[3], zd[3];
       ns.obs3(reset_obs, 8, false, zs);
@@ -1094,15 +1098,18 @@ __device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p) {
   for (int j = 1; j < M; ++j) {
     int src = base | ((lane + j) & (M - 1));
     R qx = shfl(s.px, src), qy = shfl(s.py, src), qz = shfl(s.pz, src);
-    R ux = shfl(s.vx, src), uy = shfl(s.vy, src), uz = shfl(s.vz, src);
     R dx = s.px - qx, dy = s.py - qy, dz = s.pz - qz;
     R dist = Mth<R>::sqrt(dx * dx + dy * dy + dz * dz);
-    R inv = R(1) / Mth<R>::max(dist, R(1e-5));
-    R nx = dx * inv, ny = dy * inv, nz = dz * inv;
-    R delta = (ux - s.vx) * nx + (uy - s.vy) * ny + (uz - s.vz) * nz;
     bool c = dist < p.coll_dist;
     hit = hit || c;
-    if (c && delta > R(0)) { dvx += delta * nx; dvy += delta * ny; dvz += delta * nz; }
+    // contacts are rare: the partner's velocity is fetched (warp-convergent shuffles) only when some lane needs it
+    if (__any_sync(0xffffffffu, c)) {
+      R ux = shfl(s.vx, src), uy = shfl(s.vy, src), uz = shfl(s.vz, src);
+      R inv = R(1) / Mth<R>::max(dist, R(1e-5));
+      R nx = dx * inv, ny = dy * inv, nz = dz * inv;
+      R delta = (ux - s.vx) * nx + (uy - s.vy) * ny + (uz - s.vz) * nz;
+      if (c && delta > R(0)) { dvx += delta * nx; dvy += delta * ny; dvz += delta * nz; }
+    }
   }
   s.vx += dvx; s.vy += dvy; s.vz += dvz;
   return hit;
