@@ -32,7 +32,9 @@ static cudaError_t launch_tma_w(const Params<float>& p, cudaStream_t st, unsigne
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = p.pdl ? 1 : 0;
+  // measured on B200 (tools/small_sweep.py): for grids under ~320 CTAs the dependent-launch hand-over costs more
+  // than the launch ramp it hides (5.1 vs 3.6 us per step at 128 CTAs); above, it wins (6.8 vs 7.5 us at 512 CTAs)
+  cfg.numAttrs = (p.pdl && grid >= 320u) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T, ONEWAVE>, p);
 }
 
