@@ -322,6 +322,23 @@ def run_ours(args):
                        "roofline_frac": n_o * bytes_o / (ms_o * 1e-3 / KO) / 1e9 / hbm_peak}
         e.close()
         del e, a_o
+    # f1: K env steps fused in one launch with the state held in registers - the closed-loop
+    # lever once a single step is at the HBM roofline (Mellinger in-kernel, no action input)
+    KF, n_f = 8, 4 << 20
+    e = make_env(n_f, device, seed=4, env_id_offset=rank * n_f, cfg="cfg5")
+    e.reset()
+    RING_PERIOD[0] = 1
+    ms_f = time_graph(torch, lambda i: e.step_k(KF, None), 20, 3, device, dist if multi else None, None)
+    tf = torch.tensor([ms_f], device=device, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+    ms_f = float(tf.item())
+    e.check_finite()
+    others["cfg5_fused_k8"] = {"n_envs_per_gpu_step": n_f, "k_steps_per_launch": KF, "value": world * n_f * KF * 20 / (ms_f * 1e-3),
+                               "unit": "env-steps/s", "ms_per_launch": ms_f / 20, "kernel_variant": e.kernel_variant,
+                               "note": "qs_step_k: HBM is touched once per K env steps, so the per-step HBM roofline does not apply"}
+    e.close()
+    del e
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through qs_step_host -------------------------------------------------------------------

@@ -236,10 +236,14 @@ class QuadrotorDynamics(object):
         return (1 - linearity) * w ** 2 + linearity * w
 
     def look_at(self):                                                                       # :527-534
-        degrees_down = 45.0
+        """eye, center, up of the onboard camera (45 degrees down), for gluLookAt-style renderers."""
         R = self.rot
-        look = R[:, 0] * np.cos(np.radians(degrees_down)) - R[:, 2] * np.sin(np.radians(degrees_down))
-        return self.pos, self.pos + look, R[:, 2]
+        eye = self.pos + R @ np.array([0., 0., -0.02])
+        theta = np.radians(45.0)
+        to = np.cos(theta) * R[:, 0] - np.sin(theta) * R[:, 2]
+        n = np.linalg.norm(to)
+        to = to / n if n >= 1e-5 else to
+        return eye, eye + to, np.cross(to, R[:, 1])
 
     def close(self):
         for h in self._handles.values():
