@@ -80,7 +80,8 @@ class QuadrotorDynamics(object):
             self._vec_kwargs = dict(dynamics_params=self.model_params, controller="raw", dim_mode=dim_mode,
                                     sim_steps=dynamics_steps_num, room_size=float(self.room_box[1][2]), gravity=gravity,
                                     device=device, dtype=dtype, seed=seed, auto_reset=False, info=True,
-                                    noise_mode=noise_mode, goals=np.zeros((self.num_envs, 3)))
+                                    noise_mode=noise_mode, goals=np.zeros((self.num_envs, 3)),
+                                    host_mapped=self.num_envs <= 64)
             self._handle(1.0 / 200.0, True)        # allocates the state tensor; re-keyed by the dt of the first step
             self.set_state(np.zeros(3), np.zeros(3), np.eye(3), np.zeros(3))
 
@@ -132,18 +133,39 @@ class QuadrotorDynamics(object):
         return _OUView(self)
 
     def _get(self, name):
-        v = self._vec.get_field(name).double().cpu().numpy()
+        vec = self._vec
+        if vec.host_mapped and self.num_envs == 1:           # state is host memory: read the words in place
+            first, count = vec._fields()[name]
+            if first < 0:
+                raise AttributeError("state has no %s row in this configuration" % name)
+            w = vec.state.numpy()[:, 0, :].reshape(-1)[first:first + count].astype(np.float64)
+            return w.reshape(3, 3) if name == "rot" else w
+        v = vec.get_field(name).double().cpu().numpy()
         return v[0] if self.num_envs == 1 else v
 
+    def _put(self, name, value):
+        vec = self._vec
+        if vec.host_mapped and self.num_envs == 1:
+            first, count = vec._fields()[name]
+            st = vec.state.numpy()
+            v = np.asarray(value, dtype=np.float64).reshape(-1)
+            for k in range(count):
+                st[(first + k) // 4, 0, (first + k) % 4] = v[k]
+        else:
+            vec.set_field(name, np.asarray(value, dtype=np.float64).reshape(-1, vec._fields()[name][1]))
+
     def _info(self, first, count):
-        v = self._vec.info[:, first:first + count].double().cpu().numpy()
+        if self._vec.host_mapped:
+            v = self._vec.info.numpy()[:, first:first + count].astype(np.float64)
+        else:
+            v = self._vec.info[:, first:first + count].double().cpu().numpy()
         return v[0] if self.num_envs == 1 else v
 
     def _controller_step(self, name, action, dt, goal=None, zero_middle=True):
         """controller mixing + dynamics_steps_num x step1 (what every reference controller's step() does)."""
         h = self._handle(dt, zero_middle)
         if goal is not None:
-            h.set_field("goals", np.asarray(goal, dtype=np.float64).reshape(-1, 3))
+            self._put("goals", goal)
         a = None if action is None else np.asarray(action, dtype=np.float64).reshape(self.num_envs, -1)
         h.dynamics_step(a, controller=name, n_substeps=self.dynamics_steps_num)
         self._fresh = False
@@ -156,21 +178,21 @@ class QuadrotorDynamics(object):
             for v in (position, velocity, omega):
                 assert v.shape == (3,)
             assert rotation.shape == (3, 3)
-        self._vec.set_field("pos", position.reshape(-1, 3))
-        self._vec.set_field("vel", velocity.reshape(-1, 3))
-        self._vec.set_field("rot", rotation.reshape(-1, 9))
-        self._vec.set_field("omega", omega.astype(np.float32).astype(np.float64).reshape(-1, 3))     # :223
+        self._put("pos", position)
+        self._put("vel", velocity)
+        self._put("rot", rotation)
+        self._put("omega", omega.astype(np.float32).astype(np.float64))                            # :223
         self.thrusts = copy.deepcopy(thrusts)
         self._fresh = True
 
     def reset(self):
-        self._vec.set_field("thrust_cmds_damp", [0., 0., 0., 0.])
-        self._vec.set_field("thrust_rot_damp", [0., 0., 0., 0.])
+        self._put("thrust_cmds_damp", np.zeros(4 * self.num_envs))
+        self._put("thrust_rot_damp", np.zeros(4 * self.num_envs))
 
-    pos = property(lambda self: self._get("pos"), lambda self, v: self._vec.set_field("pos", np.reshape(v, (-1, 3))))
-    vel = property(lambda self: self._get("vel"), lambda self, v: self._vec.set_field("vel", np.reshape(v, (-1, 3))))
-    omega = property(lambda self: self._get("omega"), lambda self, v: self._vec.set_field("omega", np.reshape(v, (-1, 3))))
-    rot = property(lambda self: self._get("rot"), lambda self, v: self._vec.set_field("rot", np.reshape(v, (-1, 9))))
+    pos = property(lambda self: self._get("pos"), lambda self, v: self._put("pos", v))
+    vel = property(lambda self: self._get("vel"), lambda self, v: self._put("vel", v))
+    omega = property(lambda self: self._get("omega"), lambda self, v: self._put("omega", v))
+    rot = property(lambda self: self._get("rot"), lambda self, v: self._put("rot", v))
     thrust_cmds_damp = property(lambda self: self._get("thrust_cmds_damp"))
     thrust_rot_damp = property(lambda self: self._get("thrust_rot_damp"))
 
@@ -387,7 +409,7 @@ class QuadrotorEnv(object):
                   init_random_state=self.init_random_state, rew_coeff=self._rew_coeff_arg, sense_noise=self._sense_noise_arg,
                   gravity=self.gravity, device=self._device, dtype=self._dtype, seed=self._philox_seed,
                   noise_mode=self._noise_mode, auto_reset=False, info=True, multi_reward=self._multi_reward,
-                  goals=np.asarray(self.goal, dtype=np.float64).reshape(1, 3), box=self.box)
+                  goals=np.asarray(self.goal, dtype=np.float64).reshape(1, 3), box=self.box, host_mapped=True)
         vec = QuadVecEnv(1, **kw)
         if old_state is not None:
             if old_state.shape == vec.state.shape:      # OU state, gyro bias and the SVD timer survive a model change
@@ -435,7 +457,7 @@ class QuadrotorEnv(object):
 
     # ---- the env API ---------------------------------------------------------------------------------------
     def _np(self, t):
-        return t.double().cpu().numpy()
+        return t.numpy().astype(np.float64) if t.device.type == "cpu" else t.double().cpu().numpy()
 
     def state_vector(self, env=None):
         """Observation of the current state (get_state.state_<obs_repr>): the last vector the device produced."""
@@ -448,14 +470,10 @@ class QuadrotorEnv(object):
         if self.excite and self.tick % 5 == 0:                                                # :957-962
             self.goal = np.concatenate([np.random.uniform(low=-0.5, high=0.5, size=(2,)),
                                         np.random.uniform(low=1.5, high=2.5, size=(1,))])
-            self._vec.set_field("goals", self.goal.reshape(1, 3))
-        obs, rew, done = self._vec.step(action.reshape(1, -1))
-        try:
-            self._vec.check_finite()
-        except _lib.QuadsimError as e:                                                        # :633-636
-            if e.code == _lib.QS_ENONFINITE:
-                raise ValueError('QuadEnv: reward is Nan')
-            raise
+            self.dynamics._put("goals", self.goal)
+        obs, rew, done = self._vec.step(action.reshape(1, -1))         # host-mapped: results are host memory, already synced
+        if not np.isfinite(float(rew[0])):                                                    # :633-636
+            raise ValueError('QuadEnv: reward is Nan')
         self.dynamics._fresh = False
         info_row = self._np(self._vec.info)[0]
         self.crashed = bool(info_row[_lib.QS_INFO_CRASHED])
@@ -490,7 +508,7 @@ class QuadrotorEnv(object):
             self.goal = np.array([0., 0., np.random.uniform(0.5, 2.0)])
         else:
             self.goal = np.array([0., 0., 2.])
-        self._vec.set_field("goals", self.goal.reshape(1, 3))
+        self.dynamics._put("goals", self.goal)
         obs = self._vec.reset()
         self.dynamics._fresh = True
         self.crashed, self.tick = False, 0

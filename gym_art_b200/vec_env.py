@@ -151,7 +151,8 @@ class QuadVecEnv(object):
                  sense_noise=None, gravity=GRAV, device="cuda:0", dtype="float32", seed=0, noise_mode="philox",
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
-                 max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None):
+                 max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None,
+                 host_mapped=False):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -186,19 +187,27 @@ class QuadVecEnv(object):
         self.obs_repr = obs_repr
         self.goal = np.array([self.cfg.goal[0], self.cfg.goal[1], self.cfg.goal[2]])
         N = self.num_envs
+        # host_mapped: every buffer is PINNED HOST memory that the kernels read and write across PCIe (the device
+        # address of a pinned allocation equals its host address under unified addressing).  For a handful of envs -
+        # the single-env facades - this removes every copy: one launch + one stream sync per call, results and state
+        # are plain host memory.  Not for throughput work.
+        self.host_mapped = bool(host_mapped)
+        self.mem = torch.device("cpu") if self.host_mapped else self.device
+        self._stage = {}
         with torch.cuda.device(self.device):
             if state is None:
-                self.state = torch.zeros((self.layout.rows, N, 4), dtype=self.tdtype, device=self.device)
+                self.state = self._alloc((self.layout.rows, N, 4), self.tdtype)
             else:       # a second handle over the same drones (e.g. another controller or dt): same layout required
                 assert tuple(state.shape) == (self.layout.rows, N, 4) and state.dtype == self.tdtype and state.is_contiguous()
+                assert state.device.type == self.mem.type
                 self.state = state
-            self.obs = torch.zeros((N, self.obs_dim), dtype=self.tdtype, device=self.device)
-            self.rew = torch.zeros((N,), dtype=self.tdtype, device=self.device)
-            self._done_u8 = torch.zeros((N,), dtype=torch.uint8, device=self.device)
+            self.obs = self._alloc((N, self.obs_dim), self.tdtype)
+            self.rew = self._alloc((N,), self.tdtype)
+            self._done_u8 = self._alloc((N,), torch.uint8)
             self.done = self._done_u8.view(torch.bool)      # zero-copy: the kernel writes 0 / 1
-            self.info = torch.zeros((N, _lib.QS_INFO_DIM), dtype=self.tdtype, device=self.device) if info else None
+            self.info = self._alloc((N, _lib.QS_INFO_DIM), self.tdtype) if info else None
         if state is None:
-            self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.device).reshape(1, 9))
+            self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.mem).reshape(1, 9))
         if goals is not None and state is None:
             self.set_field("goals", np.asarray(goals, dtype=np.float64).reshape(N, 3))
         self._h = C.c_void_p()
@@ -252,6 +261,31 @@ class QuadVecEnv(object):
         except Exception:
             pass
 
+    def _alloc(self, shape, dtype):
+        if self.host_mapped:
+            return self.torch.zeros(shape, dtype=dtype, pin_memory=True)
+        return self.torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def _in(self, name, x, dtype, shape):
+        """A kernel input as a contiguous tensor the device can address: a device tensor, or (host_mapped) a persistent
+        pinned staging buffer the value is copied into."""
+        t = self.torch
+        v = t.as_tensor(x, dtype=dtype, device=self.mem) if not isinstance(x, np.ndarray) else t.as_tensor(np.ascontiguousarray(x)).to(dtype=dtype, device=self.mem)
+        if tuple(v.shape) != tuple(shape):
+            v = v.reshape(shape)
+        if not self.host_mapped:
+            return v.contiguous()
+        buf = self._stage.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = self._stage[name] = t.empty(shape, dtype=dtype, pin_memory=True)
+        buf.copy_(v)
+        return buf
+
+    def _done_call(self):
+        """host_mapped: results live in host memory, valid once the stream has drained."""
+        if self.host_mapped:
+            self.torch.cuda.current_stream(self.device).synchronize()
+
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
@@ -270,7 +304,7 @@ class QuadVecEnv(object):
         first, count = self._fields()[name]
         if first < 0:
             raise AttributeError("state has no %s row in this configuration" % name)
-        idx = self.torch.arange(first, first + count, device=self.device)
+        idx = self.torch.arange(first, first + count, device=self.mem)
         v = self.state[idx // 4, :, idx % 4].transpose(0, 1).contiguous()
         if name == "rot":
             return v.reshape(self.num_envs, 3, 3)
@@ -297,20 +331,20 @@ class QuadVecEnv(object):
         first, count = self._fields()[name]
         if first < 0:
             raise AttributeError("state has no %s row in this configuration" % name)
-        v = t.as_tensor(value, dtype=self.tdtype, device=self.device).reshape(-1, count).expand(self.num_envs, count)
-        idx = t.arange(first, first + count, device=self.device)
+        v = t.as_tensor(value, dtype=self.tdtype, device=self.mem).reshape(-1, count).expand(self.num_envs, count)
+        idx = t.arange(first, first + count, device=self.mem)
         if mask is not None:
-            m = t.as_tensor(mask, device=self.device).bool()
+            m = t.as_tensor(mask, device=self.mem).bool()
             v = t.where(m[:, None], v, self.state[idx // 4, :, idx % 4].transpose(0, 1))
         self.state[idx // 4, :, idx % 4] = v.transpose(0, 1)
 
     def set_state(self, pos, vel, rot, omega, mask=None):
         """QuadrotorDynamics.set_state + reset() (quadrotor.py:213-224, :438-440) for all (or masked) envs."""
         t = self.torch
-        om = t.as_tensor(omega, dtype=self.tdtype, device=self.device).float().to(self.tdtype)   # float32 cast, :223
+        om = t.as_tensor(omega, dtype=self.tdtype, device=self.mem).float().to(self.tdtype)      # float32 cast, :223
         self.set_field("pos", pos, mask)
         self.set_field("vel", vel, mask)
-        self.set_field("rot", t.as_tensor(rot, dtype=self.tdtype, device=self.device).reshape(-1, 9), mask)
+        self.set_field("rot", t.as_tensor(rot, dtype=self.tdtype, device=self.mem).reshape(-1, 9), mask)
         self.set_field("omega", om, mask)
         self.set_field("thrust_rot_damp", [0., 0., 0., 0.], mask)
         self.set_field("thrust_cmds_damp", [0., 0., 0., 0.], mask)
@@ -329,9 +363,9 @@ class QuadVecEnv(object):
         K = len(consts)
         if index is None:
             index = np.arange(self.num_envs) % K
-        idx = t.as_tensor(np.asarray(index), device=self.device, dtype=t.long)
-        tab = t.as_tensor(table, dtype=self.tdtype, device=self.device)
-        self.models = tab[:, idx, :].contiguous()
+        idx = t.as_tensor(np.asarray(index), device=self.mem, dtype=t.long)
+        tab = t.as_tensor(table, dtype=self.tdtype, device=self.mem)
+        self.models = self._in("models", tab[:, idx, :], self.tdtype, (table.shape[0], self.num_envs, 4))
         self.model_params, self.model_consts, self.model_index = list(params_list), consts, idx
         _lib.check(self.lib.qs_bind_models(self._h, self.models.data_ptr()), self._h)
 
@@ -360,14 +394,14 @@ class QuadVecEnv(object):
         """QS_NOISE_INJECTED: unit draws for the next reset()/step() calls; shapes [N,sim_steps,4], [N,30], [N,48]."""
         t = self.torch
 
-        def dev(x, shape):
+        def dev(name, x, shape):
             if x is None:
                 return None
-            v = t.as_tensor(np.asarray(x), dtype=self.tdtype, device=self.device).reshape(shape).contiguous()
-            return v
+            return self._in(name, np.asarray(x), self.tdtype, shape)
 
         N = self.num_envs
-        refs = (dev(ou_z, (N, self.sim_steps, 4)), dev(obs_z, (N, _lib.QS_OBS_Z)), dev(reset_z, (N, _lib.QS_RESET_Z)))
+        refs = (dev("ou_z", ou_z, (N, self.sim_steps, 4)), dev("obs_z", obs_z, (N, _lib.QS_OBS_Z)),
+                dev("reset_z", reset_z, (N, _lib.QS_RESET_Z)))
         self._noise_refs = refs      # keep the device buffers alive until replaced
         ptr = lambda v: None if v is None else v.data_ptr()
         _lib.check(self.lib.qs_set_noise_injection(self._h, ptr(refs[0]), ptr(refs[1]), ptr(refs[2])), self._h)
@@ -376,24 +410,23 @@ class QuadVecEnv(object):
     def reset(self, mask=None):
         m = None
         if mask is not None:
-            m = self.torch.as_tensor(mask, device=self.device).to(self.torch.uint8).contiguous()
+            m = self._in("mask", self.torch.as_tensor(mask).to(self.torch.uint8), self.torch.uint8, (self.num_envs,))
         _lib.check(self.lib.qs_reset(self._h, None if m is None else m.data_ptr(), self.obs.data_ptr(), self._stream()),
                    self._h)
+        self._done_call()
         return self.obs
 
     def _actions(self, actions, k=None):
         if actions is None:
             return None
-        a = self.torch.as_tensor(actions, dtype=self.tdtype, device=self.device)
         want = (self.num_envs, self.act_dim) if k is None else (k, self.num_envs, self.act_dim)
-        if tuple(a.shape) != want:
-            a = a.reshape(want)
-        return a.contiguous()
+        return self._in("actions", actions, self.tdtype, want)
 
     def step(self, actions=None):
         a = self._actions(actions)
         _lib.check(self.lib.qs_step(self._h, None if a is None else a.data_ptr(), self.obs.data_ptr(), self.rew.data_ptr(),
                                     self._done_u8.data_ptr(), self._stream()), self._h)
+        self._done_call()
         return self.obs, self.rew, self.done
 
     def capture_steps(self, n_steps, actions=None):
@@ -420,6 +453,7 @@ class QuadVecEnv(object):
         a = self._actions(actions, k)
         _lib.check(self.lib.qs_step_k(self._h, int(k), None if a is None else a.data_ptr(), self.obs.data_ptr(),
                                       self.rew.data_ptr(), self._done_u8.data_ptr(), self._stream()), self._h)
+        self._done_call()
         return self.obs, self.rew, self.done
 
     def step_host(self, actions_host, obs_host, rew_host, done_host):
@@ -441,9 +475,10 @@ class QuadVecEnv(object):
         adim = 4 if cid < 0 else [4, 1, 2, 4, 4, 4, 4][cid]
         a = None
         if actions is not None:
-            a = self.torch.as_tensor(actions, dtype=self.tdtype, device=self.device).reshape(self.num_envs, adim).contiguous()
+            a = self._in("dyn_actions", actions, self.tdtype, (self.num_envs, adim))
         n = self.sim_steps if n_substeps is None else int(n_substeps)
         _lib.check(self.lib.qs_dynamics_step(self._h, cid, None if a is None else a.data_ptr(), n, self._stream()), self._h)
+        self._done_call()
 
     # ---- bookkeeping -----------------------------------------------------------------------------------
     def stats(self, clear=False):
