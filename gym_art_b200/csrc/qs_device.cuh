@@ -68,6 +68,7 @@ struct Params {
   int init_random, auto_reset, sense_on, ou_on, gyro_bias_mode;
   int dyn_controller, dyn_substeps;   // qs_dynamics_step
   int inject, need_rare;              // variant selection (host)
+  int tma_generic;                    // fp32 generic configuration through the TMA harness (A/B knob QUADSIM_TMA_GENERIC)
   int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
   long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
   int pdl;                            // step kernel launched with programmatic dependent launch (see env_step_tma_kernel)
@@ -1353,6 +1354,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 constexpr int TMA_MIN_CTAS = 4;   // resident CTAs per SM the fast kernel is tuned for (registers <= 128)
+constexpr int TMA_MIN_CTAS_RARE = 3;   // the run-time-parameterised generic configuration needs ~160 registers
 constexpr int WARPS = BLOCK / 32;
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -1388,7 +1390,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // own instantiation with the ring, the mbarriers and every CTA barrier compiled out: direct vector loads, per-warp
 // observation flush.  (tests/test_gpu_fullsize.py holds both instantiations to bit-identical results.)
 template <class T, bool ONEWAVE>
-__global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const __grid_constant__ Params<float> p) {
+__global__ void __launch_bounds__(BLOCK, T::RARE ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS)
+env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   typedef float R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
@@ -1396,7 +1399,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
-  const bool has_act = p.actions != nullptr;
+  const bool has_act = p.actions != nullptr && p.act_dim == 4;          // (1- and 2-wide actions are read by run_steps itself)
   const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
   const int obs_dim = T::PLAIN ? 18 : p.obs_dim;
   const int obs_tile_floats = BLOCK * obs_dim;                           // per stage
@@ -1493,6 +1496,10 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
       if (ou_row) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
       if (act_row) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
       if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
+      if (T::RARE) {
+        if (p.row_gyro >= 0) { float4 q = buf[p.row_gyro * BLOCK]; s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; }
+        if (p.row_goal >= 0) { float4 q = buf[p.row_goal * BLOCK]; s.gx = q.x; s.gy = q.y; s.gz = q.z; }
+      }
       finish_load(s);
 
       __syncwarp();
@@ -1509,7 +1516,7 @@ __global__ void __launch_bounds__(BLOCK, TMA_MIN_CTAS) env_step_tma_kernel(const
 
     R o[26];
     StepOut<R> out;
-    run_steps<R, T>(s, p, i, active, a0, svd_t0, step0, o, out, &pre);
+    run_steps<R, T>(s, p, i, active, has_act ? a0 : nullptr, svd_t0, step0, o, out, &pre);
     svd_end = out.svd_t;
 
     if (active) {
@@ -1672,6 +1679,8 @@ QS_DECL_FAST(launch_fast_shifted_philox);
 QS_DECL_FAST(launch_fast_shifted_inject);
 QS_DECL_FAST(launch_fast_velyaw_philox);
 QS_DECL_FAST(launch_fast_velyaw_inject);
+QS_DECL_FAST(launch_tma_generic_philox);     // every other fp32 configuration (qs_tma_generic.inl)
+QS_DECL_FAST(launch_tma_generic_inject);
 #undef QS_DECL_FAST
 
 }  // namespace qs

@@ -31,6 +31,10 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
     return p.inject ? launch_fast_mellinger_inject(p, st, name) : launch_fast_mellinger_philox(p, st, name);
   }
 #endif
+#ifdef QS_FAST_VARIANTS
+  // fp32: everything outside the specialised subset still runs through the persistent TMA harness
+  if (p.tma_generic) return p.inject ? launch_tma_generic_inject(p, st, name) : launch_tma_generic_philox(p, st, name);
+#endif
   if (p.models != nullptr) {
     if (p.inject) { if (name) *name = "generic-permodel-injected"; return launch_step_t<R, TGenInjectPEM>(p, st); }
     if (name) *name = "generic-permodel-philox";

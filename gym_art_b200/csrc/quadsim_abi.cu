@@ -44,6 +44,7 @@ struct QsHandle {
   cudaEvent_t hev[kHostStreams];
   bool host_ready;
   int host_zero_copy;        // A/B knob QUADSIM_HOST_ZEROCOPY (default 1)
+  int tma_generic;           // A/B knob QUADSIM_TMA_GENERIC (default 1)
   cudaStream_t zc_stream;
   const char* last_host_path;
   void *h_act, *h_obs, *h_rew;
@@ -174,6 +175,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.dyn_controller = -1; p.dyn_substeps = c.sim_steps;
   p.inject = (c.noise_mode == QS_NOISE_INJECTED) ? 1 : 0;
   p.need_rare = need_rare(h) ? 1 : 0;
+  p.tma_generic = h->tma_generic;
   p.tma_rows = h->lay.rows;
   p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
   p.pdl = h->pdl;
@@ -291,6 +293,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->last_variant = "";
   h->host_ready = false;
   { const char* e = getenv("QUADSIM_HOST_ZEROCOPY"); h->host_zero_copy = e ? atoi(e) : 1; }
+  { const char* e = getenv("QUADSIM_TMA_GENERIC"); h->tma_generic = e ? atoi(e) : 1; }
   h->zc_stream = nullptr;
   h->last_host_path = "";
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;

@@ -165,7 +165,7 @@ def test_fp32_per_step_1e5_relative(name):
             assert rel_err(ob, g.reset_obs[i], 1.0) < 1e-5
     print(name, "fp32 per-step worst rel err", worst)
     # the throughput kernels themselves (injected-noise twins) are what this test holds to the bar
-    assert env.kernel_variant == EXPECTED_VARIANT.get(name, "generic-injected"), (name, env.kernel_variant)
+    assert env.kernel_variant == EXPECTED_VARIANT.get(name, "tma-generic-injected"), (name, env.kernel_variant)
 
 
 @pytest.mark.parametrize("name,bound", [("hb_mellinger_nonoise", 2e-5), ("hb_mellinger_noise_act", 2e-5),
