@@ -6,22 +6,27 @@
 namespace qs {
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
   }
-  return n;
+  return cached[dev];
 }
 
 template <class T, bool ONEWAVE>
 static cudaError_t launch_tma_w(const Params<float>& p, cudaStream_t st, unsigned grid, size_t smem) {
-  static bool attr_set = false;   // one flag per instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // per instantiation and per device (function attributes are per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(env_step_tma_kernel<T, ONEWAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
