@@ -238,6 +238,9 @@ def run_ours(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     if multi:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     hbm_peak, peak_src = load_peaks()
     K, W = args.steps, max(args.warmup, 3)
