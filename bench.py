@@ -226,6 +226,28 @@ def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, per_chunk_ho
 RING_PERIOD = [1]
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's threads (and so its first-touch pinned host buffers) to the NUMA node its GPU hangs off: with
+    8 ranks writing 40 GB/s each into host memory, remote-socket traffic is what limits the end-to-end path."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -237,6 +259,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    numa = bind_to_gpu_numa_node(torch, local) if multi else None
     if multi:
         # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -382,7 +405,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N_BATCH * 16,
                     "d2h_bytes_per_step": N_BATCH * (72 + 4 + 1), "steps": KE,
                     "api": "qs_step_host on pinned host tensors: the step kernel reads the actions and writes obs/reward/done "
-                           "across PCIe itself (%s)" % e0.host_path},
+                           "across PCIe itself (%s)" % e0.host_path, "numa_node_rank0": numa},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": NCU_TRAFFIC[N_BATCH], "traffic_source": "profiles/r1_ncu_cfg2_65536.txt (ncu replays a "
