@@ -405,3 +405,25 @@ def test_capture_steps_graph_and_spaces():
     assert e1.clock == e2.clock and e2.clock[1] == 1 + 16
     m = _env(64, controller="omega_thrust", dynamics_params="Crazyflie")
     assert m.action_space.high[0] == pytest.approx(0.9) and m.action_space.low[1] == pytest.approx(-10 * np.pi)
+
+
+def test_mellinger_closed_loop_converges_like_the_reference():
+    """SURVEY.md section 4 pin (ii): after one 5 s episode from a default spawn the Hummingbird under the Mellinger
+    controller sits within ~1 cm of the goal (reference probe: final pos (0.009, 0.005, 1.996)); here for 8,192 envs
+    with Philox thrust noise, in the fp32 throughput kernel."""
+    env = _env(8192, dynamics_params="DefaultQuad", controller="mellinger", ep_time=5, seed=12)
+    env.reset()
+    for _ in range(500):
+        o, r, d = env.step(None)
+    dist = o[:, :3].norm(dim=1)
+    # the reference's controller fixes the desired heading to world +x (quadrotor_control.py:333), so the ~9 % of envs
+    # that spawn at +x facing the origin (yaw near 180 degrees) sit on its attitude-error singularity and fly off - in
+    # the reference / oracle exactly as here (oracle: 734 of 8,192); everybody else converges
+    assert float(dist.median()) < 0.02 and float(dist.quantile(0.85)) < 0.05
+    lost = float((dist > 0.5).float().mean())
+    assert lost < 0.15, lost
+    R = env.rot
+    assert float(R[:, 2, 2].median()) > 0.999                   # upright
+    assert not bool(d.any()) and bool((env.tick == 500).all())  # the 501st step ends the episode (quadrotor.py:986-987)
+    o, r, d = env.step(None)
+    assert bool(d.all()) and bool((env.tick == 0).all())
