@@ -32,6 +32,9 @@ static cudaError_t launch_fast_c(const Params<float>& p, cudaStream_t st) {
     return launch_fast_cs<C, 2, true, true>(p, st);
   }
   if (plain) return launch_fast_cs<C, 2, true, false>(p, st);
+  // other observation layouts / previous-action row / K-step launches at the default sim_steps still get the unrolled
+  // substeps and hoisted OU draws
+  if (p.sim_steps == 2) return launch_fast_cs<C, 2, false, false>(p, st);
   return launch_fast_cs<C, -1, false, false>(p, st);
 }
 
