@@ -46,6 +46,7 @@ struct Params {
   const R* ou_z;            // injected: [n][sim_steps][4]
   const R* obs_z;           // injected: [n][OBS_Z]
   const R* reset_z;         // injected: [n][RESET_Z]
+  const R* goal_z;          // injected: [n][4] moving-goal draws (excite xyz, resample_goal z)
   double* stats;            // [3]
   int* status;              // sticky non-finite flag
   long long n;              // envs on the handle = row stride of the state buffer
@@ -66,6 +67,7 @@ struct Params {
   int controller, zero_middle, n_agents, dim_mode;
   int obs_rel, obs_h, obs_acc, obs_act;
   int init_random, auto_reset, sense_on, ou_on, gyro_bias_mode;
+  int resample_goal, excite;          // moving goals (quadrotor.py:1078-1081, :957-962); the goal row is then written back
   int dyn_controller, dyn_substeps;   // qs_dynamics_step
   int inject, need_rare;              // variant selection (host)
   int tma_generic;                    // fp32 generic configuration through the TMA harness (A/B knob QUADSIM_TMA_GENERIC)
@@ -274,8 +276,8 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 }
 
 // Philox slot map (8 bits): obs groups 0..9 (step) / 16..25 (reset obs), reset draws 26..38, OU substeps 64+s
-enum Slot { SLOT_OBS = 0, SLOT_RESET_OBS = 16, SLOT_RESET_POS = 26, SLOT_RESET_VEL = 27, SLOT_RESET_OM = 28,
-            SLOT_RESET_UP = 29, SLOT_RESET_FWD = 30, SLOT_OU = 64 };
+enum Slot { SLOT_OBS = 0, SLOT_EXCITE = 12, SLOT_RESET_OBS = 16, SLOT_RESET_POS = 26, SLOT_RESET_VEL = 27, SLOT_RESET_OM = 28,
+            SLOT_RESET_UP = 29, SLOT_RESET_FWD = 30, SLOT_RESET_GOAL = 40, SLOT_OU = 64 };
 
 template <typename R>
 struct Rng {
@@ -499,7 +501,8 @@ __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, 
   if (!T::PLAIN && p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
   if (T::RARE) {
     if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0));
-    // the goal row is read-only for the step path
+    // the goal row is read-only for the step path unless the goal moves
+    if (p.row_goal >= 0 && (p.resample_goal || p.excite)) st4(p.state, p.n, p.row_goal, i, s.gx, s.gy, s.gz, R(0));
   }
 }
 
@@ -845,6 +848,15 @@ struct NoiseSrc {
     }
   }
   __device__ __forceinline__ R reset_at(int k) const { return p.reset_z ? p.reset_z[i * RESET_Z + k] : R(0); }
+  // moving-goal draws: excite (slots 0..2, one call per step) and resample_goal (slot 3, at reset)
+  __device__ __forceinline__ void goal4(bool at_reset, R* u) const {
+    if (T::INJECT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = p.goal_z ? p.goal_z[i * 4 + k] : R(0);
+    } else {
+      rng.unif4(at_reset ? SLOT_RESET_GOAL : SLOT_EXCITE, u);
+    }
+  }
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1006,6 +1018,16 @@ __device__ __forceinline__ void flush_tile(const Params<R>& p, const R* tile, lo
 template <typename R, class T>
 __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const NoiseSrc<R, T>& ns) {
   const R PI = R(3.14159265358979323846);
+  if (T::RARE) {
+    if (p.resample_goal || p.excite) {                                  // :1078-1081: the goal is re-made at every reset
+      s.gx = p.goal[0]; s.gy = p.goal[1]; s.gz = p.goal[2];
+      if (p.resample_goal) {
+        R g[4];
+        ns.goal4(true, g);
+        s.gx = R(0); s.gy = R(0); s.gz = R(1.25) + R(0.75) * g[3];     // np.random.uniform(0.5, 2.0)
+      }
+    }
+  }
   R u[4];
   if (T::INJECT) { u[0] = ns.reset_at(0); u[1] = ns.reset_at(1); u[2] = ns.reset_at(2); u[3] = ns.reset_at(3); }
   else ns.rng.unif4(SLOT_RESET_POS, u);
@@ -1192,6 +1214,16 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
       }
     }
     R a_prev[4] = {s.pa[0], s.pa[1], s.pa[2], s.pa[3]};                 // actions[1]
+    if (T::RARE) {
+      if (p.excite) {                                                   // :957-962: a new goal every 5th tick
+        const int tk = (int)s.tick;
+        if (tk % 5 == 0) {
+          R g[4];
+          ns.goal4(false, g);
+          s.gx = R(0.5) * g[0]; s.gy = R(0.5) * g[1]; s.gz = R(2) + R(0.5) * g[2];
+        }
+      }
+    }
     // ---- controller + dynamics (:966-970, :261-262) ----
     R cmd[4];
     controller_cmds<R, T>(s, p, m, ctrl, a, cmd);

@@ -31,6 +31,7 @@ struct QsHandle {
   const void* ou_z;
   const void* obs_z;
   const void* reset_z;
+  const void* goal_z;
   double* d_stats;
   int* d_status;
   qs::Clock* d_clock;        // device-resident {svd_timer, step}: steps stay CUDA-graph capturable
@@ -95,6 +96,7 @@ int validate(const QsConfig* c, std::string* why) {
   if (!(c->dt > 0.0)) { *why = "dt must be positive"; return QS_EINVAL; }
   if (c->n_agents < 1 || c->n_agents > 32 || !is_pow2(c->n_agents)) { *why = "n_agents must be 1, 2, 4, 8, 16 or 32"; return QS_EINVAL; }
   if (c->n_envs % c->n_agents != 0) { *why = "n_envs must be a multiple of n_agents"; return QS_EINVAL; }
+  if ((c->resample_goal || c->excite) && !c->per_env_goal) { *why = "resample_goal / excite need per_env_goal (a goal row)"; return QS_EINVAL; }
   if (c->per_env_model && c->n_agents > 1) { *why = "per-env models are not built for swarms"; return QS_EUNSUPPORTED; }
   if (c->use_formation && c->per_env_goal) { *why = "use_formation and per_env_goal are mutually exclusive"; return QS_EINVAL; }
   if (!(c->model.mass > 0.0) || !(c->model.inertia[0] > 0.0) || !(c->model.inertia[1] > 0.0) || !(c->model.inertia[2] > 0.0)) {
@@ -149,6 +151,8 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.ou_z = (const R*)h->ou_z;
   p.obs_z = (const R*)h->obs_z;
   p.reset_z = (const R*)h->reset_z;
+  p.goal_z = (const R*)h->goal_z;
+  p.resample_goal = c.resample_goal ? 1 : 0; p.excite = c.excite ? 1 : 0;
   p.stats = h->d_stats;
   p.status = h->d_status;
   p.n = c.n_envs;
@@ -287,6 +291,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->state = h->info = nullptr;
   h->models = nullptr;
   h->ou_z = h->obs_z = h->reset_z = nullptr;
+  h->goal_z = nullptr;
   h->d_stats = nullptr; h->d_status = nullptr; h->d_clock = nullptr; h->d_ticket = nullptr;
   h->launches = 0;
   { const char* e = getenv("QUADSIM_PDL"); h->pdl = e ? atoi(e) : 1; }   // A/B knob: programmatic dependent launch, default on
@@ -364,6 +369,13 @@ int qs_set_noise_injection(QsHandle* h, const void* ou_z, const void* obs_z, con
   if (!h) return QS_EINVAL;
   if (h->cfg.noise_mode != QS_NOISE_INJECTED) return fail(h, QS_EINVAL, "handle was not created with QS_NOISE_INJECTED");
   h->ou_z = ou_z; h->obs_z = obs_z; h->reset_z = reset_z;
+  return QS_OK;
+}
+
+int qs_set_goal_injection(QsHandle* h, const void* goal_z) {
+  if (!h) return QS_EINVAL;
+  if (h->cfg.noise_mode != QS_NOISE_INJECTED) return fail(h, QS_EINVAL, "handle was not created with QS_NOISE_INJECTED");
+  h->goal_z = goal_z;
   return QS_OK;
 }
 

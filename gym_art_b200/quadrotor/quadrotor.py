@@ -409,7 +409,8 @@ class QuadrotorEnv(object):
                   init_random_state=self.init_random_state, rew_coeff=self._rew_coeff_arg, sense_noise=self._sense_noise_arg,
                   gravity=self.gravity, device=self._device, dtype=self._dtype, seed=self._philox_seed,
                   noise_mode=self._noise_mode, auto_reset=False, info=True, multi_reward=self._multi_reward,
-                  goals=np.asarray(self.goal, dtype=np.float64).reshape(1, 3), box=self.box, host_mapped=True)
+                  goals=np.asarray(self.goal, dtype=np.float64).reshape(1, 3), box=self.box, host_mapped=True,
+                  resample_goal=self.resample_goal, excite=self.excite)
         vec = QuadVecEnv(1, **kw)
         if old_state is not None:
             if old_state.shape == vec.state.shape:      # OU state, gyro bias and the SVD timer survive a model change
@@ -467,14 +468,13 @@ class QuadrotorEnv(object):
         action = np.asarray(action, dtype=np.float64)
         self.actions[1] = copy.deepcopy(self.actions[0])
         self.actions[0] = copy.deepcopy(action)
-        if self.excite and self.tick % 5 == 0:                                                # :957-962
-            self.goal = np.concatenate([np.random.uniform(low=-0.5, high=0.5, size=(2,)),
-                                        np.random.uniform(low=1.5, high=2.5, size=(1,))])
-            self.dynamics._put("goals", self.goal)
+        # (excite, :957-962: the kernel draws the new goal every 5th tick itself)
         obs, rew, done = self._vec.step(action.reshape(1, -1))         # host-mapped: results are host memory, already synced
         if not np.isfinite(float(rew[0])):                                                    # :633-636
             raise ValueError('QuadEnv: reward is Nan')
         self.dynamics._fresh = False
+        if self.excite:
+            self.goal = self.dynamics._get("goals")
         info_row = self._np(self._vec.info)[0]
         self.crashed = bool(info_row[_lib.QS_INFO_CRASHED])
         self.controller.action = info_row[_lib.QS_INFO_CMDS:_lib.QS_INFO_CMDS + 4].copy()
@@ -504,12 +504,12 @@ class QuadrotorEnv(object):
     def _reset(self):                                                                         # :1059-1144
         if self.dynamics_randomize_every is not None and (self.traj_count + 1) % self.dynamics_randomize_every == 0:
             self.resample_dynamics()
-        if self.resample_goal:                                                                # :1078-1081
-            self.goal = np.array([0., 0., np.random.uniform(0.5, 2.0)])
-        else:
+        if not (self.resample_goal or self.excite):                                           # :1078-1081
             self.goal = np.array([0., 0., 2.])
-        self.dynamics._put("goals", self.goal)
-        obs = self._vec.reset()
+            self.dynamics._put("goals", self.goal)
+        obs = self._vec.reset()                      # resample_goal / excite: the reset kernel re-makes the goal itself
+        if self.resample_goal or self.excite:
+            self.goal = self.dynamics._get("goals")
         self.dynamics._fresh = True
         self.crashed, self.tick = False, 0
         self.actions = [np.zeros(4), np.zeros(4)]

@@ -67,7 +67,7 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
                 rew_coeff=None, sense_noise=None, device_index=0, dtype="float32", seed=0, noise_mode="philox",
                 auto_reset=True, n_agents=1, per_env_goal=False, env_id_offset=0, multi_reward=False, collision_k=1.0,
                 goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi, formation=None,
-                per_env_model=False):
+                per_env_model=False, resample_goal=False, excite=False):
     """Pure host function (no GPU): ctor arguments -> QsConfig.  Raises the reference's ValueErrors."""
     cfg = _lib.QsConfig()
     cfg.abi_version = _lib.QS_ABI_VERSION
@@ -94,7 +94,8 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
     cfg.sim_steps = int(sim_steps)
     dt = 1.0 / sim_freq                                                               # quadrotor.py:790
     cfg.ep_len = int(ep_time / (dt * sim_steps))                                      # quadrotor.py:792
-    cfg.per_env_goal = int(bool(per_env_goal))
+    cfg.per_env_goal = int(bool(per_env_goal) or bool(resample_goal) or bool(excite))
+    cfg.resample_goal, cfg.excite = int(bool(resample_goal)), int(bool(excite))         # quadrotor.py:1078-1081, :957-962
     cfg.dt = dt
     cfg.svd_period = 0.5                                                              # quadrotor.py:105
     for k in range(3):
@@ -152,7 +153,7 @@ class QuadVecEnv(object):
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
                  max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None,
-                 host_mapped=False):
+                 host_mapped=False, resample_goal=False, excite=False):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -178,7 +179,8 @@ class QuadVecEnv(object):
             device_index=dev_index, dtype=dtype, seed=seed, noise_mode=noise_mode, auto_reset=auto_reset,
             n_agents=n_agents, per_env_goal=goals is not None, env_id_offset=env_id_offset, multi_reward=multi_reward,
             collision_k=collision_k, goal=goal, box=box, spawn_z_min=spawn_z_min, max_init_vel=max_init_vel,
-            max_init_omega=max_init_omega, formation=formation, per_env_model=per_env_dynamics is not None)
+            max_init_omega=max_init_omega, formation=formation, per_env_model=per_env_dynamics is not None,
+            resample_goal=resample_goal, excite=excite)
         self.layout = _lib.state_layout(self.cfg)
         self.num_envs = int(num_envs)
         self.n_agents = int(n_agents)
@@ -208,6 +210,8 @@ class QuadVecEnv(object):
             self.info = self._alloc((N, _lib.QS_INFO_DIM), self.tdtype) if info else None
         if state is None:
             self.set_field("rot", torch.eye(3, dtype=self.tdtype, device=self.mem).reshape(1, 9))
+        if goals is None and (resample_goal or excite) and state is None:
+            self.set_field("goals", np.asarray(goal, dtype=np.float64).reshape(1, 3))
         if goals is not None and state is None:
             self.set_field("goals", np.asarray(goals, dtype=np.float64).reshape(N, 3))
         self._h = C.c_void_p()
@@ -390,8 +394,9 @@ class QuadVecEnv(object):
         return out
 
     # ---- noise injection (test mode) -----------------------------------------------------------------
-    def set_noise(self, ou_z=None, obs_z=None, reset_z=None):
-        """QS_NOISE_INJECTED: unit draws for the next reset()/step() calls; shapes [N,sim_steps,4], [N,30], [N,48]."""
+    def set_noise(self, ou_z=None, obs_z=None, reset_z=None, goal_z=None):
+        """QS_NOISE_INJECTED: unit draws for the next reset()/step() calls; shapes [N,sim_steps,4], [N,30], [N,48]
+        (+ goal_z [N,4] for the excite / resample_goal options)."""
         t = self.torch
 
         def dev(name, x, shape):
@@ -405,6 +410,10 @@ class QuadVecEnv(object):
         self._noise_refs = refs      # keep the device buffers alive until replaced
         ptr = lambda v: None if v is None else v.data_ptr()
         _lib.check(self.lib.qs_set_noise_injection(self._h, ptr(refs[0]), ptr(refs[1]), ptr(refs[2])), self._h)
+        if self.cfg.resample_goal or self.cfg.excite:
+            gz = dev("goal_z", goal_z, (N, _lib.QS_GOAL_Z))
+            self._noise_refs = refs + (gz,)
+            _lib.check(self.lib.qs_set_goal_injection(self._h, ptr(gz)), self._h)
 
     # ---- the env API -----------------------------------------------------------------------------------
     def reset(self, mask=None):

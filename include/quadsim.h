@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 5
+#define QS_ABI_VERSION 6
 
 typedef struct QsHandle QsHandle;
 typedef void* qs_stream_t; /* cudaStream_t */
@@ -99,6 +99,9 @@ typedef enum QsNoiseMode {
 #define QS_RZ_NFWD 15   /*                    accepted "fwd" Gaussian   (quad_utils.py:50-52) */
 #define QS_RZ_OBS 18    /* obs_z of the observation returned by the reset (:1143) */
 /* ou_z   [n_envs][sim_steps][4] : OUNoise.noise() normals, one per substep (quad_utils.py:197-201) */
+/* goal_z [n_envs][QS_GOAL_Z] (qs_set_goal_injection): unit uniforms of the moving-goal options -
+ *   [0..2] excite goal x, y, z (quadrotor.py:959-961), [3] resample_goal height (quadrotor.py:1079) */
+#define QS_GOAL_Z 4
 
 /* Optional per-env diagnostics, info [n_envs][QS_INFO_DIM] (reference: info['obs_comp'], quadrotor.py:994-1006) */
 #define QS_INFO_DIM 48
@@ -182,6 +185,8 @@ typedef struct QsConfig {
   int32_t sim_steps;
   int32_t ep_len;
   int32_t per_env_goal; /* goals live in the state buffer (row given by QsStateLayout.row_goal) */
+  int32_t resample_goal; /* goal = (0, 0, U(0.5, 2)) at every reset (quadrotor.py:1078-1079); needs per_env_goal */
+  int32_t excite;      /* goal = (U(-.5,.5), U(-.5,.5), U(1.5,2.5)) every 5th tick (quadrotor.py:957-962); needs per_env_goal */
   int32_t _pad;
   double dt;           /* 1 / sim_freq */
   double svd_period;   /* since_last_svd_limit = 0.5 s (quadrotor.py:105) */
@@ -231,6 +236,9 @@ int qs_bind_models(QsHandle* h, const void* models);
 int qs_bind_info(QsHandle* h, void* info);
 /* QS_NOISE_INJECTED: device buffers of unit draws consumed by the next reset/step calls (any may be NULL = zeros) */
 int qs_set_noise_injection(QsHandle* h, const void* ou_z, const void* obs_z, const void* reset_z);
+
+/* QS_NOISE_INJECTED + excite / resample_goal: device buffer real[n_envs][QS_GOAL_Z] (NULL = zeros) */
+int qs_set_goal_injection(QsHandle* h, const void* goal_z);
 
 /* replaces QuadrotorEnv.reset() (quadrotor.py:1059-1144) for the envs whose mask byte is non-zero
  * (mask NULL = all).  obs: real[n_envs][obs_dim], rows of unmasked envs are left untouched. */

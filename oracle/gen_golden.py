@@ -84,6 +84,11 @@ CASES = {
     "cf_relative_omegathrust": (qo.CTRL_OMEGA_THRUST, "omega_thrust", _act_omega_thrust, 300, 18, False,
                                 dict(dynamics_params="Crazyflie", ep_time=1,
                                      dyn_sampler_1={"class": "RelativeSampler", "noise_ratio": 0.2, "sampler": "normal"})),
+    # moving goals: excite (a new random goal every 5 ticks, quadrotor.py:957-962) and resample_goal (:1078-1079)
+    "hb_mellinger_excite": (qo.CTRL_MELLINGER, None, _uni(0, 0, 4), 450, 19, False,
+                            dict(dynamics_params="DefaultQuad", raw_control=False, ep_time=2, excite=True, sense_noise="default")),
+    "cf_raw_resample_goal": (qo.CTRL_RAW, None, _uni(-0.2, 0.6, 4), 300, 20, False,
+                             dict(dynamics_params="Crazyflie", ep_time=0.5, resample_goal=True)),
     "mq_raw_simsteps4": (qo.CTRL_RAW, None, _uni(-0.5, 0.8, 4), 300, 15, False,
                          dict(dynamics_params="MediumQuad", ep_time=2, sim_steps=4, sim_freq=100.0)),
 }
@@ -110,8 +115,10 @@ def rollout(name):
     init = dict(ou0=env.dynamics.thrust_noise.state.copy(), svd_timer0=float(env.dynamics.since_last_svd),
                 gyro_bias0=env.sense_noise.gyro_bias.copy())
     rec = {k: [] for k in ("actions", "ou_z", "obs_z", "obs", "rew", "done", "pos", "vel", "rot", "omega", "rot_damp",
-                           "cmds_damp", "ou", "accelerometer", "reset_z", "reset_obs", "reset_step")}
+                           "cmds_damp", "ou", "accelerometer", "reset_z", "reset_obs", "reset_step", "goal_z", "reset_goal_z",
+                           "goal")}
     obs, rz = rr.reset()
+    rec["reset_goal_z"].append(rr.last_goal_z.copy())
     rec["reset_z"].append(rz)
     rec["reset_obs"].append(obs)
     rec["reset_step"].append(0)
@@ -121,12 +128,14 @@ def rollout(name):
         a4[:A] = a
         o, r, d, info, ou_z, obs_z = rr.step(a4)
         st = rr.state()
-        for k, v in (("actions", a), ("ou_z", ou_z), ("obs_z", obs_z), ("obs", o), ("rew", r), ("done", d)):
+        for k, v in (("actions", a), ("ou_z", ou_z), ("obs_z", obs_z), ("obs", o), ("rew", r), ("done", d),
+                     ("goal_z", rr.last_goal_z.copy()), ("goal", np.array(env.goal, dtype=np.float64))):
             rec[k].append(v)
         for k in ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou", "accelerometer"):
             rec[k].append(st[k])
         if d:
             obs, rz = rr.reset()
+            rec["reset_goal_z"].append(rr.last_goal_z.copy())
             rec["reset_z"].append(rz)
             rec["reset_obs"].append(obs)
             rec["reset_step"].append(t + 1)

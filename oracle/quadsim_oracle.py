@@ -22,6 +22,7 @@ EPS = 1e-6    # quadrotor.py:54
 # injected-noise slot layout, mirrored by include/quadsim.h ----------------------------------------
 OBS_Z = 30            # n_pos3 u_pos3 n_vel3 u_vel3 n_gyro3 n_gyro_rw3 n_theta3 u_theta3 n_accS3 n_accD3
 RESET_Z = 18 + OBS_Z  # u_pos3 yaw1 u_vel3 u_velmag1 u_om3 u_ommag1 n_up3 n_fwd3 | obs_z for the post-reset obs
+GOAL_Z = 4            # excite goal u_xy2 u_z1 (quadrotor.py:957-962) | resample_goal u_z1 (:1078-1079)
 (Z_NPOS, Z_UPOS, Z_NVEL, Z_UVEL, Z_NGYRO, Z_NGYRO_RW, Z_NTHETA, Z_UTHETA, Z_NACC_S, Z_NACC_D) = range(0, 30, 3)
 (RZ_UPOS, RZ_YAW, RZ_UVEL, RZ_UVELMAG, RZ_UOM, RZ_UOMMAG, RZ_NUP, RZ_NFWD, RZ_OBS) = (0, 3, 4, 7, 8, 11, 12, 15, 18)
 
@@ -356,7 +357,8 @@ class OracleVecEnv(object):
     def __init__(self, params, n_envs, controller=CTRL_RAW, zero_middle=True, sim_freq=200.0, sim_steps=2,
                  obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10.0, init_random_state=False, rew_coeff=None,
                  sense_noise=None, gravity=GRAV, auto_reset=True, goal=(0.0, 0.0, 2.0), box=2.0,
-                 multi_reward=False, n_agents=1, collision_k=1.0, collision_coeff=0.0, goals=None, dim_mode="3D"):
+                 multi_reward=False, n_agents=1, collision_k=1.0, collision_coeff=0.0, goals=None, dim_mode="3D",
+                 resample_goal=False, excite=False):
         self.m = model_constants(params)
         self.m["gravity"] = gravity
         self.N = int(n_envs)
@@ -365,6 +367,8 @@ class OracleVecEnv(object):
         if dim_mode != "3D" and init_random_state:
             raise ValueError("oracle: init_random_state is restated for dim_mode='3D' only")
         self.zero_middle = zero_middle
+        self.resample_goal, self.excite = bool(resample_goal), bool(excite)   # quadrotor.py:1078-1081, :957-962
+        self.goal_default = np.array(goal, dtype=np.float64)
         self.sim_steps = int(sim_steps)
         self.dt = 1.0 / sim_freq                                          # quadrotor.py:790
         self.ep_len = int(ep_time / (self.dt * self.sim_steps))           # :792
@@ -592,13 +596,19 @@ class OracleVecEnv(object):
         return np.concatenate(parts, axis=1), gyro_bias
 
     # ---------------------------------------------------------------------------------------------
-    def reset(self, mask=None, reset_z=None):
+    def reset(self, mask=None, reset_z=None, goal_z=None):
         """quadrotor.py:1059-1144 for the envs in mask.  reset_z: [N, RESET_Z] unit draws; returns obs [N,O]."""
         N = self.N
         if mask is None:
             mask = np.ones(N, dtype=bool)
         if reset_z is None:
             reset_z = np.zeros((N, RESET_Z))
+        if self.resample_goal or self.excite:                             # :1078-1081: the goal is re-made at every reset
+            g = np.tile(self.goal_default, (N, 1))
+            if self.resample_goal:                                        # np.random.uniform(0.5, 2.0)
+                u = np.zeros(N) if goal_z is None else np.asarray(goal_z, dtype=np.float64).reshape(N, GOAL_Z)[:, 3]
+                g = np.stack([np.zeros(N), np.zeros(N), 1.25 + 0.75 * u], axis=1)
+            self.goal = np.where(mask[:, None], g, self.goal)
         goal = self.goal
         pos = self.box * reset_z[:, RZ_UPOS:RZ_UPOS + 3] + goal           # :1087
         if self.dim_mode == "1D":                                         # :1089-1092
@@ -700,7 +710,7 @@ class OracleVecEnv(object):
         self.collided = hit.reshape(self.N)
 
     # ---------------------------------------------------------------------------------------------
-    def step(self, action, ou_z=None, obs_z=None, reset_z=None):
+    def step(self, action, ou_z=None, obs_z=None, reset_z=None, goal_z=None):
         """quadrotor.py:942-1028 (+ auto-reset).  Returns obs [N,O], reward [N], done [N] (bool)."""
         N = self.N
         action = np.asarray(action, dtype=np.float64).reshape(N, -1)
@@ -712,6 +722,10 @@ class OracleVecEnv(object):
         act4[:, :action.shape[1]] = action
         self.act_prev = self.act_cur.copy()                   # :943 actions[1] = actions[0]
         self.act_cur = act4.copy()                                    # :944 actions[0] = action
+        if self.excite:                                                   # :957-962, every 5th tick (before the increment)
+            gz = np.zeros((N, GOAL_Z)) if goal_z is None else np.asarray(goal_z, dtype=np.float64).reshape(N, GOAL_Z)
+            new = np.stack([0.5 * gz[:, 0], 0.5 * gz[:, 1], 2.0 + 0.5 * gz[:, 2]], axis=1)
+            self.goal = np.where((self.tick % 5 == 0)[:, None], new, self.goal)
         cmds = self.control(action)                                       # :966-970
         self.last_cmds = cmds
         self.dynamics_step(cmds, ou_z)
@@ -730,6 +744,6 @@ class OracleVecEnv(object):
             r = self.ep_return[done]
             self.stats += np.array([np.sum(r), np.sum(r * r), float(r.size)])
             if self.auto_reset:
-                obs_reset = self.reset(mask=done, reset_z=reset_z)
+                obs_reset = self.reset(mask=done, reset_z=reset_z, goal_z=goal_z)
                 obs = np.where(done[:, None], obs_reset, obs)
         return obs, reward, done

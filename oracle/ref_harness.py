@@ -103,8 +103,11 @@ class ReferenceRunner(object):
     def _reset_z_from_tape(self, log, pos_goal):
         tr = _TapeReader(log)
         rz = np.zeros(qo.RESET_Z)
-        rz[qo.RZ_UPOS:qo.RZ_UPOS + 3] = tr.pop("uniform", (3,))            # quadrotor.py:1087
         env = self.env
+        self.last_goal_z = np.zeros(qo.GOAL_Z)
+        if env.resample_goal:                                             # quadrotor.py:1078-1079, drawn before the spawn
+            self.last_goal_z[3] = tr.pop("uniform", ())
+        rz[qo.RZ_UPOS:qo.RZ_UPOS + 3] = tr.pop("uniform", (3,))            # quadrotor.py:1087
         if env.init_random_state:                                         # quadrotor.py:227-239
             tr.pop("uniform", (3,))                                       # pos draw, discarded (:228, :1113 `_`)
             rz[qo.RZ_UVEL:qo.RZ_UVEL + 3] = tr.pop("uniform", (3,))
@@ -141,10 +144,16 @@ class ReferenceRunner(object):
         env = self.env
         with self.tape:
             obs, rew, done, info = env.step(np.array(action, dtype=np.float64))
+        tick_before = env.tick - 1
         tr = _TapeReader(self.tape.take())
         zs = []
+        self.last_goal_z = np.zeros(qo.GOAL_Z)
         if self.noise_on:
             zs.append(_read_add_noise(tr, self.gyro_bias_mode))           # quadrotor.py:947
+        if env.excite and tick_before % 5 == 0:                           # :957-962
+            self.last_goal_z[0:2] = tr.pop("uniform", (2,))
+            self.last_goal_z[2] = tr.pop("uniform", (1,))[0]
+        if self.noise_on:
             zs.append(_read_add_noise(tr, self.gyro_bias_mode))           # :970
         ou_z = np.zeros((env.sim_steps, 4))
         for s in range(env.sim_steps):
@@ -178,4 +187,5 @@ def oracle_kwargs_from_env(env, controller_id):
     return dict(controller=controller_id, zero_middle=env.raw_control_zero_middle, sim_freq=1.0 / env.dt,
                 sim_steps=env.sim_steps, obs_repr=env.obs_repr, ep_time=env.ep_time, room_size=env.room_size,
                 init_random_state=env.init_random_state, rew_coeff=dict(env.rew_coeff), sense_noise=sn,
-                gravity=env.gravity, dim_mode=env.dim_mode, multi_reward="pos_log_weight" in env.rew_coeff)
+                gravity=env.gravity, dim_mode=env.dim_mode, multi_reward="pos_log_weight" in env.rew_coeff,
+                resample_goal=bool(env.resample_goal), excite=bool(env.excite))

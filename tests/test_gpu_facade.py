@@ -44,7 +44,8 @@ def test_known_answer_through_the_reference_api():
 
 
 @pytest.mark.parametrize("name,module", [("hb_mellinger_noise_act", "quadrotor"), ("cf_raw_noise_rnd", "quadrotor"),
-                                         ("hb_multi_reward", "multi")])
+                                         ("hb_multi_reward", "multi"), ("hb_mellinger_excite", "quadrotor"),
+                                         ("cf_raw_resample_goal", "quadrotor")])
 def test_env_facade_replays_reference_rollout(name, module):
     """reset()/step() through the facade with the reference's recorded noise tape injected: obs / reward / done of
     every step equal the reference's to 1e-9 over whole episodes (fp64 build)."""
@@ -60,19 +61,21 @@ def test_env_facade_replays_reference_rollout(name, module):
     vec.clock = (float(g.svd_timer0), 0)
     if vec.layout.row_ou >= 0:
         vec.set_field("ou_state", g.ou0)
-    vec.set_noise(reset_z=g.reset_z[0][None])
+    vec.set_noise(reset_z=g.reset_z[0][None], goal_z=g.reset_goal_z[0][None])
     o = env.reset()
     np.testing.assert_allclose(o, g.reset_obs[0], rtol=0, atol=1e-9)
     T = min(g.T, 620)
     for t in range(T):
-        vec.set_noise(ou_z=g.ou_z[t][None], obs_z=g.obs_z[t][None])
+        vec.set_noise(ou_z=g.ou_z[t][None], obs_z=g.obs_z[t][None], goal_z=g.goal_z[t][None])
         o, r, d, info = env.step(g.actions[t])
+        if "goal" in g.a:
+            np.testing.assert_allclose(env.goal, g.goal[t], rtol=0, atol=1e-12)
         np.testing.assert_allclose(o, g.obs[t], rtol=0, atol=2e-9, err_msg="obs step %d" % t)
         assert abs(r - g.rew[t]) < 1e-10 and d == bool(g.done[t])
         np.testing.assert_allclose(env.dynamics.accelerometer, g.accelerometer[t], rtol=0, atol=1e-8)
         if d:
             k = g.reset_index_after(t)
-            vec.set_noise(reset_z=g.reset_z[k][None])
+            vec.set_noise(reset_z=g.reset_z[k][None], goal_z=g.reset_goal_z[k][None])
             np.testing.assert_allclose(env.reset(), g.reset_obs[k], rtol=0, atol=1e-9)
             assert env.tick == 0 and env.traj_count == k
     env.close()

@@ -42,7 +42,8 @@ def make_env(g, n, dtype, noise_mode="injected", auto_reset=False, info=False, *
               dim_mode=ok["dim_mode"], sim_freq=ok["sim_freq"], sim_steps=ok["sim_steps"], obs_repr=ok["obs_repr"],
               ep_time=ok["ep_time"], room_size=ok["room_size"], init_random_state=ok["init_random_state"],
               rew_coeff=ok["rew_coeff"], sense_noise=ok["sense_noise"], gravity=ok["gravity"],
-              multi_reward=ok["multi_reward"], dtype=dtype, noise_mode=noise_mode, auto_reset=auto_reset, info=info)
+              multi_reward=ok["multi_reward"], dtype=dtype, noise_mode=noise_mode, auto_reset=auto_reset, info=info,
+              resample_goal=ok.get("resample_goal", False), excite=ok.get("excite", False))
     kw.update(over)
     env = QuadVecEnv(n, **kw)
     env.clock = (float(g.svd_timer0), 0)
@@ -71,6 +72,8 @@ def resync(env, g, t):
     env.set_field("thrust_cmds_damp", g.cmds_damp[t])
     if env.layout.row_ou >= 0:
         env.set_field("ou_state", g.ou[t])
+    if env.layout.row_goal >= 0 and "goal" in g.a:
+        env.set_field("goals", g.goal[t])
 
 
 def rel_err(a, b, floor):
@@ -84,12 +87,12 @@ def test_fp64_rollout_matches_reference(name):
     n = 3
     env = make_env(g, n, "float64")
     A = env.act_dim
-    env.set_noise(reset_z=tile(g.reset_z[0], n))
+    env.set_noise(reset_z=tile(g.reset_z[0], n), goal_z=tile(g.reset_goal_z[0], n))
     obs = env.reset().cpu().numpy()
     np.testing.assert_allclose(obs, tile(g.reset_obs[0], n), rtol=0, atol=1e-12)
     worst = 0.0
     for t in range(g.T):
-        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n))
+        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n), goal_z=tile(g.goal_z[t], n))
         o, r, d = env.step(tile(g.actions[t][:A], n))
         o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
         assert bool(d[0]) == bool(g.done[t]) and np.all(d == d[0])
@@ -100,7 +103,7 @@ def test_fp64_rollout_matches_reference(name):
         assert err < 2e-10, "step %d err %g" % (t, err)
         if d[0]:
             i = g.reset_index_after(t)
-            env.set_noise(reset_z=tile(g.reset_z[i], n))
+            env.set_noise(reset_z=tile(g.reset_z[i], n), goal_z=tile(g.reset_goal_z[i], n))
             ob = env.reset().cpu().numpy()
             np.testing.assert_allclose(ob, tile(g.reset_obs[i], n), rtol=0, atol=1e-12)
     env.check_finite()
@@ -114,12 +117,12 @@ def test_fp64_per_step_1e12(name):
     n = 2
     env = make_env(g, n, "float64")
     A = env.act_dim
-    env.set_noise(reset_z=tile(g.reset_z[0], n))
+    env.set_noise(reset_z=tile(g.reset_z[0], n), goal_z=tile(g.reset_goal_z[0], n))
     env.reset()
     for t in range(min(g.T, 400)):
         if t > 0 and not g.done[t - 1]:
             resync(env, g, t - 1)
-        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n))
+        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n), goal_z=tile(g.goal_z[t], n))
         o, r, d = env.step(tile(g.actions[t][:A], n))
         st = state_of(env)
         scale = lambda x: np.maximum(np.abs(x), 1.0)
@@ -129,7 +132,7 @@ def test_fp64_per_step_1e12(name):
             assert np.max(np.abs(st[k] - g.a[k][t]) / scale(g.a[k][t])) < 1e-12, "%s step %d" % (k, t)
         if g.done[t]:
             i = g.reset_index_after(t)
-            env.set_noise(reset_z=tile(g.reset_z[i], n))
+            env.set_noise(reset_z=tile(g.reset_z[i], n), goal_z=tile(g.reset_goal_z[i], n))
             ob = env.reset().cpu().numpy()
             np.testing.assert_allclose(ob, tile(g.reset_obs[i], n), rtol=0, atol=1e-12)
 
@@ -143,14 +146,14 @@ def test_fp32_per_step_1e5_relative(name):
     n = 2
     env = make_env(g, n, "float32")
     A = env.act_dim
-    env.set_noise(reset_z=tile(g.reset_z[0], n))
+    env.set_noise(reset_z=tile(g.reset_z[0], n), goal_z=tile(g.reset_goal_z[0], n))
     ob = env.reset().cpu().numpy()
     assert rel_err(ob, g.reset_obs[0], 1.0) < 1e-5
     worst = 0.0
     for t in range(min(g.T, 400)):
         if t > 0 and not g.done[t - 1]:
             resync(env, g, t - 1)
-        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n))
+        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n), goal_z=tile(g.goal_z[t], n))
         o, r, d = env.step(tile(g.actions[t][:A], n))
         assert bool(d[0].item()) == bool(g.done[t])
         st = state_of(env)
@@ -160,7 +163,7 @@ def test_fp32_per_step_1e5_relative(name):
         assert e < 1e-5, "step %d rel err %g" % (t, e)
         if g.done[t]:
             i = g.reset_index_after(t)
-            env.set_noise(reset_z=tile(g.reset_z[i], n))
+            env.set_noise(reset_z=tile(g.reset_z[i], n), goal_z=tile(g.reset_goal_z[i], n))
             ob = env.reset().cpu().numpy()
             assert rel_err(ob, g.reset_obs[i], 1.0) < 1e-5
     print(name, "fp32 per-step worst rel err", worst)
@@ -179,13 +182,13 @@ def test_fp32_500_step_drift(name, bound):
     n = 2
     env = make_env(g, n, "float32")
     A = env.act_dim
-    env.set_noise(reset_z=tile(g.reset_z[0], n))
+    env.set_noise(reset_z=tile(g.reset_z[0], n), goal_z=tile(g.reset_goal_z[0], n))
     env.reset()
     worst = 0.0
     for t in range(min(g.T, 500)):
         if g.done[t]:
             break
-        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n))
+        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n), goal_z=tile(g.goal_z[t], n))
         env.step(tile(g.actions[t][:A], n))
         st = state_of(env)
         worst = max(worst, max(rel_err(st[k], g.a[k][t], 1.0) for k in ("pos", "vel", "rot", "omega")))
@@ -219,7 +222,7 @@ def test_auto_reset_equals_explicit_reset_fp64():
     g = Golden("mq_raw_simsteps4")
     n = 5
     env = make_env(g, n, "float64", auto_reset=True)
-    env.set_noise(reset_z=tile(g.reset_z[0], n))
+    env.set_noise(reset_z=tile(g.reset_z[0], n), goal_z=tile(g.reset_goal_z[0], n))
     env.reset()
     for t in range(g.T):
         rz = None

@@ -27,10 +27,10 @@ def test_oracle_reproduces_reference_rollout(name):
     g = Golden(name)
     oe = make_oracle(g)
     A = qo.CTRL_ACT_DIM[g.controller]
-    obs0 = oe.reset(reset_z=g.reset_z[0][None])
+    obs0 = oe.reset(reset_z=g.reset_z[0][None], goal_z=g.reset_goal_z[0][None])
     np.testing.assert_allclose(obs0[0], g.reset_obs[0], rtol=0, atol=ATOL)
     for t in range(g.T):
-        o, r, d = oe.step(g.actions[t][None, :A], ou_z=g.ou_z[t][None], obs_z=g.obs_z[t][None])
+        o, r, d = oe.step(g.actions[t][None, :A], ou_z=g.ou_z[t][None], obs_z=g.obs_z[t][None], goal_z=g.goal_z[t][None])
         assert bool(d[0]) == bool(g.done[t])
         np.testing.assert_allclose(o[0], g.obs[t], rtol=0, atol=ATOL, err_msg="obs step %d" % t)
         np.testing.assert_allclose(r[0], g.rew[t], rtol=0, atol=ATOL, err_msg="rew step %d" % t)
@@ -38,7 +38,7 @@ def test_oracle_reproduces_reference_rollout(name):
             np.testing.assert_allclose(getattr(oe, k)[0], g.a[k][t], rtol=0, atol=ATOL, err_msg="%s step %d" % (k, t))
         if d[0]:
             i = g.reset_index_after(t)
-            ob = oe.reset(reset_z=g.reset_z[i][None])
+            ob = oe.reset(reset_z=g.reset_z[i][None], goal_z=g.reset_goal_z[i][None])
             np.testing.assert_allclose(ob[0], g.reset_obs[i], rtol=0, atol=ATOL)
 
 

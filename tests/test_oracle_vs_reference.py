@@ -22,7 +22,7 @@ def _compare(n_steps, controller_id=qo.CTRL_RAW, ext=None, seed=0, act_fn=None, 
     oe.ou = env.dynamics.thrust_noise.state[None].copy()
     oe.gyro_bias = env.sense_noise.gyro_bias[None].copy()
     obs_r, rz = rr.reset()
-    obs_o = oe.reset(reset_z=rz[None])
+    obs_o = oe.reset(reset_z=rz[None], goal_z=rr.last_goal_z[None])
     np.testing.assert_allclose(obs_o[0], obs_r, rtol=0, atol=ATOL)
     rng = np.random.RandomState(77 + seed)
     A = qo.CTRL_ACT_DIM[controller_id]
@@ -31,7 +31,7 @@ def _compare(n_steps, controller_id=qo.CTRL_RAW, ext=None, seed=0, act_fn=None, 
         a4 = np.zeros(4)
         a4[:A] = a
         o_r, r_r, d_r, info, ou_z, obs_z = rr.step(a4)
-        o_o, r_o, d_o = oe.step(a[None], ou_z=ou_z[None], obs_z=obs_z[None])
+        o_o, r_o, d_o = oe.step(a[None], ou_z=ou_z[None], obs_z=obs_z[None], goal_z=rr.last_goal_z[None])
         st = rr.state()
         assert d_r == bool(d_o[0])
         np.testing.assert_allclose(o_o[0], o_r, rtol=0, atol=ATOL, err_msg="obs %d" % t)
@@ -40,7 +40,7 @@ def _compare(n_steps, controller_id=qo.CTRL_RAW, ext=None, seed=0, act_fn=None, 
             np.testing.assert_allclose(getattr(oe, k)[0], st[k], rtol=0, atol=ATOL, err_msg="%s %d" % (k, t))
         if d_r:
             obs_r, rz = rr.reset()
-            obs_o = oe.reset(reset_z=rz[None])
+            obs_o = oe.reset(reset_z=rz[None], goal_z=rr.last_goal_z[None])
             np.testing.assert_allclose(obs_o[0], obs_r, rtol=0, atol=ATOL)
 
 
@@ -118,3 +118,12 @@ def test_live_reward_variants_and_drag():
                         "damp_time_down": 0.3}, "damp": {"vel": 0.001, "omega_quadratic": 0.015}}
     _compare(300, seed=42, dynamics_params="Crazyflie", ep_time=0.5, dynamics_change=change, init_random_state=True,
              act_fn=lambda rng: rng.uniform(-0.2, 0.6, 4))
+
+
+def test_live_moving_goals_excite_and_resample():
+    """excite: a new random goal every 5 ticks (quadrotor.py:957-962); resample_goal: goal height drawn at reset
+    (:1078-1079), with the spawn position following the new goal (:1087)."""
+    _compare(260, controller_id=qo.CTRL_MELLINGER, seed=50, dynamics_params="DefaultQuad", raw_control=False, ep_time=1,
+             excite=True, sense_noise="default", act_fn=lambda rng: np.zeros(4))
+    _compare(260, seed=51, dynamics_params="Crazyflie", ep_time=0.3, resample_goal=True, init_random_state=True)
+    _compare(160, seed=52, dynamics_params="Crazyflie", ep_time=0.3, resample_goal=True, excite=True)
