@@ -29,7 +29,7 @@ STATUS_NAMES = {QS_EINVAL: "QS_EINVAL", QS_ECUDA: "QS_ECUDA", QS_ENONFINITE: "QS
 
 # every symbol include/quadsim.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = ["qs_abi_version", "qs_state_layout", "qs_create", "qs_destroy", "qs_last_error", "qs_bind_state", "qs_bind_models", "qs_bind_info",
-           "qs_set_noise_injection", "qs_set_goal_injection", "qs_reset", "qs_step", "qs_step_k", "qs_dynamics_step", "qs_step_host", "qs_get_stats",
+           "qs_set_noise_injection", "qs_set_goal_injection", "qs_reset", "qs_observe", "qs_step", "qs_step_k", "qs_dynamics_step", "qs_step_host", "qs_get_stats",
            "qs_stats_device_ptr", "qs_check", "qs_get_clock", "qs_set_clock", "qs_launch_count", "qs_last_variant", "qs_last_host_path"]
 
 
@@ -106,6 +106,7 @@ def load():
         "qs_set_noise_injection": (C.c_int, [H, P, P, P]),
         "qs_set_goal_injection": (C.c_int, [H, P]),
         "qs_reset": (C.c_int, [H, P, P, P]),
+        "qs_observe": (C.c_int, [H, P, P, P]),
         "qs_step": (C.c_int, [H, P, P, P, P, P]),
         "qs_step_k": (C.c_int, [H, C.c_int, P, P, P, P, P]),
         "qs_dynamics_step": (C.c_int, [H, C.c_int, P, C.c_int, P]),

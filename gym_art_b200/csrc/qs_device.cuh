@@ -47,6 +47,7 @@ struct Params {
   const R* obs_z;           // injected: [n][OBS_Z]
   const R* reset_z;         // injected: [n][RESET_Z]
   const R* goal_z;          // injected: [n][4] moving-goal draws (excite xyz, resample_goal z)
+  const R* acc_in;          // qs_observe: clean accelerometer readings [n][3] or null
   double* stats;            // [3]
   int* status;              // sticky non-finite flag
   long long n;              // envs on the handle = row stride of the state buffer
@@ -1640,6 +1641,40 @@ __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// state_<obs_repr>(env) / SensorNoise.add_noise on the bound state (get_state.py, sensor_noise.py:100-159): a fresh
+// noisy observation without stepping.  One add_noise call: draws come from the reset-observation slots.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R, class T>
+__global__ void __launch_bounds__(BLOCK) env_observe_kernel(const __grid_constant__ Params<R> p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  R* tile = reinterpret_cast<R*>(smem_raw);
+  const long long block_first = p.begin + (long long)blockIdx.x * BLOCK;
+  const long long i = block_first + threadIdx.x;
+  const bool active = i < p.end;
+  if (active) {
+    St<R> s;
+    load_state<R, T>(s, p, i, true);
+    NoiseSrc<R, T> ns(p, i);
+    ns.begin_step(p.clock->step);
+    if (p.acc_in != nullptr) {        // world acceleration that reproduces the given reading: R a - (0, 0, gravity)
+      const R ax = p.acc_in[i * 3], ay = p.acc_in[i * 3 + 1], az = p.acc_in[i * 3 + 2];
+      s.ax = s.r[0] * ax + s.r[1] * ay + s.r[2] * az;
+      s.ay = s.r[3] * ax + s.r[4] * ay + s.r[5] * az;
+      s.az = s.r[6] * ax + s.r[7] * ay + s.r[8] * az - p.gravity;
+    } else {
+      s.fresh = true;                 // (0, 0, GRAV), the reading set_state leaves behind (quadrotor.py:221)
+    }
+    R o[26];
+    build_obs<R, T>(s, p, ns, true, s.pa, o);
+    if (T::RARE) { if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0)); }   // the bias walks on
+    obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
+  }
+  __syncthreads();
+  flush_tile(p, tile, block_first, nullptr);
+  finish_clock(p, p.clock->svd_timer, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // controller.step_func / QuadrotorDynamics.step on the bound state, no env bookkeeping
 // ---------------------------------------------------------------------------------------------------------
 template <typename R, class T>
@@ -1698,6 +1733,7 @@ __global__ void clock_advance_kernel(const __grid_constant__ Params<R> p) {
 template <typename R> cudaError_t launch_step(const Params<R>& p, cudaStream_t st, const char** variant_name);
 template <typename R> cudaError_t launch_reset(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_dynamics(const Params<R>& p, cudaStream_t st);
+template <typename R> cudaError_t launch_observe(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_clock_advance(const Params<R>& p, cudaStream_t st);
 // fp32 fast subset (qs_fast.inl, one translation unit per controller x noise source)
 #define QS_DECL_FAST(name) cudaError_t name(const Params<float>& p, cudaStream_t st, const char** variant_name)

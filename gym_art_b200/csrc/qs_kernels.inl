@@ -68,6 +68,16 @@ cudaError_t launch_dynamics<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) 
 }
 
 template <>
+cudaError_t launch_observe<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) {
+  typedef QS_REAL R;
+  const unsigned grid = (unsigned)((p.end - p.begin + BLOCK - 1) / BLOCK);
+  const size_t smem = (size_t)BLOCK * p.obs_dim * sizeof(R);
+  if (p.inject) env_observe_kernel<R, TGenInject><<<grid, BLOCK, smem, st>>>(p);
+  else env_observe_kernel<R, TGenPhilox><<<grid, BLOCK, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <>
 cudaError_t launch_clock_advance<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) {
   clock_advance_kernel<QS_REAL><<<1, 1, 0, st>>>(p);
   return cudaGetLastError();

@@ -399,6 +399,26 @@ int qs_reset(QsHandle* h, const uint8_t* mask, void* obs, qs_stream_t stream) {
   return QS_OK;
 }
 
+int qs_observe(QsHandle* h, const void* accelerometer, void* obs, qs_stream_t stream) {
+  int rc = check_ready(h, false, nullptr);
+  if (rc != QS_OK) return rc;
+  if (!obs) return fail(h, QS_EINVAL, "obs is NULL");
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaError_t e;
+  if (h->cfg.dtype == QS_F32) {
+    qs::Params<float> p; fill_params<float>(h, &p);
+    p.acc_in = (const float*)accelerometer; p.obs = (float*)obs; p.begin = 0; p.end = p.n;
+    e = qs::launch_observe<float>(p, (cudaStream_t)stream);
+  } else {
+    qs::Params<double> p; fill_params<double>(h, &p);
+    p.acc_in = (const double*)accelerometer; p.obs = (double*)obs; p.begin = 0; p.end = p.n;
+    e = qs::launch_observe<double>(p, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return fail(h, QS_ECUDA, "env_observe launch: %s", cudaGetErrorString(e));
+  h->launches++;
+  return QS_OK;
+}
+
 int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8_t* done, qs_stream_t stream) {
   int rc = check_ready(h, true, actions);
   if (rc != QS_OK) return rc;

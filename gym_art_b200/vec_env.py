@@ -425,6 +425,14 @@ class QuadVecEnv(object):
         self._done_call()
         return self.obs
 
+    def observe(self, accelerometer=None):
+        """A fresh noisy observation of the current state without stepping (state_<obs_repr>(env) / add_noise)."""
+        acc = None if accelerometer is None else self._in("acc_in", accelerometer, self.tdtype, (self.num_envs, 3))
+        _lib.check(self.lib.qs_observe(self._h, None if acc is None else acc.data_ptr(), self.obs.data_ptr(), self._stream()),
+                   self._h)
+        self._done_call()
+        return self.obs
+
     def _actions(self, actions, k=None):
         if actions is None:
             return None

@@ -244,6 +244,12 @@ int qs_set_goal_injection(QsHandle* h, const void* goal_z);
  * (mask NULL = all).  obs: real[n_envs][obs_dim], rows of unmasked envs are left untouched. */
 int qs_reset(QsHandle* h, const uint8_t* mask, void* obs, qs_stream_t stream);
 
+/* replaces state_<obs_repr>(env) (get_state.py) / SensorNoise.add_noise (sensor_noise.py:100-159): a fresh noisy
+ * observation of the bound state without stepping (one add_noise call; injected mode reads the reset-observation slots
+ * reset_z[QS_RZ_OBS..]).  accelerometer: optional clean body-frame readings real[n_envs][3] (NULL = (0, 0, 9.81), the
+ * value set_state leaves behind, quadrotor.py:221).  obs: real[n_envs][obs_dim]. */
+int qs_observe(QsHandle* h, const void* accelerometer, void* obs, qs_stream_t stream);
+
 /* replaces QuadrotorEnv.step() (quadrotor.py:942-1028): controller -> sim_steps x step1 -> collision ->
  * crash/reward/tick/done -> (auto-reset) -> observation, one fused kernel.
  * actions: real[n_envs][act_dim] (may be NULL for QS_CTRL_MELLINGER: the reference ignores the action and the

@@ -427,3 +427,54 @@ def test_mellinger_closed_loop_converges_like_the_reference():
     assert not bool(d.any()) and bool((env.tick == 500).all())  # the 501st step ends the episode (quadrotor.py:986-987)
     o, r, d = env.step(None)
     assert bool(d.all()) and bool((env.tick == 0).all())
+
+
+def test_observe_matches_oracle_add_noise_fp64():
+    """qs_observe == one SensorNoise.add_noise call + state_<obs_repr> on the current state (sensor_noise.py:100-159,
+    get_state.py), every noise feature on, injected draws, given accelerometer readings."""
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    from oracle import quadsim_oracle as qo
+    n = 777
+    rng = np.random.RandomState(4)
+    sn = dict(pos_unif_range=0.01, vel_unif_range=0.02, quat_norm_std=0.01, quat_unif_range=0.02, gyro_norm_std=0.1)
+    params = quad_models.crazyflie_params()
+    kw = dict(obs_repr="xyz_vxyz_R_omega_acc_act", sense_noise=sn, init_random_state=True, ep_time=1)
+    env = QuadVecEnv(n, dynamics_params=params, dtype="float64", noise_mode="injected", auto_reset=False, **kw)
+    oe = qo.OracleVecEnv(params, n, auto_reset=False, **kw)
+    rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+    rz[:, qo.RZ_NUP:] = rng.standard_normal((n, qo.RESET_Z - qo.RZ_NUP))
+    env.set_noise(reset_z=rz)
+    env.reset(), oe.reset(reset_z=rz)
+    for rep in range(3):                                           # the gyro-bias random walk advances on every call
+        rz = rng.standard_normal((n, qo.RESET_Z))
+        rz[:, qo.RZ_OBS + qo.Z_UPOS:qo.RZ_OBS + qo.Z_UPOS + 3] = rng.uniform(-1, 1, (n, 3))
+        rz[:, qo.RZ_OBS + qo.Z_UVEL:qo.RZ_OBS + qo.Z_UVEL + 3] = rng.uniform(-1, 1, (n, 3))
+        rz[:, qo.RZ_OBS + qo.Z_UTHETA:qo.RZ_OBS + qo.Z_UTHETA + 3] = rng.uniform(-1, 1, (n, 3))
+        acc = rng.uniform(-3, 12, (n, 3))
+        env.set_noise(reset_z=rz)
+        o = env.observe(acc).cpu().numpy()
+        oe.accelerometer = acc.copy()
+        oo, oe.gyro_bias = oe.observe(rz[:, qo.RZ_OBS:qo.RZ_OBS + qo.OBS_Z], n_calls=1)
+        np.testing.assert_allclose(o, oo, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(env.gyro_bias.cpu().numpy(), oe.gyro_bias, rtol=0, atol=1e-14)
+    env.close()
+
+
+def test_sensor_noise_object_add_noise():
+    """SensorNoise.add_noise with the reference's call shape; noisy R stays orthogonal - the one property the reference's
+    own noise scripts check (test_noise.py:265-269: allclose(R.T, inv(R), 1e-5))."""
+    from gym_art_b200.quadrotor.sensor_noise import SensorNoise
+    sn = SensorNoise(quat_norm_std=0.02, quat_unif_range=0.01)
+    c, s = np.cos(0.4), np.sin(0.4)
+    R = np.array([[c, -s, 0.], [s, c, 0.], [0., 0., 1.]])
+    pos, vel, omega, acc = np.array([1., -2., 3.]), np.array([0.1, 0.2, 0.3]), np.array([0.5, -0.5, 0.1]), np.array([0., 0., 9.81])
+    outs = [sn.add_noise(pos, vel, R, omega, acc, dt=0.005, seed=1) for _ in range(200)]
+    P = np.array([o[0] for o in outs]); V = np.array([o[1] for o in outs]); W = np.array([o[3] for o in outs]); A = np.array([o[4] for o in outs])
+    assert np.all(np.abs(P.mean(0) - pos) < 0.002) and 0.003 < P.std(0).mean() < 0.007          # pos_norm_std 0.005
+    assert np.all(np.abs(V.mean(0) - vel) < 0.004) and 0.007 < V.std(0).mean() < 0.013          # vel_norm_std 0.01
+    assert np.all(np.abs(W.mean(0) - omega) < 1e-3) and np.all(np.abs(A.mean(0) - acc) < 0.02)
+    for o in outs[:20]:
+        Rn = o[2]
+        assert np.allclose(Rn.T, np.linalg.inv(Rn), atol=1e-5) and not np.allclose(Rn, R, atol=1e-4)
+    assert SensorNoise(bypass=True).add_noise(pos, vel, R, omega, acc, dt=0.005)[0] is pos
