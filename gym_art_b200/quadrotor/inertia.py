@@ -97,3 +97,47 @@ class QuadLink(object):
         self.prop_pos = pos[6:10].copy()        # the motor centres, as in the reference (inertia.py:309)
         if verbose:
             print("QuadLink: m=%g com=%s diag(I)=%s" % (self.m, self.com, np.diagonal(self.I_com)))
+
+
+class QuadLinkSimplified(object):
+    """The reference's simplified body (inertia.py:312-420, `dynamics_simplification=True`): two perpendicular rods
+    carrying the whole mass and four massless propellers.  Attributes as QuadLink: m, com, I_com, prop_pos, motor_xyz."""
+
+    motors_num = 4
+    rods_num = 2
+
+    def __init__(self, params=None, verbose=False):
+        from .quad_models import crazyflie_params
+        base = crazyflie_params()["geom"]                   # the reference fills unspecified parts from CrazyFlie values
+        base.update(params or {})
+        p = self.params = base
+        self.arm_length = np.sqrt(p["motor_pos"]["xyz"][0] ** 2 * 2) * 2                 # diagonal motor-to-motor distance
+        p["propellers"] = {"h": 0.002, "r": self.arm_length / 4, "m": 0.0}
+        mxy = self.arm_length * np.sqrt(2) / 4
+        p["motor_pos"]["xyz"] = [mxy, mxy, 0.0]
+        self.motor_xyz = np.array(p["motor_pos"]["xyz"], dtype=np.float64)
+        if "mass" not in p:
+            def box_m(d):
+                return d["m"] if d.get("m") is not None else d["density"] * d["l"] * d["w"] * d["h"]
+
+            def cyl_m(d):
+                return d["m"] if d.get("m") is not None else d["density"] * np.pi * d["h"] * d["r"] ** 2
+
+            p["mass"] = box_m(p["body"]) + box_m(p["payload"]) + 4 * box_m(p["arms"]) + 4 * cyl_m(p["motors"]) + \
+                4 * cyl_m(p["propellers"])
+        p["arms"] = {"l": self.arm_length, "r": self.arm_length / 20, "m": p["mass"] / 2}
+        angle = float(p["arms_pos"]["angle"]) / 180. * np.pi
+        self.arm_angle = angle if angle != 0. else 0.01
+        arm_xyz = np.array([0., 0., p["arms_pos"]["z"]])
+        motors_xyz = (MOTOR_SIGNS * self.motor_xyz[:, None]).T
+        rod_m = p["arms"]["m"]
+        rod_I = np.diag([rod_m * self.arm_length ** 2 / 12., 0., rod_m * self.arm_length ** 2 / 12.])   # RodLink.I_com :121-126
+        self.m = 2 * rod_m                                  # the propellers are massless
+        self.com = (2 * rod_m * arm_xyz) / self.m
+        total = np.zeros((3, 3))
+        for a in (-self.arm_angle, self.arm_angle):
+            c, s = np.cos(a), np.sin(a)
+            Rz = np.array([[c, -s, 0.], [s, c, 0.], [0., 0., 1.]])
+            total = total + _shift(Rz @ rod_I @ Rz.T, rod_m, arm_xyz - self.com)
+        self.I_com = total
+        self.prop_pos = motors_xyz - self.com

@@ -6,7 +6,7 @@ Follows QuadrotorDynamics.__init__/update_model (gym_art/quadrotor/quadrotor.py:
 import numpy as np
 
 from .. import _lib
-from .inertia import QuadLink
+from .inertia import QuadLink, QuadLinkSimplified
 
 GRAV = 9.81
 EPS = 1e-6
@@ -18,9 +18,10 @@ OU_THETA = 0.15                                # quad_utils.py:181
 class ModelConstants(object):
     """Everything the kernels need to know about one quadrotor model."""
 
-    def __init__(self, params, gravity=GRAV):
+    def __init__(self, params, gravity=GRAV, dynamics_simplification=False):
         self.params = params
-        self.link = QuadLink(params=params["geom"])
+        # quadrotor.py:143-146
+        self.link = QuadLinkSimplified(params=params["geom"]) if dynamics_simplification else QuadLink(params=params["geom"])
         motor, damp, noise = params["motor"], params["damp"], params["noise"]
         self.mass = float(self.link.m)
         self.inertia = np.array(np.diagonal(self.link.I_com), dtype=np.float64)

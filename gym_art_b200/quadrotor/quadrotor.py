@@ -81,14 +81,14 @@ class QuadrotorDynamics(object):
                                     sim_steps=dynamics_steps_num, room_size=float(self.room_box[1][2]), gravity=gravity,
                                     device=device, dtype=dtype, seed=seed, auto_reset=False, info=True,
                                     noise_mode=noise_mode, goals=np.zeros((self.num_envs, 3)),
-                                    host_mapped=self.num_envs <= 64)
+                                    host_mapped=self.num_envs <= 64, dynamics_simplification=dynamics_simplification)
             self._handle(1.0 / 200.0, True)        # allocates the state tensor; re-keyed by the dt of the first step
             self.set_state(np.zeros(3), np.zeros(3), np.eye(3), np.zeros(3))
 
     # ---- model (quadrotor.py:142-208) --------------------------------------------------------------------
     def update_model(self, model_params):
         self.model_params = model_params
-        m = ModelConstants(model_params, gravity=self.gravity)
+        m = ModelConstants(model_params, gravity=self.gravity, dynamics_simplification=self.dynamics_simplification)
         self.model = m                                           # carries link geometry + derived constants
         for k in ("mass", "inertia", "thrust_to_weight", "torque_to_thrust", "motor_linearity", "C_rot_drag",
                   "C_rot_roll", "motor_damp_time_up", "motor_damp_time_down", "thrust_noise_ratio", "vel_damp",
@@ -410,7 +410,7 @@ class QuadrotorEnv(object):
                   gravity=self.gravity, device=self._device, dtype=self._dtype, seed=self._philox_seed,
                   noise_mode=self._noise_mode, auto_reset=False, info=True, multi_reward=self._multi_reward,
                   goals=np.asarray(self.goal, dtype=np.float64).reshape(1, 3), box=self.box, host_mapped=True,
-                  resample_goal=self.resample_goal, excite=self.excite)
+                  resample_goal=self.resample_goal, excite=self.excite, dynamics_simplification=self.dynamics_simplification)
         vec = QuadVecEnv(1, **kw)
         if old_state is not None:
             if old_state.shape == vec.state.shape:      # OU state, gyro bias and the SVD timer survive a model change

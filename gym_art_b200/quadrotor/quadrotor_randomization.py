@@ -165,6 +165,24 @@ def sample_t2w_t2t(params, t2w_min, t2w_max, t2t_min=0.003, t2t_max=0.009):   # 
     return params
 
 
+def sample_simplified_random_dyn():
+    """:263-326 - random parameters for the simplified (two rods) body: mass, arm length, motor parameters."""
+    g = {"mass": np.random.uniform(low=0.020, high=0.6)}
+    arm_length = np.random.uniform(low=0.05, high=0.5)
+    g["arms"] = {"l": arm_length}
+    mxy = arm_length * np.sqrt(2) / 4
+    g["motor_pos"] = {"xyz": [mxy, mxy, 0.0]}
+    t2w = np.random.uniform(low=1.5, high=3.5)
+    damp = {"vel": 0.0, "omega_quadratic": 0.0}
+    noise = {"thrust_noise_ratio": np.random.uniform(low=0.05, high=0.1)}
+    damp_time_up = np.random.uniform(low=0.1, high=0.2)
+    damp_time_down_scale = np.random.uniform(low=1.0, high=2.0)
+    motor = {"thrust_to_weight": t2w, "torque_to_thrust": np.random.uniform(low=0.005, high=0.02),
+             "assymetry": np.random.uniform(low=0.9, high=1.1, size=4), "linearity": 1.0, "C_drag": 0., "C_roll": 0.,
+             "damp_time_up": damp_time_up, "damp_time_down": damp_time_down_scale * damp_time_up}
+    return {"geom": g, "damp": damp, "noise": noise, "motor": motor}
+
+
 class Crazyflie(object):                                                  # :329-343
     def sample(self, params=None):
         return quad_models.crazyflie_params()

@@ -26,6 +26,7 @@ REW_COEFF_MULTI_DEFAULT = {"pos": 1., "pos_offset": 0.1, "pos_log_weight": 1., "
 
 
 def resolve_dynamics_params(dynamics_params, dynamics_change=None, check=True):
+    # (the limits check assumes the full link geometry; simplified-geometry dicts skip the parts they do not have)
     """quadrotor.py:738-744 + :1030-1056: sampler name (or dict) -> checked parameter dict."""
     if isinstance(dynamics_params, str):
         params = getattr(quad_rand, dynamics_params)().sample()
@@ -153,7 +154,7 @@ class QuadVecEnv(object):
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
                  max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None,
-                 host_mapped=False, resample_goal=False, excite=False):
+                 host_mapped=False, resample_goal=False, excite=False, dynamics_simplification=False):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -171,7 +172,7 @@ class QuadVecEnv(object):
                 controller = "mellinger"
         self.controller_name = controller
         self.dynamics_params = resolve_dynamics_params(dynamics_params, dynamics_change)
-        self.model = ModelConstants(self.dynamics_params, gravity=gravity)
+        self.model = ModelConstants(self.dynamics_params, gravity=gravity, dynamics_simplification=dynamics_simplification)
         self.cfg, self.rew_coeff, self.sense_noise = make_config(
             num_envs, self.model, controller=controller, raw_control_zero_middle=raw_control_zero_middle,
             dim_mode=dim_mode, sim_freq=sim_freq, sim_steps=sim_steps, obs_repr=obs_repr, ep_time=ep_time,

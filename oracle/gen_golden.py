@@ -89,6 +89,8 @@ CASES = {
                             dict(dynamics_params="DefaultQuad", raw_control=False, ep_time=2, excite=True, sense_noise="default")),
     "cf_raw_resample_goal": (qo.CTRL_RAW, None, _uni(-0.2, 0.6, 4), 300, 20, False,
                              dict(dynamics_params="Crazyflie", ep_time=0.5, resample_goal=True)),
+    "cf_raw_simplified": (qo.CTRL_RAW, None, _uni(-0.2, 0.8, 4), 300, 21, False,
+                          dict(dynamics_params="Crazyflie", ep_time=1, dynamics_simplification=True, sense_noise="default")),
     "mq_raw_simsteps4": (qo.CTRL_RAW, None, _uni(-0.5, 0.8, 4), 300, 15, False,
                          dict(dynamics_params="MediumQuad", ep_time=2, sim_steps=4, sim_freq=100.0)),
 }
@@ -212,8 +214,14 @@ def random_models():
     np.random.seed(300)
     p = qr.sample_t2w_t2t(qr.sample_linearity(qr.sample_nodelay(ref.quad_models.defaultquad_params())), 1.8, 2.5)
     cases.append(("helpers_0", p))
+    for simp_name, simp_params in (("simplified_cf", ref.quad_models.crazyflie_params()),
+                                   ("simplified_hb", ref.quad_models.defaultquad_params())):
+        cases.append((simp_name, simp_params))
+    np.random.seed(400)
+    cases.append(("simplified_random", qr.sample_simplified_random_dyn()))
     for name, params in cases:
-        d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2)
+        d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2,
+                                            dynamics_simplification=name.startswith("simplified"))
         ctrl = ref.control.OmegaThrustControl(d)
         out[name + "_params_json"] = np.array(json.dumps(_plain(params)))
         for k in ("mass", "inertia", "prop_pos", "thrust_max", "torque_max", "arm"):

@@ -126,9 +126,42 @@ def quadlink_constants(geom):
     return dict(mass=m_total, I_com=I_com, prop_pos=prop_pos, motor_xyz=motor_xyz)
 
 
-def model_constants(params):
+def quadlink_simplified_constants(geom):
+    """inertia.py:312-420 (QuadLinkSimplified): two rods of half the mass each, massless propellers."""
+    defaults = {"body": {"l": 0.03, "w": 0.03, "h": 0.004, "m": 0.005}, "payload": {"l": 0.035, "w": 0.02, "h": 0.008, "m": 0.01},
+                "arms": {"w": 0.005, "h": 0.005, "m": 0.001}, "motors": {"h": 0.02, "r": 0.0035, "m": 0.0015},
+                "arms_pos": {"angle": 45.0, "z": 0.0}}                    # :327-336 (CrazyFlie values for unspecified parts)
+    geom = dict(defaults, **geom)
+    arm_length = np.sqrt(geom["motor_pos"]["xyz"][0] ** 2 * 2) * 2        # :345
+    mxy = arm_length * np.sqrt(2) / 4                                     # :347
+    if "mass" in geom:
+        mass = geom["mass"]
+    else:                                                                 # :351-358, propellers already massless (:346)
+        def bm(d):
+            return d["m"] if d.get("m") is not None else d["density"] * d["l"] * d["w"] * d["h"]
+
+        def cm(d):
+            return d["m"] if d.get("m") is not None else d["density"] * np.pi * d["h"] * d["r"] ** 2
+        mass = bm(geom["body"]) + bm(geom["payload"]) + 4 * bm(geom["arms"]) + 4 * cm(geom["motors"])
+    rod_m = mass / 2                                                      # :360
+    ang = float(geom["arms_pos"]["angle"]) / 180.0 * np.pi
+    if ang == 0.0:
+        ang = 0.01
+    a = rod_m * arm_length ** 2 / 12.0                                    # RodLink.I_com :121-126
+    I = np.zeros((3, 3))
+    for al in (-ang, ang):                                                # :391-394, rods at the COM
+        Rz = np.array([[np.cos(al), -np.sin(al), 0.0], [np.sin(al), np.cos(al), 0.0], [0.0, 0.0, 1.0]])
+        I = I + Rz @ np.diag([a, 0.0, a]) @ Rz.T
+    sx = np.array([1.0, -1.0, -1.0, 1.0])
+    sy = np.array([-1.0, -1.0, 1.0, 1.0])
+    z_arm = geom["arms_pos"]["z"]
+    prop_pos = np.stack([sx * mxy, sy * mxy, np.zeros(4) - z_arm], axis=1)   # motors at z = 0, COM at the rods' height
+    return dict(mass=2 * rod_m, I_com=I, prop_pos=prop_pos, motor_xyz=np.array([mxy, mxy, 0.0]))
+
+
+def model_constants(params, simplified=False):
     """quadrotor.py:77-208 (QuadrotorDynamics.__init__/update_model) -> flat dict of float64 constants."""
-    ql = quadlink_constants(params["geom"])
+    ql = quadlink_simplified_constants(params["geom"]) if simplified else quadlink_constants(params["geom"])
     motor, damp, noise = params["motor"], params["damp"], params["noise"]
     mass = ql["mass"]
     inertia = np.diagonal(ql["I_com"]).copy()                             # :152
@@ -358,8 +391,8 @@ class OracleVecEnv(object):
                  obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10.0, init_random_state=False, rew_coeff=None,
                  sense_noise=None, gravity=GRAV, auto_reset=True, goal=(0.0, 0.0, 2.0), box=2.0,
                  multi_reward=False, n_agents=1, collision_k=1.0, collision_coeff=0.0, goals=None, dim_mode="3D",
-                 resample_goal=False, excite=False):
-        self.m = model_constants(params)
+                 resample_goal=False, excite=False, dynamics_simplification=False):
+        self.m = model_constants(params, simplified=dynamics_simplification)
         self.m["gravity"] = gravity
         self.N = int(n_envs)
         self.controller = controller

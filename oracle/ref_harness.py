@@ -188,4 +188,5 @@ def oracle_kwargs_from_env(env, controller_id):
                 sim_steps=env.sim_steps, obs_repr=env.obs_repr, ep_time=env.ep_time, room_size=env.room_size,
                 init_random_state=env.init_random_state, rew_coeff=dict(env.rew_coeff), sense_noise=sn,
                 gravity=env.gravity, dim_mode=env.dim_mode, multi_reward="pos_log_weight" in env.rew_coeff,
-                resample_goal=bool(env.resample_goal), excite=bool(env.excite))
+                resample_goal=bool(env.resample_goal), excite=bool(env.excite),
+                dynamics_simplification=bool(env.dynamics_simplification))

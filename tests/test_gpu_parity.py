@@ -31,7 +31,7 @@ EXPECTED_VARIANT = {
     "cf_omegathrust_noise_rnd": "tma-omega-thrust-injected", "cf_relative_omegathrust": "tma-omega-thrust-injected",
     "hb_mellinger_noise_act": "tma-mellinger-injected", "hb_mellinger_nonoise": "tma-mellinger-injected",
     "cf_mellinger_rnd": "tma-mellinger-injected", "rq_mellinger": "tma-mellinger-injected",
-    "hb_velyaw": "tma-velocity-yaw-injected", "hb_shifted": "tma-shifted-injected",
+    "hb_velyaw": "tma-velocity-yaw-injected", "hb_shifted": "tma-shifted-injected", "cf_raw_simplified": "tma-raw-injected",
 }
 
 
@@ -43,7 +43,8 @@ def make_env(g, n, dtype, noise_mode="injected", auto_reset=False, info=False, *
               ep_time=ok["ep_time"], room_size=ok["room_size"], init_random_state=ok["init_random_state"],
               rew_coeff=ok["rew_coeff"], sense_noise=ok["sense_noise"], gravity=ok["gravity"],
               multi_reward=ok["multi_reward"], dtype=dtype, noise_mode=noise_mode, auto_reset=auto_reset, info=info,
-              resample_goal=ok.get("resample_goal", False), excite=ok.get("excite", False))
+              resample_goal=ok.get("resample_goal", False), excite=ok.get("excite", False),
+              dynamics_simplification=ok.get("dynamics_simplification", False))
     kw.update(over)
     env = QuadVecEnv(n, **kw)
     env.clock = (float(g.svd_timer0), 0)

@@ -82,6 +82,10 @@ def _random_cases():
     np.random.seed(300)
     p = qr.sample_t2w_t2t(qr.sample_linearity(qr.sample_nodelay(quad_models.defaultquad_params())), 1.8, 2.5)
     cases.append(("helpers_0", p))
+    cases.append(("simplified_cf", quad_models.crazyflie_params()))
+    cases.append(("simplified_hb", quad_models.defaultquad_params()))
+    np.random.seed(400)
+    cases.append(("simplified_random", qr.sample_simplified_random_dyn()))
     return cases
 
 
@@ -93,11 +97,17 @@ def test_randomisation_reproduces_reference_draw_for_draw():
     assert [n for n, _ in cases] == [str(n) for n in rm["names"]]
     for name, params in cases:
         ref_params = json.loads(str(rm[name + "_params_json"]))
-        m = ModelConstants(params)                           # like the reference's QuadLink, fills in geom.arms.l
+        simp = name.startswith("simplified")                 # QuadLinkSimplified (inertia.py:312), dynamics_simplification=True
+        m = ModelConstants(params, dynamics_simplification=simp)   # like the reference's links, fills in derived geometry
         _assert_tree_close(_plain(params), _plain(ref_params), name)
         for key in ("mass", "inertia", "prop_pos", "thrust_max", "torque_max", "arm", "Jinv"):
             np.testing.assert_allclose(getattr(m, key), rm["%s_%s" % (name, key)], rtol=1e-12, atol=1e-18,
                                        err_msg="%s %s" % (name, key))
+        if simp:
+            om = qo.model_constants(json.loads(str(rm[name + "_params_json"])), simplified=True)
+            np.testing.assert_allclose(om["mass"], m.mass, rtol=1e-13)
+            np.testing.assert_allclose(om["inertia"], m.inertia, rtol=1e-12)
+            continue
         om = qo.model_constants(params)                      # the oracle's independent restatement agrees too
         np.testing.assert_allclose(om["mass"], m.mass, rtol=1e-13)
         np.testing.assert_allclose(om["inertia"], m.inertia, rtol=1e-12)
