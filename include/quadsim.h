@@ -14,7 +14,8 @@
  *   - plain C: pointers + sizes, no torch / C++ types.  Every function returns QS_OK (0) or a negative
  *     QsStatus; nothing throws across the ABI; the text of the last failure is qs_last_error().
  *   - every buffer is owned by the caller (normally torch tensors on the handle's device).  "real" is
- *     float for QS_F32 handles and double for QS_F64 handles.
+ *     float for QS_F32 handles and double for QS_F64 handles.  The state buffer must be 32-byte aligned, actions and
+ *     observations 16-byte aligned (cudaMalloc / torch allocations always are).
  *   - all work is enqueued on the caller's stream; the library never synchronises the device except in
  *     the *_host entry points, which are synchronous by definition.
  *   - a handle is bound to one device and is not thread-safe; use one handle per GPU.

@@ -255,6 +255,8 @@ def test_errors_without_state_or_actions():
     assert lib.qs_bind_state(h, state.data_ptr()) == _lib.QS_OK
     assert lib.qs_step(h, None, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == _lib.QS_EINVAL   # raw needs actions
     assert lib.qs_set_noise_injection(h, None, None, None) == _lib.QS_EINVAL                            # Philox handle
+    assert lib.qs_step(h, buf.data_ptr(), buf.data_ptr() + 4, buf.data_ptr(), buf.data_ptr(), None) == _lib.QS_EINVAL  # misaligned obs
+    assert b"aligned" in lib.qs_last_error(h)
     assert lib.qs_destroy(h) == _lib.QS_OK
 
 
