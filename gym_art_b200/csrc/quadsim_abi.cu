@@ -424,8 +424,9 @@ int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uin
   if (rc != QS_OK) return rc;
   if (k < 1) return fail(h, QS_EINVAL, "k must be >= 1");
   if (!obs || !rew || !done) return fail(h, QS_EINVAL, "obs/rew/done must not be NULL");
-  if (((uintptr_t)obs) % 16 != 0 || (actions && ((uintptr_t)actions) % 16 != 0))
-    return fail(h, QS_EINVAL, "actions and obs must be 16-byte aligned (vector loads / bulk stores)");
+  const uintptr_t al = h->cfg.dtype == QS_F64 ? 32 : 16;       // one 4-wide vector of `real`
+  if (((uintptr_t)obs) % al != 0 || (actions && ((uintptr_t)actions) % al != 0))
+    return fail(h, QS_EINVAL, "actions and obs must be aligned to 4 reals (16 bytes f32 / 32 bytes f64): vector loads, bulk stores");
   if (k > 1 && h->cfg.noise_mode == QS_NOISE_INJECTED) return fail(h, QS_EUNSUPPORTED, "qs_step_k with injected noise needs k == 1");
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
   if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, k, actions, obs, rew, done, (cudaStream_t)stream, 0, h->cfg.n_envs, 1);
