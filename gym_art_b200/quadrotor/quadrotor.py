@@ -17,11 +17,12 @@ import copy
 import numpy as np
 
 from .. import _lib
-from ..vec_env import QuadVecEnv, resolve_dynamics_params
+from ..vec_env import QuadVecEnv
 from . import quadrotor_randomization as quad_rand
 from .model import GRAV, ModelConstants
-from .quadrotor_control import (NonlinearPositionController, OmegaThrustControl, RawControl, ShiftedMotorControl,
-                                VelocityYawControl, VerticalControl, VertPlaneControl)
+from .quadrotor_control import (NonlinearPositionController, OmegaThrustControl, RawControl,  # noqa: F401  (re-exported:
+                                ShiftedMotorControl, VelocityYawControl, VerticalControl,    # the reference module star-imports them)
+                                VertPlaneControl)
 from .sensor_noise import SensorNoise  # noqa: F401  (re-exported like the reference module does)
 from .spaces import Box
 

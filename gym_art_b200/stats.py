@@ -3,8 +3,6 @@
 Each rank's kernel accumulates {sum of returns, sum of squared returns, finished episodes} into a device-resident
 double[3]; once per episode boundary the ranks all-reduce(SUM) those 24 bytes over NCCL (gloo in the CPU tests).
 """
-import ctypes as C
-
 import numpy as np
 
 

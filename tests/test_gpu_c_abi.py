@@ -5,7 +5,6 @@ import os
 import shutil
 import subprocess
 
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu

@@ -1,8 +1,6 @@
 """GPU: the reference-shaped facades (QuadrotorEnv, QuadrotorDynamics, controllers, quadrotor_multi.QuadrotorEnv)
 driven the way code written against gym_art drives them, checked against the fixtures recorded from the live
 reference (tests/golden/, oracle/gen_golden.py)."""
-import json
-
 import numpy as np
 import pytest
 

@@ -2,7 +2,6 @@
 oracle cannot run millions of envs): invariance to batch size / position in the batch (Philox is keyed by the global
 env id, so any window of a huge run must equal a small run over the same ids bit for bit), rotation matrices stay
 orthonormal, states stay inside the room, episode bookkeeping is exact, nothing is non-finite."""
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu

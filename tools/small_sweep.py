@@ -1,4 +1,4 @@
-import os, sys
+import sys
 sys.path.insert(0, "/root/repo")
 import torch, bench
 dev = torch.device("cuda", 0)
