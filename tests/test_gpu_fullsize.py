@@ -18,12 +18,14 @@ def _cfg(name):
         return 262144 * 8, dict(dynamics_params="DefaultQuad", controller="raw", n_agents=8, formation=ring_goals(8), **base)
     if name == "cfg5":
         return 8 << 20, dict(dynamics_params="DefaultQuad", controller="mellinger", **base)     # 64 M envs / 8 GPUs
+    if name == "cfg5_64M":
+        return 64 << 20, dict(dynamics_params="DefaultQuad", controller="mellinger", **base)    # the whole job on one GPU
     raise ValueError(name)
 
 
 def _actions(torch, n, act_dim, offset, T, cfg):
     """Actions as a pure function of (global env id, t), so a window can regenerate exactly its slice."""
-    if cfg == "cfg5":
+    if cfg.startswith("cfg5"):
         return [None] * T
     ids = torch.arange(offset, offset + n, device="cuda", dtype=torch.float64)
     out = []
@@ -36,12 +38,12 @@ def _actions(torch, n, act_dim, offset, T, cfg):
     return out
 
 
-@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "cfg5"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "cfg5", "cfg5_64M"])
 def test_full_size_run_equals_windows_and_keeps_invariants(cfg):
     import torch
     from gym_art_b200 import QuadVecEnv
     n, kw = _cfg(cfg)
-    T, W = 25, 4096
+    T, W = (25, 4096) if n < (32 << 20) else (13, 4096)      # 64 M envs: one whole 11-step episode + a reset
     env = QuadVecEnv(n, **kw)
     env.reset()
     acts = _actions(torch, n, env.act_dim, 0, T, cfg)
