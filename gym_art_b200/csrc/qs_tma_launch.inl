@@ -1,6 +1,8 @@
 // qs_tma_launch.inl - host-side launch of env_step_tma_kernel: grid sizing, one-wave vs pipelined instantiation, PDL.
 // Included by the translation units that instantiate the kernel (qs_fast.inl, qs_tma_generic.inl).
 #pragma once
+#include <stdlib.h>
+
 #include "qs_device.cuh"
 
 namespace qs {
@@ -54,7 +56,12 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
   const long long slots = (long long)sm_count() * per_sm;
   // one wave: one tile per CTA.  The kernel needs only the observation tile, but it is given the full allocation so
   // that at most per_sm CTAs share an SM: the launch is latency-bound and its time is set by the fullest SM.
-  if (tiles <= slots) return launch_tma_w<T, true>(p, st, (unsigned)tiles, smem);
+  // Up to ~1.8 x slots tiles the one-tile-per-CTA kernel still wins (measured, tools/mid_sweep.py: 9.4 vs 10.6 us at
+  // 81,920 envs, 12.0 vs 12.5 at 131,072, 14.4 vs 13.9 at 163,840): the excess CTAs start as residents retire - a natural
+  // partial second wave - while the persistent pipeline would run 1-2 tiles per CTA with nothing to overlap.
+  static double factor = -1.0;
+  if (factor < 0.0) { const char* e = getenv("QUADSIM_ONEWAVE_FACTOR"); factor = e ? atof(e) : 1.8; }
+  if ((double)tiles <= factor * (double)slots) return launch_tma_w<T, true>(p, st, (unsigned)tiles, smem);
   return launch_tma_w<T, false>(p, st, (unsigned)slots, smem);                        // persistent CTAs, tile ring
 }
 

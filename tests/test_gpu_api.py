@@ -351,8 +351,8 @@ def test_per_env_models_fast_kernel_fp32(ctrl, oc):
     from gym_art_b200 import QuadVecEnv
     from oracle import quadsim_oracle as qo
     zoo = [z for i, z in enumerate(_model_zoo()) if i != 4]      # the drag/linearity model belongs to the generic kernel
-    K, per, T = len(zoo), 15400, 12
-    n = K * per                                                   # 77,000 envs > 148 x 4 resident tiles of 128
+    K, per, T = len(zoo), 28000, 10
+    n = K * per                                                   # 140,000 envs: enough tiles for the persistent pipeline
     index = np.arange(n) % K
     rng = np.random.RandomState(9)
     kw = dict(sim_steps=2, ep_time=5, sense_noise="default")

@@ -76,7 +76,7 @@ def test_two_rank_nccl_job_equals_single_gpu_job(tmp_path):
 def test_two_handles_on_two_devices_in_one_process():
     import torch
     from gym_art_b200 import QuadVecEnv
-    n = 80000                                                     # pipelined instantiation on both devices
+    n = 150000                                                    # pipelined instantiation on both devices
     envs = [QuadVecEnv(n, device="cuda:%d" % k, seed=3) for k in range(2)]
     outs = []
     for k, e in enumerate(envs):

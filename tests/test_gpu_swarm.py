@@ -94,7 +94,7 @@ def test_swarm_step_matches_oracle_fp32_per_step():
 def test_swarm_fast_kernel_matches_oracle_fp32(M):
     """The specialised swarm variant of the TMA kernel (formation goals, no info buffer), per-step against the oracle;
     E is large enough for the multi-tile (mbarrier pipeline) path of the persistent kernel."""
-    E, T = (148 * 4 * 128 * 2) // M + 3, 40
+    E, T = (148 * 4 * 128 * 2) // M + 3, 30
     rng = np.random.RandomState(13 + M)
     oe, env = _pair(E, M, "float32", 3, info=False, formation=True, ep_time=5)
     n = E * M

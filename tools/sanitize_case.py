@@ -11,7 +11,7 @@ from gym_art_b200 import QuadVecEnv  # noqa: E402
 from gym_art_b200.quadrotor import quad_models  # noqa: E402
 from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals  # noqa: E402
 
-big = 148 * 4 * 128 + 3 * 128 + 17          # more tiles than resident CTA slots, ragged tail
+big = 2 * 148 * 4 * 128 + 3 * 128 + 17      # enough tiles for the persistent pipeline, ragged tail
 for n, kw in ((big, dict(controller="raw")), (1000 + 5, dict(controller="omega_thrust", sense_noise="default", init_random_state=True)),
               (big - 17 + 8, dict(controller="raw", n_agents=8, formation=ring_goals(8, 0.3), collision_k=2.0)),
               (517, dict(controller="mellinger", obs_repr="xyz_vxyz_R_omega_acc_act", sense_noise="default")),
