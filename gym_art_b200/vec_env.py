@@ -541,8 +541,13 @@ class QuadVecEnv(object):
     def state_dict(self):
         """Checkpoint: the state tensor plus the global clocks (SURVEY.md section 5 "Checkpoint / resume")."""
         t, s = self.clock
-        return {"state": self.state.clone(), "svd_timer": t, "step_count": s}
+        d = {"state": self.state.clone(), "svd_timer": t, "step_count": s}
+        if self.models is not None:                       # per-env dynamics: the model constants are part of the state
+            d["models"] = self.models.clone()
+        return d
 
     def load_state_dict(self, d):
         self.state.copy_(d["state"])
         self.clock = (d["svd_timer"], d["step_count"])
+        if "models" in d and self.models is not None:
+            self.models.copy_(d["models"])
