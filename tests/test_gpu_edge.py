@@ -68,3 +68,38 @@ def test_masked_reset_extremes():
     env.reset(torch.ones(n, dtype=torch.bool, device="cuda"))                # everybody == reset()
     assert bool((env.tick == 0).all()) and not torch.equal(env.state, before)
     env.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 3e-5)])
+def test_vertplane_2d_env_matches_oracle(dtype, tol):
+    """dim_mode='2D' (VertPlaneControl, two-wide actions, spawn in the x-z plane): the reference env cannot run this
+    mode end to end, the oracle pins the controller on the live reference; here the CUDA env
+    step against the oracle's env step."""
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    n = 333
+    params = quad_models.defaultquad_params()
+    rng = np.random.RandomState(8)
+    kw = dict(dim_mode="2D", ep_time=0.15, sense_noise="default", obs_repr="xyz_vxyz_R_omega_h")
+    oe = qo.OracleVecEnv(params, n, controller=qo.CTRL_VERTPLANE, auto_reset=True, **kw)
+    env = QuadVecEnv(n, dynamics_params=params, dtype=dtype, noise_mode="injected", auto_reset=True, **kw)
+    assert env.controller_name == "vertplane" and env.act_dim == 2
+    rz = rng.uniform(-1, 1, (n, qo.RESET_Z))
+    env.set_noise(reset_z=rz)
+    np.testing.assert_allclose(env.reset().double().cpu().numpy(), oe.reset(reset_z=rz), rtol=0, atol=tol)
+    assert float(env.pos[:, 1].abs().max()) == 0.0                   # y = goal.y in 2D (quadrotor.py:1091-1092)
+    for t in range(40):
+        if dtype == "float32":
+            for f, of in (("pos", "pos"), ("vel", "vel"), ("rot", "rot"), ("omega", "omega"), ("thrust_rot_damp", "rot_damp"),
+                          ("thrust_cmds_damp", "cmds_damp"), ("ou_state", "ou")):
+                setattr(oe, of, env.get_field(f).double().cpu().numpy())
+        cast = (lambda x: x.astype(np.float32).astype(np.float64)) if dtype == "float32" else (lambda x: x)
+        a = cast(rng.uniform(-1, 1, (n, 2)))
+        ou_z, obs_z, rz = cast(rng.standard_normal((n, 2, 4))), cast(rng.standard_normal((n, qo.OBS_Z))), cast(rng.uniform(-1, 1, (n, qo.RESET_Z)))
+        env.set_noise(ou_z=ou_z, obs_z=obs_z, reset_z=rz)
+        o, r, d = env.step(a)
+        oo, ro, do = oe.step(a, ou_z=ou_z, obs_z=obs_z, reset_z=rz)
+        assert np.array_equal(d.cpu().numpy(), do)
+        err = np.max(np.abs(o.double().cpu().numpy() - oo) / np.maximum(np.abs(oo), 1.0))
+        assert err < tol and np.max(np.abs(r.double().cpu().numpy() - ro)) < tol, (t, err)
+    env.close()
