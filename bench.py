@@ -261,9 +261,6 @@ def run_ours(args):
     torch.cuda.set_device(device)
     numa = bind_to_gpu_numa_node(torch, local) if multi else None
     if multi:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     hbm_peak, peak_src = load_peaks()
     K, W = args.steps, max(args.warmup, 3)
@@ -434,7 +431,7 @@ def run_ours(args):
             "clocks": clocks,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if multi:
         dist.barrier()
         dist.destroy_process_group()
@@ -458,7 +455,28 @@ def run_reference(args):
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = [None]
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner, for one) is sent to
+    stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes the line to the real stdout."""
+    sys.stdout.flush()
+    _REAL_STDOUT[0] = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT[0] is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT[0], data)
 
 
 def main():
@@ -471,6 +489,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
