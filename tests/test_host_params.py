@@ -150,3 +150,26 @@ def test_absolute_sampler_ranges():
     p = qr.AbsoluteSampler(base, noise, sampler="uniform").sample(copy.deepcopy(base))
     assert 0.9 * 1.9 - 1e-9 <= p["motor"]["thrust_to_weight"] <= 1.1 * 1.9 + 1e-9
     assert p["motor"]["thrust_to_weight"] != base["motor"]["thrust_to_weight"]
+
+
+def test_batched_model_pipeline_equals_the_scalar_one():
+    """K random quadrotors through the vectorised sampler -> link model -> derived constants: every column of the
+    [14, K, 4] table equals what the scalar pipeline (the one pinned on the reference) makes of the same parameters."""
+    import time
+    from gym_art_b200.quadrotor import batched_models as bm
+    rng = np.random.RandomState(3)
+    K, dt = 64, 0.005
+    b = bm.sample_randomquad_batch(K, rng)
+    rows = bm.model_rows_batch(b, dt)
+    assert rows.shape == (14, K, 4)
+    for k in range(K):
+        want = ModelConstants(bm.params_of(b, k)).rows(dt)
+        np.testing.assert_allclose(rows[:, k, :], want, rtol=1e-10, atol=1e-18, err_msg="model %d" % k)
+    # same laws as randomquad_parameters (moments), and fast enough for one model per env
+    big = bm.sample_randomquad_batch(20000, np.random.RandomState(4))
+    t2w = big["thrust_to_weight"]
+    assert abs(t2w.mean() - 2.5) < 0.02 and 1.5 <= t2w.min() and t2w.max() <= 3.5
+    assert abs(big["geom"]["motor_xyz"][:, 0].mean() - 0.0625) < 0.001
+    t0 = time.perf_counter()
+    r = bm.model_rows_batch(big, dt)
+    assert time.perf_counter() - t0 < 5.0 and np.isfinite(r).all() and (r[5, :, 3] > 0).all()
