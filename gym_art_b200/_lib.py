@@ -28,7 +28,7 @@ STATUS_NAMES = {QS_EINVAL: "QS_EINVAL", QS_ECUDA: "QS_ECUDA", QS_ENONFINITE: "QS
                 QS_EUNSUPPORTED: "QS_EUNSUPPORTED", QS_EABI: "QS_EABI"}
 
 # every symbol include/quadsim.h declares (tests/test_abi.py checks the library exports each one)
-EXPORTS = ["qs_abi_version", "qs_state_layout", "qs_create", "qs_destroy", "qs_last_error", "qs_bind_state", "qs_bind_models", "qs_bind_info",
+EXPORTS = ["qs_abi_version", "qs_state_layout", "qs_create", "qs_destroy", "qs_last_error", "qs_bind_state", "qs_bind_models", "qs_bind_terminal_obs", "qs_bind_info",
            "qs_set_noise_injection", "qs_set_goal_injection", "qs_reset", "qs_observe", "qs_step", "qs_step_k", "qs_dynamics_step", "qs_step_host", "qs_get_stats",
            "qs_stats_device_ptr", "qs_check", "qs_get_clock", "qs_set_clock", "qs_launch_count", "qs_last_variant", "qs_last_host_path"]
 
@@ -102,6 +102,7 @@ def load():
         "qs_last_error": (C.c_char_p, [H]),
         "qs_bind_state": (C.c_int, [H, P]),
         "qs_bind_info": (C.c_int, [H, P]),
+        "qs_bind_terminal_obs": (C.c_int, [H, P]),
         "qs_bind_models": (C.c_int, [H, P]),
         "qs_set_noise_injection": (C.c_int, [H, P, P, P]),
         "qs_set_goal_injection": (C.c_int, [H, P]),

@@ -41,6 +41,7 @@ struct Params {
   R* rew;                   // [n]
   uint8_t* done;            // [n]
   R* info;                  // [n][INFO_DIM] or null
+  R* term_obs;              // [n][obs_dim] or null: observation of the terminal state of envs that auto-reset this step
   const R* models;          // per-env model constants [MODEL_ROWS][n][4] or null (quadsim.h "Per-env model buffer")
   const uint8_t* reset_mask;
   const R* ou_z;            // injected: [n][sim_steps][4]
@@ -1277,10 +1278,12 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----
     const bool walk = T::RARE && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
     const bool resetting = done && p.auto_reset;
-    if ((last && !resetting) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o, (PRE && sense) ? dr.zobs : nullptr);
+    const bool want_term = resetting && p.term_obs != nullptr;          // the obs the reference returns on its done step (:988)
+    if ((last && (!resetting || want_term)) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o, (PRE && sense) ? dr.zobs : nullptr);
     if (done) {
       if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
       if (resetting) {
+        if (want_term && last && active) obs_to_tile<R, T::PLAIN>(p, o, p.term_obs + i * (T::PLAIN ? 18 : p.obs_dim));
         reset_env<R, T>(s, p, ns);
         if (last || walk) build_obs<R, T>(s, p, ns, true, s.pa, o);     // :1143 (actions[1] = 0 after reset)
       }

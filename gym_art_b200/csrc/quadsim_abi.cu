@@ -27,6 +27,7 @@ struct QsHandle {
   QsStateLayout lay;
   void* state;
   void* info;
+  void* term_obs;
   const void* models;
   const void* ou_z;
   const void* obs_z;
@@ -148,6 +149,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.state = (R*)h->state;
   p.info = (R*)h->info;
   p.models = (const R*)h->models;
+  p.term_obs = (R*)h->term_obs;
   p.ou_z = (const R*)h->ou_z;
   p.obs_z = (const R*)h->obs_z;
   p.reset_z = (const R*)h->reset_z;
@@ -290,6 +292,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   layout_of(cfg, &h->lay);
   h->state = h->info = nullptr;
   h->models = nullptr;
+  h->term_obs = nullptr;
   h->ou_z = h->obs_z = h->reset_z = nullptr;
   h->goal_z = nullptr;
   h->d_stats = nullptr; h->d_status = nullptr; h->d_clock = nullptr; h->d_ticket = nullptr;
@@ -356,6 +359,12 @@ int qs_bind_models(QsHandle* h, const void* models) {
   if (!models) return fail(h, QS_EINVAL, "models is NULL");
   if (((uintptr_t)models) % 32 != 0) return fail(h, QS_EINVAL, "models must be 32-byte aligned");
   h->models = models;
+  return QS_OK;
+}
+
+int qs_bind_terminal_obs(QsHandle* h, void* terminal_obs) {
+  if (!h) return QS_EINVAL;
+  h->term_obs = terminal_obs;
   return QS_OK;
 }
 

@@ -154,7 +154,7 @@ class QuadVecEnv(object):
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
                  max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None,
-                 host_mapped=False, resample_goal=False, excite=False, dynamics_simplification=False):
+                 host_mapped=False, resample_goal=False, excite=False, dynamics_simplification=False, terminal_obs=False):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -220,6 +220,12 @@ class QuadVecEnv(object):
         _lib.check(self.lib.qs_bind_state(self._h, self.state.data_ptr()), self._h)
         if info:
             _lib.check(self.lib.qs_bind_info(self._h, self.info.data_ptr()), self._h)
+        # auto-reset hides the terminal state behind the next episode's first observation; terminal_obs=True keeps the
+        # observation the reference's step() returns on its done step (rows of envs with done=1 are valid)
+        self.terminal_obs = None
+        if terminal_obs:
+            self.terminal_obs = self._alloc((N, self.obs_dim), self.tdtype)
+            _lib.check(self.lib.qs_bind_terminal_obs(self._h, self.terminal_obs.data_ptr()), self._h)
         self._noise_refs = None
         # spaces of ONE env, as the reference's controller / env report them (quadrotor.py:890, :898-936)
         from .quadrotor.spaces import Box

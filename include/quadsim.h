@@ -233,6 +233,11 @@ int qs_bind_state(QsHandle* h, void* state);
 /* QsConfig.per_env_model handles: device buffer real[QS_MODEL_ROWS][n_envs][4]; may be re-bound or rewritten between
  * steps (the reference resamples dynamics between episodes); the library never frees it */
 int qs_bind_models(QsHandle* h, const void* models);
+/* optional (auto_reset handles): real[n_envs][obs_dim].  A step that ends an env's episode returns the FIRST observation
+ * of the next episode in `obs`; the observation of the terminal state - what the reference's step() returns on its done
+ * step (quadrotor.py:988) - is written to this buffer, rows of envs that did not finish are left untouched.
+ * NULL to disable. */
+int qs_bind_terminal_obs(QsHandle* h, void* terminal_obs);
 /* optional diagnostics buffer real[n_envs][QS_INFO_DIM] (NULL to disable) */
 int qs_bind_info(QsHandle* h, void* info);
 /* QS_NOISE_INJECTED: device buffers of unit draws consumed by the next reset/step calls (any may be NULL = zeros) */

@@ -239,6 +239,38 @@ def test_auto_reset_equals_explicit_reset_fp64():
     assert st[2] == 5 * n
 
 
+@pytest.mark.parametrize("name,dtype,tol", [("mq_raw_simsteps4", "float64", 2e-10), ("cf_raw_noise_rnd", "float64", 2e-9),
+                                            ("hb_raw_nonoise", "float32", 5e-3)])
+def test_terminal_observation_is_the_reference_done_step_obs(name, dtype, tol):
+    """With auto-reset the step returns the next episode's first observation; the terminal_obs buffer keeps what the
+    reference's step() returns on its done step (quadrotor.py:988) for exactly the envs that finished."""
+    g = Golden(name)
+    n = 3
+    env = make_env(g, n, dtype, auto_reset=True, terminal_obs=True)
+    env.set_noise(reset_z=tile(g.reset_z[0], n), goal_z=tile(g.reset_goal_z[0], n))
+    env.reset()
+    sentinel = 12345.0
+    seen = 0
+    for t in range(g.T):
+        rz = gz = None
+        if g.done[t]:
+            k = g.reset_index_after(t)
+            rz, gz = tile(g.reset_z[k], n), tile(g.reset_goal_z[k], n)
+        env.terminal_obs.fill_(sentinel)
+        env.set_noise(ou_z=tile(g.ou_z[t], n), obs_z=tile(g.obs_z[t], n), reset_z=rz, goal_z=gz if gz is not None else tile(g.goal_z[t], n))
+        o, r, d = env.step(tile(g.actions[t][:env.act_dim], n))
+        term = env.terminal_obs.double().cpu().numpy()
+        if g.done[t]:
+            seen += 1
+            assert np.max(np.abs(term - g.obs[t]) / np.maximum(np.abs(g.obs[t]), 1.0)) < tol, t
+            want = g.reset_obs[g.reset_index_after(t)]
+            assert np.max(np.abs(o.double().cpu().numpy() - want) / np.maximum(np.abs(want), 1.0)) < max(tol, 1e-9)
+        else:
+            assert np.all(term == sentinel)
+    assert seen >= 1
+    env.close()
+
+
 def test_batched_oracle_parity_ragged_n():
     """Many distinct envs (N not a multiple of the CTA size) against the batched oracle, fp64, injected noise,
     auto-reset, sensor noise, random init: every env has its own actions and draws."""
