@@ -209,8 +209,9 @@ typedef struct QsConfig {
  *   row 0: pos.xyz, vel.x        row 1: vel.yz, omega.xy      row 2: omega.z, R00 R01 R02
  *   row 3: R10 R11 R12 R20       row 4: R21 R22, tick, ep_return
  *   row 5: thrust_rot_damp[4]    row 6: thrust_cmds_damp[4]
- *   optional rows (index or -1): OU state (iff ou_sigma > 0), previous action (iff needed by obs/reward),
- *   gyro bias (iff gyro_norm_std != 0), goal (iff per_env_goal). */
+ *   optional rows (index or -1): OU state (iff ou_sigma > 0 or per_env_model), previous action (iff the observation
+ *   contains `act` or the action_change reward coefficient is non-zero), gyro bias (iff gyro_norm_std != 0),
+ *   goal (iff per_env_goal, resample_goal or excite). */
 typedef struct QsStateLayout {
   int32_t rows;
   int32_t row_ou, row_prev_action, row_gyro_bias, row_goal;
