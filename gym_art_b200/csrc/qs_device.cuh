@@ -49,6 +49,7 @@ struct Params {
   const R* reset_z;         // injected: [n][RESET_Z]
   const R* goal_z;          // injected: [n][4] moving-goal draws (excite xyz, resample_goal z)
   const R* acc_in;          // qs_observe: clean accelerometer readings [n][3] or null
+  unsigned long long* timing;   // QS_PHASE_TIMING experiment builds only
   double* stats;            // [3]
   int* status;              // sticky non-finite flag
   long long n;              // envs on the handle = row stride of the state buffer
@@ -1454,6 +1455,11 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   pdl_launch_dependents();                       // the next launch may start its prologue; it waits below for our completion
   pdl_wait();                                    // everything before this line touched no global memory
 
+#ifdef QS_PHASE_TIMING
+  // experiment build (tools/phase_timing.py): %globaltimer stamps of one lane per warp into the info buffer
+  unsigned long long ts0, ts1 = 0, ts2 = 0, ts3 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0) :: "memory");
+#endif
   const double svd_t0 = p.clock->svd_timer;
   const unsigned long long step0 = p.clock->step;
   double svd_end = svd_t0;
@@ -1550,10 +1556,16 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       }
     }
 
+#ifdef QS_PHASE_TIMING
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1) : "f"(s.px + s.r[8] + a0[0] + s.cd[3]) : "memory");   // data arrived
+#endif
     R o[26];
     StepOut<R> out;
     run_steps<R, T>(s, p, i, active, has_act ? a0 : nullptr, svd_t0, step0, o, out, &pre);
     svd_end = out.svd_t;
+#ifdef QS_PHASE_TIMING
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2) : "f"(o[0] + o[17] + out.rew_sum + s.vz) : "memory");   // computed
+#endif
 
     if (active) {
       store_state<R, T>(s, p, i);
@@ -1581,6 +1593,15 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
           for (int k = lane; k < total; k += 32) dst[k] = wtile[k];
         }
       }
+#ifdef QS_PHASE_TIMING
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts3) :: "memory");                                            // stores issued
+      if (lane == 0 && p.timing != nullptr) {
+        unsigned int smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* rec = p.timing + ((long long)blockIdx.x * WARPS + warp) * 5;
+        rec[0] = ts0; rec[1] = ts1; rec[2] = ts2; rec[3] = ts3; rec[4] = smid;
+      }
+#endif
       if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
       // (the clock was read at the top of every thread, and run_steps depended on the values: no fence needed here)
       if (lane == 0) {

@@ -150,6 +150,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.info = (R*)h->info;
   p.models = (const R*)h->models;
   p.term_obs = (R*)h->term_obs;
+  { const char* e = getenv("QUADSIM_TIMING_PTR"); p.timing = e ? (unsigned long long*)strtoull(e, nullptr, 0) : nullptr; }
   p.ou_z = (const R*)h->ou_z;
   p.obs_z = (const R*)h->obs_z;
   p.reset_z = (const R*)h->reset_z;
