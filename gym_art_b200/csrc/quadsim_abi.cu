@@ -47,6 +47,7 @@ struct QsHandle {
   bool host_ready;
   int host_zero_copy;        // A/B knob QUADSIM_HOST_ZEROCOPY (default 1)
   int tma_generic;           // A/B knob QUADSIM_TMA_GENERIC (default 1)
+  unsigned long long* timing;   // QUADSIM_TIMING_PTR: stamp buffer of QS_PHASE_TIMING experiment builds (else unused)
   cudaStream_t zc_stream;
   const char* last_host_path;
   void *h_act, *h_obs, *h_rew;
@@ -150,7 +151,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.info = (R*)h->info;
   p.models = (const R*)h->models;
   p.term_obs = (R*)h->term_obs;
-  { const char* e = getenv("QUADSIM_TIMING_PTR"); p.timing = e ? (unsigned long long*)strtoull(e, nullptr, 0) : nullptr; }
+  p.timing = h->timing;
   p.ou_z = (const R*)h->ou_z;
   p.obs_z = (const R*)h->obs_z;
   p.reset_z = (const R*)h->reset_z;
@@ -303,6 +304,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->host_ready = false;
   { const char* e = getenv("QUADSIM_HOST_ZEROCOPY"); h->host_zero_copy = e ? atoi(e) : 1; }
   { const char* e = getenv("QUADSIM_TMA_GENERIC"); h->tma_generic = e ? atoi(e) : 1; }
+  { const char* e = getenv("QUADSIM_TIMING_PTR"); h->timing = e ? (unsigned long long*)strtoull(e, nullptr, 0) : nullptr; }
   h->zc_stream = nullptr;
   h->last_host_path = "";
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
