@@ -374,6 +374,31 @@ def run_ours(args):
                                "note": "qs_step_k: HBM is touched once per K env steps, so the per-step HBM roofline does not apply"}
     e.close()
     del e
+    # context only: 16 INDEPENDENT 65,536-env groups stepped concurrently on their own streams (QuadVecEnvGroup) - one
+    # group's loads run under another's compute and stores, which a single dependent stream of launches cannot do
+    from gym_art_b200.groups import QuadVecEnvGroup
+    grp = QuadVecEnvGroup(16, N_BATCH, device=str(device), dynamics_params="DefaultQuad", controller="raw", ep_time=EP_TIME,
+                          seed=5, env_id_offset=rank * 16 * N_BATCH)
+    grp.reset()
+    g_acts = [torch.rand((N_BATCH, 4), device=device, generator=gen) * 2 - 1 for _ in range(16)]
+    gg = grp.capture_steps(200, g_acts)
+    gg.replay()
+    torch.cuda.synchronize(device)
+    if multi:
+        dist.barrier()
+    ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ge0.record(); gg.replay(); ge1.record()
+    torch.cuda.synchronize(device)
+    tg = torch.tensor([ge0.elapsed_time(ge1)], device=device, dtype=torch.float64)
+    if multi:
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    ms_g = float(tg.item())
+    others["cfg2_16_independent_groups_concurrent"] = {
+        "n_envs_per_gpu_step": N_BATCH, "groups": 16, "value": world * 16 * 200 * N_BATCH / (ms_g * 1e-3), "unit": "env-steps/s",
+        "us_per_group_step": ms_g * 1e3 / (16 * 200), "roofline_frac": 16 * 200 * N_BATCH * BYTES_PER_ENV_STEP / (ms_g * 1e-3) / 1e9 / hbm_peak,
+        "note": "NOT the headline workload: 16 batches with no dependence between them, one stream each"}
+    grp.close()
+    del grp, g_acts, gg
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through qs_step_host -------------------------------------------------------------------
