@@ -10,7 +10,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QUADSIM_LIB") or os.path.join(HERE, "libquadsim.so")   # override: A/B builds only
 
-QS_ABI_VERSION = 6
+QS_ABI_VERSION = 7
+QS_MODELS_PLAIN = 1
 QS_OK, QS_EINVAL, QS_ECUDA, QS_ENONFINITE, QS_ESTATE, QS_EUNSUPPORTED, QS_EABI = 0, -1, -2, -3, -4, -5, -6
 QS_F32, QS_F64 = 0, 1
 (QS_CTRL_RAW, QS_CTRL_VERTICAL, QS_CTRL_VERTPLANE, QS_CTRL_SHIFTED, QS_CTRL_OMEGA_THRUST, QS_CTRL_VELOCITY_YAW,
@@ -103,7 +104,7 @@ def load():
         "qs_bind_state": (C.c_int, [H, P]),
         "qs_bind_info": (C.c_int, [H, P]),
         "qs_bind_terminal_obs": (C.c_int, [H, P]),
-        "qs_bind_models": (C.c_int, [H, P]),
+        "qs_bind_models": (C.c_int, [H, P, C.c_int32]),
         "qs_set_noise_injection": (C.c_int, [H, P, P, P]),
         "qs_set_goal_injection": (C.c_int, [H, P]),
         "qs_reset": (C.c_int, [H, P, P, P]),
@@ -111,7 +112,7 @@ def load():
         "qs_step": (C.c_int, [H, P, P, P, P, P]),
         "qs_step_k": (C.c_int, [H, C.c_int, P, P, P, P, P]),
         "qs_dynamics_step": (C.c_int, [H, C.c_int, P, C.c_int, P]),
-        "qs_step_host": (C.c_int, [H, P, P, P, P]),
+        "qs_step_host": (C.c_int, [H, P, P, P, P, P]),
         "qs_get_stats": (C.c_int, [H, C.POINTER(C.c_double * 3), C.c_int, P]),
         "qs_stats_device_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),
         "qs_check": (C.c_int, [H, P]),

@@ -77,6 +77,9 @@ struct Params {
   int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
   long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
   int pdl;                            // step kernel launched with programmatic dependent launch (see env_step_tma_kernel)
+  int ow_threads;                     // threads per CTA of a one-wave launch (32, 64 or 128)
+  int prefetch;                       // L2 prefetch of the CTA's first tile ahead of griddepcontrol.wait: 0 off, 1 bulk, 3 lines
+  int spec_draw;                      // draw the step's noise ahead of griddepcontrol.wait from a speculative clock read
   // model
   R dt;
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
@@ -1383,6 +1386,38 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+// hint only: pulls [src, src + bytes) into L2.  Legal ahead of griddepcontrol.wait - L2 is the point of coherence, so a
+// line the previous grid is still writing can never be observed stale through it.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+// One 128-byte line per thread and trip over the rows of one tile of a structure-of-arrays state buffer (+ its action
+// row): pulls the tile into L2.  Pure hint (see bulk_prefetch_l2).  cta_envs is 32, 64 or 128: a tile row is cta_envs / 8
+// lines, so thread t always owns line (t mod lines-per-row) of rows t / lines-per-row, + cta_envs / lines-per-row = 8, ...
+__device__ __forceinline__ void prefetch_tile_lines(const char* state_row0, long long row_bytes, int n_rows, const char* actions,
+                                                    int rows, int tid, int cta_envs) {
+  const int sh = (cta_envs == 128) ? 4 : (cta_envs == 64 ? 3 : 2);      // log2(lines per row)
+  const int e8 = (tid & ((1 << sh) - 1)) << 3;                           // first env of this thread's line
+  if (e8 >= rows) return;
+  const char* src = state_row0 + (long long)(tid >> sh) * row_bytes + (e8 << 4);
+  for (int r = tid >> sh; r < n_rows; r += 8) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(src) : "memory");
+    src += 8 * row_bytes;
+  }
+  if (actions != nullptr && (tid >> sh) == (n_rows & 7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + (e8 << 4)) : "memory");
+}
+// clock reads that may race with the previous grid (speculative, ahead of the wait) or follow such a read (after the
+// wait): always served by L2, never by a line L1 picked up earlier
+__device__ __forceinline__ unsigned long long ld_clock_step(const Clock* c) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(&c->step) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_clock_svd(const Clock* c) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(&c->svd_timer) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -1435,6 +1470,9 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   __shared__ long long tile_slot[2];                                     // tile held by each stage (-1: none)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // a one-wave launch may use smaller CTAs (p.ow_threads = 64): 2-warp granularity spreads the warps evenly over the SMs
+  const int cta_envs = ONEWAVE ? (int)blockDim.x : BLOCK;
+  const int cta_warps = cta_envs >> 5;
   const int rows_in = p.tma_rows;                                        // state rows in the buffer (7 + OU + prev action)
   const bool has_act = p.actions != nullptr && p.act_dim == 4;          // (1- and 2-wide actions are read by run_steps itself)
   const int stage_vecs = (rows_in + 1) * BLOCK;                          // float4 slots per stage, last row = actions
@@ -1443,25 +1481,76 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   float4* in = reinterpret_cast<float4*>(smem_raw);
   // (a one-wave launch allocates only the observation tile)
   float* obs_tiles = reinterpret_cast<float*>(smem_raw + (ONEWAVE ? (size_t)0 : (size_t)2 * stage_vecs * sizeof(float4)));
-  const long long n_tiles = (p.end - p.begin + BLOCK - 1) / BLOCK;
+  const long long n_tiles = (p.end - p.begin + cta_envs - 1) / cta_envs;
   const long long G = gridDim.x;
   constexpr bool multi = !ONEWAVE;                                       // more tiles than resident CTAs
 
-  __shared__ unsigned int warps_done;
+  __shared__ unsigned int warps_read;
   if (!multi) {
-    if (tid == 0) warps_done = 0u;
+    if (tid == 0) warps_read = 0u;
     __syncthreads();
   }
+#ifdef QS_PHASE_TIMING
+  unsigned long long ts_a;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_a) :: "memory");
+#endif
   pdl_launch_dependents();                       // the next launch may start its prologue; it waits below for our completion
-  pdl_wait();                                    // everything before this line touched no global memory
+
+  // ---- ahead of the wait: nothing here depends on what the previous grid is still writing ------------------------------
+  // (1) L2 prefetch of this CTA's first tile: the CTA is resident well before the previous grid completes (it took the
+  //     slot of a CTA that retired), and the previous grid is in its compute / store phase with DRAM idle; this grid's
+  //     loads then find their lines in L2 or already on their way.  A hint only: coherent whatever the previous grid
+  //     still writes.
+  if (p.prefetch > 0) {
+    const long long first = p.begin + (long long)blockIdx.x * cta_envs;
+    long long rows = p.end - first;
+    if (rows > cta_envs) rows = cta_envs;
+    if (p.prefetch == 1) {                                               // one bulk prefetch per row, issued by thread 0
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)rows * 16u;
+        const char* src = reinterpret_cast<const char*>(p.state + first * 4);
+        for (int r = 0; r < rows_in; ++r) { bulk_prefetch_l2(src, bytes); src += p.row_bytes; }
+        if (has_act) bulk_prefetch_l2(p.actions + first * 4, bytes);
+      }
+    } else {                                                             // one line per thread and trip (measured best)
+      prefetch_tile_lines(reinterpret_cast<const char*>(p.state + first * 4), p.row_bytes, rows_in,
+                          has_act ? reinterpret_cast<const char*>(p.actions + first * 4) : nullptr, (int)rows, tid, cta_envs);
+    }
+  }
+  // (2) the draws of the step depend on (env id, step index) alone.  The step index lives in device memory (CUDA-graph
+  //     replays must see it advance); the previous launch of this handle advanced it EARLY in its run (see below), so
+  //     a read here almost always returns the final value: draw from it now, check it after the wait, redraw if it
+  //     moved (same code, second trip of the loop - results cannot depend on which trip produced them).
+  constexpr bool PREDRAW = T::SIM > 0 && T::PLAIN;
+  const long long i_first = p.begin + (long long)blockIdx.x * cta_envs + tid;
+  Pre<R, T> pre;
+  unsigned long long step0 = 0ull;
+  double svd_t0 = 0.0;
+  {
+    const bool spec = ONEWAVE && PREDRAW && p.spec_draw != 0;
+    unsigned long long drawn_for = ~0ull;
+#pragma unroll 1
+    for (int trip = spec ? 0 : 1; trip < 2; ++trip) {
+      unsigned long long s_now;
+      if (trip == 0) {
+        s_now = ld_clock_step(p.clock);
+      } else {
+        pdl_wait();                              // everything above touched global memory only as a hint / a guess
+        s_now = ld_clock_step(p.clock);
+        svd_t0 = ld_clock_svd(p.clock);
+        step0 = s_now;
+        if (!(ONEWAVE && PREDRAW) || s_now == drawn_for) break;
+      }
+      predraw<R, T>(p, i_first, i_first < p.end, s_now, pre);
+      drawn_for = s_now;
+    }
+  }
 
 #ifdef QS_PHASE_TIMING
   // experiment build (tools/phase_timing.py): %globaltimer stamps of one lane per warp into the info buffer
   unsigned long long ts0, ts1 = 0, ts2 = 0, ts3 = 0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0) :: "memory");
 #endif
-  const double svd_t0 = p.clock->svd_timer;
-  const unsigned long long step0 = p.clock->step;
   double svd_end = svd_t0;
 
   auto issue_load = [&](long long tile, int stage) {
@@ -1501,7 +1590,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   long long tile = blockIdx.x;
   while (tile >= 0) {
     const int stage = j & 1;
-    const long long block_first = p.begin + tile * BLOCK;
+    const long long block_first = p.begin + tile * cta_envs;
     const long long i = block_first + tid;
     const bool active = i < p.end;
 
@@ -1523,8 +1612,18 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       if (has_act) cp_async16(buf + rows_in * BLOCK, p.actions + il * 4);
       cp_async_commit();
     }
-    Pre<R, T> pre;
-    if (T::SIM > 0 && T::PLAIN) predraw<R, T>(p, i, active, step0, pre);
+    if (PREDRAW && !ONEWAVE) predraw<R, T>(p, i, active, step0, pre);
+    unsigned int ticket = 0u;
+    if (ONEWAVE) {
+      // Early clock advance: every warp has read the clock by now (its draws depended on the value); the last CTA of
+      // the grid to say so advances it - long before the grid ends, so the next launch's speculative read sees the final
+      // value, and the end of this grid is its last store rather than an atomic round trip followed by a dependent
+      // store.  The ticket comes back while the state loads are in flight; it is looked at after the step is computed.
+      // (the increment is made to depend on the two values read, so the reads have completed before it is issued)
+      const unsigned int one = 1u + (unsigned int)(step0 >> 63) + (unsigned int)((unsigned long long)__double_as_longlong(svd_t0) >> 63);
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&warps_read, one) == (unsigned)cta_warps - 1u) ticket = atomicAdd(p.launch_ticket, 1u) + 1u;
+    }
     if (multi) {
       if (j == 0) {
         cp_async_wait_all();                                             // a thread reads back only what it copied itself
@@ -1567,6 +1666,13 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2) : "f"(o[0] + o[17] + out.rew_sum + s.vz) : "memory");   // computed
 #endif
 
+    if (!multi) {
+      // (the clock was read by every warp of every CTA before the last ticket was taken: nobody can see the update)
+      if (ticket == (unsigned)gridDim.x) {
+        *p.launch_ticket = 0u;
+        if (p.clock_advance) { p.clock->svd_timer = out.svd_t; p.clock->step = step0 + (unsigned long long)p.k_steps; }
+      }
+    }
     if (active) {
       store_state<R, T>(s, p, i);
       p.rew[i] = out.rew_sum;
@@ -1574,8 +1680,8 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     }
     if (!multi) {
       // ---- one-wave launch (small N): latency-bound, so no CTA barrier anywhere - every warp transposes and ships
-      // its own 32 observation rows, the last warp to finish takes the CTA's launch ticket.  (Same run_steps
-      // instance as the pipelined path: results do not depend on which path a batch size selects.)
+      // its own 32 observation rows.  (Same run_steps instance as the pipelined path: results do not depend on which
+      // path a batch size selects.)
       float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
       obs_to_tile<R, T::PLAIN>(p, o, wtile + lane * obs_dim);
       __syncwarp();
@@ -1585,7 +1691,13 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       if (wrows > 0) {
         const int total = (int)wrows * obs_dim;
         float* dst = p.obs + warp_first * obs_dim;             // 128 * obs_dim bytes per full warp: 16-byte aligned
-        if ((total & 3) == 0) {
+        if (T::PLAIN && wrows == 32) {                         // 32 x 18 words = 144 vectors: four full trips + half a trip
+          const float4* t4 = reinterpret_cast<const float4*>(wtile) + lane;
+          float4* d4 = reinterpret_cast<float4*>(dst) + lane;
+          const float4 v0 = t4[0], v1 = t4[32], v2 = t4[64], v3 = t4[96];
+          d4[0] = v0; d4[32] = v1; d4[64] = v2; d4[96] = v3;
+          if (lane < 16) d4[128] = t4[128];
+        } else if ((total & 3) == 0) {
           const float4* t4 = reinterpret_cast<const float4*>(wtile);
           float4* d4 = reinterpret_cast<float4*>(dst);
           for (int k = lane; k < (total >> 2); k += 32) d4[k] = t4[k];
@@ -1598,15 +1710,12 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       if (lane == 0 && p.timing != nullptr) {
         unsigned int smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        unsigned long long* rec = p.timing + ((long long)blockIdx.x * WARPS + warp) * 5;
-        rec[0] = ts0; rec[1] = ts1; rec[2] = ts2; rec[3] = ts3; rec[4] = smid;
+        // two record sets (step parity), so the last two launches of a graph can be laid side by side
+        unsigned long long* rec = p.timing + ((long long)(((p.env_id_offset / p.n) + (long long)step0) & 1) * gridDim.x * cta_warps + (long long)blockIdx.x * cta_warps + warp) * 6;
+        rec[0] = ts_a; rec[1] = ts0; rec[2] = ts1; rec[3] = ts2; rec[4] = ts3; rec[5] = smid;
       }
 #endif
       if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
-      // (the clock was read at the top of every thread, and run_steps depended on the values: no fence needed here)
-      if (lane == 0) {
-        if (atomicAdd(&warps_done, 1u) == WARPS - 1) finish_launch_one(p, out.svd_t, (unsigned long long)p.k_steps);
-      }
       return;
     }
     // observation rows: registers -> shared tile -> one bulk store per CTA

@@ -29,6 +29,7 @@ struct QsHandle {
   void* info;
   void* term_obs;
   const void* models;
+  int models_plain;          // caller asserted QS_MODELS_PLAIN for the bound model buffer
   const void* ou_z;
   const void* obs_z;
   const void* reset_z;
@@ -43,12 +44,14 @@ struct QsHandle {
   const char* last_variant;
   // qs_step_host scratch (library-owned)
   cudaStream_t hs[kHostStreams];
-  cudaEvent_t hev[kHostStreams];
-  bool host_ready;
+  int host_streams_made;     // staged path resources, created one by one (a failed setup resumes where it stopped)
   int host_zero_copy;        // A/B knob QUADSIM_HOST_ZEROCOPY (default 1)
   int tma_generic;           // A/B knob QUADSIM_TMA_GENERIC (default 1)
-  unsigned long long* timing;   // QUADSIM_TIMING_PTR: stamp buffer of QS_PHASE_TIMING experiment builds (else unused)
-  cudaStream_t zc_stream;
+  int ow_threads, prefetch, spec_draw;   // A/B knobs QUADSIM_OW_THREADS / QUADSIM_PREFETCH / QUADSIM_SPEC_DRAW (see Params)
+#ifdef QS_PHASE_TIMING
+  unsigned long long* timing;   // QUADSIM_TIMING_PTR: stamp buffer of the experiment build (tools/build_timing.sh)
+#endif
+  cudaEvent_t order_ev;      // qs_step_host: orders the library's internal streams after the caller's stream
   const char* last_host_path;
   void *h_act, *h_obs, *h_rew;
   uint8_t* h_done;
@@ -71,12 +74,17 @@ int fail(QsHandle* h, int code, const char* fmt, const char* a = "") {
 
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-// device-side alias of a pinned host pointer (false for pageable memory)
-bool device_alias(const void* host, void** dev) {
+// one 4-wide vector of `real`: what every vector load / store and bulk copy of the kernels assumes
+size_t vec_align(const QsHandle* h) { return h->cfg.dtype == QS_F64 ? 32 : 16; }
+bool vec_aligned(const QsHandle* h, const void* p) { return ((uintptr_t)p) % vec_align(h) == 0; }
+
+// device-side alias of a pinned host pointer (false for pageable memory or a pointer the kernels cannot use with vector
+// accesses: the caller then takes the staged path)
+bool device_alias(const QsHandle* h, const void* host, void** dev, bool need_vec) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
   if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
-  if (((uintptr_t)a.devicePointer) % 16 != 0) return false;
+  if (need_vec && !vec_aligned(h, a.devicePointer)) return false;
   *dev = a.devicePointer;
   return true;
 }
@@ -138,6 +146,9 @@ bool need_rare(const QsHandle* h) {
                      c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA;
   if ((c.n_agents > 1 || c.reward.log_pos || c.per_env_model) && !plain) return true;
   if (c.per_env_model && c.reward.log_pos) return true;
+  // the specialised per-env-model kernels compile out linearity / rotor drag / damping (rows 8 and 9 of the model buffer):
+  // they are taken only when the caller has asserted that every bound model is plain in that sense
+  if (c.per_env_model && !h->models_plain) return true;
   return false;
 }
 
@@ -151,7 +162,9 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.info = (R*)h->info;
   p.models = (const R*)h->models;
   p.term_obs = (R*)h->term_obs;
+#ifdef QS_PHASE_TIMING
   p.timing = h->timing;
+#endif
   p.ou_z = (const R*)h->ou_z;
   p.obs_z = (const R*)h->obs_z;
   p.reset_z = (const R*)h->reset_z;
@@ -187,6 +200,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.tma_rows = h->lay.rows;
   p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
   p.pdl = h->pdl;
+  p.ow_threads = h->ow_threads; p.prefetch = 0; p.spec_draw = h->spec_draw;
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
@@ -242,10 +256,11 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
 
 template <typename R>
 int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8_t* done, cudaStream_t st,
-            long long begin, long long end, int advance, int slot = 0) {
+            long long begin, long long end, int advance, int slot = 0, bool device_buffers = true) {
   qs::Params<R> p;
   fill_params<R>(h, &p);
   p.k_steps = k;
+  if (device_buffers) p.prefetch = h->prefetch;   // the L2 prefetch hint is for device memory (not for pinned host aliases)
   p.clock_advance = advance;
   if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos || h->cfg.per_env_model)) p.need_rare = 1;   // specialised kernels: k == 1 only
   if (!advance) p.pdl = 0;                       // chunk launches of the host pipeline follow copies on side streams
@@ -254,7 +269,13 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
   p.actions = (const R*)actions; p.obs = (R*)obs; p.rew = (R*)rew; p.done = done;
   p.begin = begin; p.end = end;
   cudaError_t e = qs::launch_step<R>(p, st, &h->last_variant);
-  if (e != cudaSuccess) return fail(h, QS_ECUDA, "env_step launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    // a launch that did not start leaves the ticket / tile counters untouched, but one that was rejected mid-pipeline
+    // (chunked host path) must not leave a partial count behind: the clock would silently stop advancing
+    cudaGetLastError();
+    cudaMemsetAsync(h->d_ticket, 0, (1 + 2 * kHostStreams) * sizeof(unsigned int), st);
+    return fail(h, QS_ECUDA, "env_step launch: %s", cudaGetErrorString(e));
+  }
   h->launches++;
   return QS_OK;
 }
@@ -294,6 +315,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   layout_of(cfg, &h->lay);
   h->state = h->info = nullptr;
   h->models = nullptr;
+  h->models_plain = 0;
   h->term_obs = nullptr;
   h->ou_z = h->obs_z = h->reset_z = nullptr;
   h->goal_z = nullptr;
@@ -301,11 +323,16 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   h->launches = 0;
   { const char* e = getenv("QUADSIM_PDL"); h->pdl = e ? atoi(e) : 1; }   // A/B knob: programmatic dependent launch, default on
   h->last_variant = "";
-  h->host_ready = false;
+  h->host_streams_made = 0;
+  h->order_ev = nullptr;
   { const char* e = getenv("QUADSIM_HOST_ZEROCOPY"); h->host_zero_copy = e ? atoi(e) : 1; }
   { const char* e = getenv("QUADSIM_TMA_GENERIC"); h->tma_generic = e ? atoi(e) : 1; }
+  { const char* e = getenv("QUADSIM_OW_THREADS"); h->ow_threads = e ? atoi(e) : 64; }
+  { const char* e = getenv("QUADSIM_PREFETCH"); h->prefetch = e ? atoi(e) : 3; }
+  { const char* e = getenv("QUADSIM_SPEC_DRAW"); h->spec_draw = e ? atoi(e) : 1; }
+#ifdef QS_PHASE_TIMING
   { const char* e = getenv("QUADSIM_TIMING_PTR"); h->timing = e ? (unsigned long long*)strtoull(e, nullptr, 0) : nullptr; }
-  h->zc_stream = nullptr;
+#endif
   h->last_host_path = "";
   h->h_act = h->h_obs = h->h_rew = nullptr; h->h_done = nullptr;
   cudaError_t e = cudaSetDevice(cfg->device);
@@ -333,11 +360,12 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
 int qs_destroy(QsHandle* h) {
   if (!h) return QS_EINVAL;
   cudaSetDevice(h->cfg.device);
-  if (h->zc_stream) cudaStreamDestroy(h->zc_stream);
-  if (h->host_ready) {
-    for (int k = 0; k < kHostStreams; ++k) { cudaStreamDestroy(h->hs[k]); cudaEventDestroy(h->hev[k]); }
-    cudaFree(h->h_act); cudaFree(h->h_obs); cudaFree(h->h_rew); cudaFree(h->h_done);
-  }
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
+  for (int k = 0; k < h->host_streams_made; ++k) cudaStreamDestroy(h->hs[k]);
+  if (h->h_act) cudaFree(h->h_act);
+  if (h->h_obs) cudaFree(h->h_obs);
+  if (h->h_rew) cudaFree(h->h_rew);
+  if (h->h_done) cudaFree(h->h_done);
   cudaFree(h->d_stats);
   cudaFree(h->d_status);
   cudaFree(h->d_clock);
@@ -356,12 +384,14 @@ int qs_bind_state(QsHandle* h, void* state) {
   return QS_OK;
 }
 
-int qs_bind_models(QsHandle* h, const void* models) {
+int qs_bind_models(QsHandle* h, const void* models, int32_t flags) {
   if (!h) return QS_EINVAL;
   if (!h->cfg.per_env_model) return fail(h, QS_EINVAL, "handle was not created with per_env_model");
   if (!models) return fail(h, QS_EINVAL, "models is NULL");
   if (((uintptr_t)models) % 32 != 0) return fail(h, QS_EINVAL, "models must be 32-byte aligned");
+  if (flags & ~QS_MODELS_PLAIN) return fail(h, QS_EINVAL, "unknown qs_bind_models flag");
   h->models = models;
+  h->models_plain = (flags & QS_MODELS_PLAIN) ? 1 : 0;
   return QS_OK;
 }
 
@@ -395,6 +425,7 @@ int qs_reset(QsHandle* h, const uint8_t* mask, void* obs, qs_stream_t stream) {
   int rc = check_ready(h, false, nullptr);
   if (rc != QS_OK) return rc;
   if (!obs) return fail(h, QS_EINVAL, "obs is NULL");
+  if (!vec_aligned(h, obs)) return fail(h, QS_EINVAL, "obs must be aligned to 4 reals (16 bytes f32 / 32 bytes f64)");
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaError_t e;
   if (h->cfg.dtype == QS_F32) {
@@ -415,6 +446,7 @@ int qs_observe(QsHandle* h, const void* accelerometer, void* obs, qs_stream_t st
   int rc = check_ready(h, false, nullptr);
   if (rc != QS_OK) return rc;
   if (!obs) return fail(h, QS_EINVAL, "obs is NULL");
+  if (!vec_aligned(h, obs)) return fail(h, QS_EINVAL, "obs must be aligned to 4 reals (16 bytes f32 / 32 bytes f64)");
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
   cudaError_t e;
   if (h->cfg.dtype == QS_F32) {
@@ -436,8 +468,7 @@ int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uin
   if (rc != QS_OK) return rc;
   if (k < 1) return fail(h, QS_EINVAL, "k must be >= 1");
   if (!obs || !rew || !done) return fail(h, QS_EINVAL, "obs/rew/done must not be NULL");
-  const uintptr_t al = h->cfg.dtype == QS_F64 ? 32 : 16;       // one 4-wide vector of `real`
-  if (((uintptr_t)obs) % al != 0 || (actions && ((uintptr_t)actions) % al != 0))
+  if (!vec_aligned(h, obs) || (actions && !vec_aligned(h, actions)))
     return fail(h, QS_EINVAL, "actions and obs must be aligned to 4 reals (16 bytes f32 / 32 bytes f64): vector loads, bulk stores");
   if (k > 1 && h->cfg.noise_mode == QS_NOISE_INJECTED) return fail(h, QS_EUNSUPPORTED, "qs_step_k with injected noise needs k == 1");
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -474,42 +505,44 @@ int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_sub
   return QS_OK;
 }
 
-int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* rew_host, uint8_t* done_host) {
+int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* rew_host, uint8_t* done_host, qs_stream_t stream) {
   int rc = check_ready(h, true, actions_host);
   if (rc != QS_OK) return rc;
   if (!obs_host || !rew_host || !done_host) return fail(h, QS_EINVAL, "obs/rew/done must not be NULL");
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t user = (cudaStream_t)stream;
   const long long n = h->cfg.n_envs;
   const size_t rs = h->cfg.dtype == QS_F32 ? sizeof(float) : sizeof(double);
   const int od = h->lay.obs_dim, ad = h->lay.act_dim;
-  // Pinned (cudaHostAlloc / cudaHostRegister) buffers are addressable from the device: one launch reads the actions
-  // and writes obs / reward / done straight across PCIe (coalesced 16-byte vectors and bulk stores), so there is no
-  // staging copy, no copy-engine hand-off and a single stream synchronisation per step.
+  // Pinned (cudaHostAlloc / cudaHostRegister) buffers are addressable from the device: one launch ON THE CALLER'S STREAM
+  // (so it is ordered after the resets, steps and state writes the caller queued there) reads the actions and writes
+  // obs / reward / done straight across PCIe (coalesced 16-byte vectors), so there is no staging copy, no copy-engine
+  // hand-off and a single stream synchronisation per step.
   if (h->host_zero_copy) {
     void* d_act = nullptr; void* d_obs = nullptr; void* d_rew = nullptr; void* d_done = nullptr;
-    if ((!actions_host || device_alias(actions_host, &d_act)) && device_alias(obs_host, &d_obs) &&
-        device_alias(rew_host, &d_rew) && device_alias(done_host, &d_done)) {
-      if (!h->zc_stream) QS_CUDA(h, cudaStreamCreateWithFlags(&h->zc_stream, cudaStreamNonBlocking));
-      if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, d_act, d_obs, d_rew, (uint8_t*)d_done, h->zc_stream, 0, n, 1);
-      else rc = do_step<double>(h, 1, d_act, d_obs, d_rew, (uint8_t*)d_done, h->zc_stream, 0, n, 1);
+    if ((!actions_host || device_alias(h, actions_host, &d_act, true)) && device_alias(h, obs_host, &d_obs, true) &&
+        device_alias(h, rew_host, &d_rew, false) && device_alias(h, done_host, &d_done, false)) {
+      if (h->cfg.dtype == QS_F32) rc = do_step<float>(h, 1, d_act, d_obs, d_rew, (uint8_t*)d_done, user, 0, n, 1, 0, false);
+      else rc = do_step<double>(h, 1, d_act, d_obs, d_rew, (uint8_t*)d_done, user, 0, n, 1, 0, false);
       if (rc != QS_OK) return rc;
-      QS_CUDA(h, cudaStreamSynchronize(h->zc_stream));
+      QS_CUDA(h, cudaStreamSynchronize(user));
       h->last_host_path = "zero-copy";
       return QS_OK;
     }
   }
   h->last_host_path = "staged";
-  if (!h->host_ready) {
-    for (int k = 0; k < kHostStreams; ++k) {
-      QS_CUDA(h, cudaStreamCreateWithFlags(&h->hs[k], cudaStreamNonBlocking));
-      QS_CUDA(h, cudaEventCreateWithFlags(&h->hev[k], cudaEventDisableTiming));
-    }
-    QS_CUDA(h, cudaMalloc(&h->h_act, (size_t)n * ad * rs));
-    QS_CUDA(h, cudaMalloc(&h->h_obs, (size_t)n * od * rs));
-    QS_CUDA(h, cudaMalloc(&h->h_rew, (size_t)n * rs));
-    QS_CUDA(h, cudaMalloc((void**)&h->h_done, (size_t)n));
-    h->host_ready = true;
+  // resources are created one by one, so a setup that failed half-way resumes instead of leaking what it had made
+  while (h->host_streams_made < kHostStreams) {
+    QS_CUDA(h, cudaStreamCreateWithFlags(&h->hs[h->host_streams_made], cudaStreamNonBlocking));
+    h->host_streams_made++;
   }
+  if (!h->order_ev) QS_CUDA(h, cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+  if (!h->h_act) QS_CUDA(h, cudaMalloc(&h->h_act, (size_t)n * ad * rs));
+  if (!h->h_obs) QS_CUDA(h, cudaMalloc(&h->h_obs, (size_t)n * od * rs));
+  if (!h->h_rew) QS_CUDA(h, cudaMalloc(&h->h_rew, (size_t)n * rs));
+  if (!h->h_done) QS_CUDA(h, cudaMalloc((void**)&h->h_done, (size_t)n));
+  // the internal streams start after everything the caller has queued on its stream so far
+  QS_CUDA(h, cudaEventRecord(h->order_ev, user));
   // chunks of whole CTAs (and whole warps, so swarm groups never straddle a chunk), one stream each:
   // H2D(actions) -> fused step -> D2H(obs, rew, done); copies of one chunk overlap the kernel of another
   long long per = (n + kHostStreams - 1) / kHostStreams;
@@ -520,6 +553,7 @@ int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* re
     if (b >= n) break;
     used = k + 1;
     cudaStream_t st = h->hs[k];
+    QS_CUDA(h, cudaStreamWaitEvent(st, h->order_ev, 0));
     if (actions_host)
       QS_CUDA(h, cudaMemcpyAsync((char*)h->h_act + (size_t)b * ad * rs, (const char*)actions_host + (size_t)b * ad * rs,
                                  (size_t)(e - b) * ad * rs, cudaMemcpyHostToDevice, st));
@@ -534,13 +568,14 @@ int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* re
     QS_CUDA(h, cudaMemcpyAsync(done_host + b, h->h_done + b, (size_t)(e - b), cudaMemcpyDeviceToHost, st));
   }
   for (int k = 0; k < used; ++k) QS_CUDA(h, cudaStreamSynchronize(h->hs[k]));
-  // the chunk launches only read the clock; advance it once for the whole step
+  // the chunk launches only read the clock; advance it once for the whole step (on the caller's stream: every chunk has
+  // completed, and whatever the caller queues next is ordered after the advance)
   cudaError_t ce;
-  if (h->cfg.dtype == QS_F32) { qs::Params<float> p; fill_params<float>(h, &p); ce = qs::launch_clock_advance<float>(p, h->hs[0]); }
-  else { qs::Params<double> p; fill_params<double>(h, &p); ce = qs::launch_clock_advance<double>(p, h->hs[0]); }
+  if (h->cfg.dtype == QS_F32) { qs::Params<float> p; fill_params<float>(h, &p); ce = qs::launch_clock_advance<float>(p, user); }
+  else { qs::Params<double> p; fill_params<double>(h, &p); ce = qs::launch_clock_advance<double>(p, user); }
   if (ce != cudaSuccess) return fail(h, QS_ECUDA, "clock_advance launch: %s", cudaGetErrorString(ce));
   h->launches++;
-  QS_CUDA(h, cudaStreamSynchronize(h->hs[0]));
+  QS_CUDA(h, cudaStreamSynchronize(user));
   return QS_OK;
 }
 

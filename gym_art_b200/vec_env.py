@@ -388,7 +388,12 @@ class QuadVecEnv(object):
             cols = tab[:, idx, :]
         self.models = self._in("models", cols, self.tdtype, (table.shape[0], self.num_envs, 4))
         self.model_index = idx
-        _lib.check(self.lib.qs_bind_models(self._h, self.models.data_ptr()), self._h)
+        # rows 8 / 9 (include/quadsim.h): linearity, C_drag, C_roll | vel_damp, damp_omega_quadratic.  Only when EVERY model
+        # is plain there may the step take the kernels that compile those terms out (checked on the float64 host table)
+        tb = np.asarray(table, dtype=np.float64)
+        self.models_plain = bool(np.all(tb[8, :, 0] == 1.0) and not np.any(tb[8, :, 1:3]) and not np.any(tb[9, :, 0:2]))
+        _lib.check(self.lib.qs_bind_models(self._h, self.models.data_ptr(), _lib.QS_MODELS_PLAIN if self.models_plain else 0),
+                   self._h)
 
     def resample_dynamics(self, n_models=None, seed=None):
         """Draw a fresh set of models with the reference's sampler chain and deal them to the envs (call between
@@ -479,7 +484,17 @@ class QuadVecEnv(object):
         overlap launch latency (the caller loop of quadrotor.py:1278-1305 without per-step host work).
         Returns the torch.cuda.CUDAGraph; outputs land in self.obs / self.rew / self.done."""
         t = self.torch
-        a = self._actions(actions)
+        if self.host_mapped:
+            raise RuntimeError("capture_steps: host_mapped envs synchronise the stream on every call and cannot be captured")
+        if actions is not None:
+            # the graph bakes the POINTER in: it must be the caller's own tensor, not a converted temporary
+            if not (isinstance(actions, t.Tensor) and actions.is_cuda and actions.device == self.device and
+                    actions.dtype == self.tdtype and actions.is_contiguous() and
+                    tuple(actions.shape) == (self.num_envs, self.act_dim)):
+                raise ValueError("capture_steps: actions must be a contiguous %s tensor of shape (%d, %d) on %s"
+                                 % (self.tdtype, self.num_envs, self.act_dim, self.device))
+            self._graph_actions = actions                # keep it alive as long as the env
+        a = actions
         stream = t.cuda.Stream(device=self.device)
         stream.wait_stream(t.cuda.current_stream(self.device))
         with t.cuda.stream(stream):
@@ -500,7 +515,8 @@ class QuadVecEnv(object):
         return self.obs, self.rew, self.done
 
     def step_host(self, actions_host, obs_host, rew_host, done_host):
-        """End-to-end step on HOST tensors (pinned for full PCIe speed): H2D, fused step, D2H, synchronous."""
+        """End-to-end step on HOST tensors (pinned for full PCIe speed): H2D, fused step, D2H, synchronous.  Ordered after
+        the work already queued on torch's current stream (reset(), step(), set_field() ...)."""
         for x in (obs_host, rew_host, done_host):
             assert x.device.type == "cpu" and x.is_contiguous()
         ap = None
@@ -508,8 +524,8 @@ class QuadVecEnv(object):
             assert actions_host.device.type == "cpu" and actions_host.is_contiguous() and actions_host.dtype == self.tdtype
             ap = actions_host.data_ptr()
         assert obs_host.dtype == self.tdtype and rew_host.dtype == self.tdtype and done_host.dtype == self.torch.uint8
-        _lib.check(self.lib.qs_step_host(self._h, ap, obs_host.data_ptr(), rew_host.data_ptr(), done_host.data_ptr()),
-                   self._h)
+        _lib.check(self.lib.qs_step_host(self._h, ap, obs_host.data_ptr(), rew_host.data_ptr(), done_host.data_ptr(),
+                                         self._stream()), self._h)
         return obs_host, rew_host, done_host
 
     def dynamics_step(self, actions, controller=None, n_substeps=None):

@@ -14,8 +14,8 @@
  *   - plain C: pointers + sizes, no torch / C++ types.  Every function returns QS_OK (0) or a negative
  *     QsStatus; nothing throws across the ABI; the text of the last failure is qs_last_error().
  *   - every buffer is owned by the caller (normally torch tensors on the handle's device).  "real" is
- *     float for QS_F32 handles and double for QS_F64 handles.  The state buffer must be 32-byte aligned, actions and
- *     observations 16-byte aligned (cudaMalloc / torch allocations always are).
+ *     float for QS_F32 handles and double for QS_F64 handles.  The state and model buffers must be 32-byte aligned,
+ *     actions and observations aligned to 4 reals (16 bytes f32 / 32 bytes f64; cudaMalloc / torch allocations are).
  *   - all work is enqueued on the caller's stream; the library never synchronises the device except in
  *     the *_host entry points, which are synchronous by definition.
  *   - a handle is bound to one device and is not thread-safe; use one handle per GPU.
@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 6
+#define QS_ABI_VERSION 7
 
 typedef struct QsHandle QsHandle;
 typedef void* qs_stream_t; /* cudaStream_t */
@@ -233,7 +233,10 @@ const char* qs_last_error(const QsHandle* h); /* h may be NULL: error of the las
 int qs_bind_state(QsHandle* h, void* state);
 /* QsConfig.per_env_model handles: device buffer real[QS_MODEL_ROWS][n_envs][4]; may be re-bound or rewritten between
  * steps (the reference resamples dynamics between episodes); the library never frees it */
-int qs_bind_models(QsHandle* h, const void* models);
+#define QS_MODELS_PLAIN 1 /* the caller asserts that EVERY bound model has linearity == 1 and C_drag = C_roll = vel_damp =
+                           * damp_omega_quadratic = 0 (rows 8 and 9), which lets the step take the kernels specialised for
+                           * that case.  Without the flag the run-time-parameterised kernel is used (always correct). */
+int qs_bind_models(QsHandle* h, const void* models, int32_t flags);
 /* optional (auto_reset handles): real[n_envs][obs_dim].  A step that ends an env's episode returns the FIRST observation
  * of the next episode in `obs`; the observation of the terminal state - what the reference's step() returns on its done
  * step (quadrotor.py:988) - is written to this buffer, rows of envs that did not finish are left untouched.
@@ -273,10 +276,12 @@ int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uin
  * reward/obs/tick.  controller = -1 passes `actions` straight through as normalized motor commands. */
 int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_substeps, qs_stream_t stream);
 
-/* Same contract as qs_step but with HOST buffers; returns after the results are in host memory.  Pinned buffers
- * (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()) are read and written by the step kernel directly
- * across PCIe in one launch; pageable buffers go through a chunked H2D / kernel / D2H pipeline over internal streams. */
-int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* rew_host, uint8_t* done_host);
+/* Same contract as qs_step but with HOST buffers; returns after the results are in host memory.  The step is ordered
+ * after everything already queued on `stream` (resets, steps, state writes).  Pinned buffers (cudaHostAlloc /
+ * cudaHostRegister, e.g. torch pin_memory()) aligned to 4 reals are read and written by the step kernel directly across
+ * PCIe in one launch on `stream`; pageable or unaligned buffers go through a chunked H2D / kernel / D2H pipeline over
+ * internal streams that wait for `stream` first. */
+int qs_step_host(QsHandle* h, const void* actions_host, void* obs_host, void* rew_host, uint8_t* done_host, qs_stream_t stream);
 
 /* Finished-episode statistics accumulated on the device: {sum of returns, sum of squared returns, episodes}.
  * qs_stats_device_ptr exposes the double[3] device buffer so the caller can all-reduce it over NCCL. */

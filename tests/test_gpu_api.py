@@ -160,6 +160,67 @@ def test_step_host_equals_step(pinned):
     assert e1.clock == e2.clock and torch.equal(e1.state, e2.state)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_is_ordered_after_the_callers_stream(pinned):
+    """qs_step_host must see the reset the caller queued on its stream just before (no synchronisation in between): the
+    stream is kept busy with a long spin kernel so that an unordered launch would read the pre-reset state."""
+    import torch
+    n = 40000
+    e1, e2 = _env(n), _env(n)
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    a_h = pin(torch.rand((n, 4)) * 2 - 1)
+    o_h, r_h, d_h = pin(torch.empty((n, 18))), pin(torch.empty(n)), pin(torch.empty(n, dtype=torch.uint8))
+    a_d = a_h.cuda()
+    e1.reset()
+    o, r, d = e1.step(a_d)
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        torch.cuda._sleep(200_000_000)          # ~0.1 s of spinning ahead of the reset
+        e2.reset()
+        e2.step_host(a_h, o_h, r_h, d_h)
+    assert torch.equal(o.cpu(), o_h) and torch.equal(r.cpu(), r_h)
+    torch.cuda.synchronize()
+    assert torch.equal(e1.state, e2.state) and e1.clock == e2.clock
+
+
+def test_capture_steps_rejects_temporaries():
+    import torch
+    env = _env(1024)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.capture_steps(2, np.zeros((1024, 4)))
+    with pytest.raises(ValueError):
+        env.capture_steps(2, torch.zeros((1024, 4), device="cuda", dtype=torch.float64))
+    a = torch.zeros((1024, 4), device="cuda")
+    g = env.capture_steps(2, a)
+    s0 = env.clock[1]
+    g.replay()
+    torch.cuda.synchronize()
+    assert env.clock[1] == s0 + 2
+
+
+def test_unaligned_host_buffers_take_the_staged_path():
+    """A pinned f64 view at a 16-byte offset is not a valid V4<double> address: zero-copy must not be chosen."""
+    import torch
+    n = 2048
+    e1 = _env(n, dtype="float64")
+    e2 = _env(n, dtype="float64")
+    e1.reset(), e2.reset()
+    base = torch.empty(n * 18 + 2, dtype=torch.float64).pin_memory()
+    o_h = base[2:].view(n, 18)                   # 16-byte offset
+    assert o_h.data_ptr() % 32 == 16
+    a_h = (torch.rand((n, 4), dtype=torch.float64) * 2 - 1).pin_memory()
+    r_h, d_h = torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    o, r, d = e1.step(a_h.cuda())
+    e2.step_host(a_h, o_h, r_h, d_h)
+    assert e2.host_path == "staged"
+    assert torch.equal(o.cpu(), o_h) and torch.equal(r.cpu(), r_h)
+    from gym_art_b200 import _lib
+    assert e2.lib.qs_reset(e2._h, None, e2.obs.data_ptr() + 8, e2._stream()) == _lib.QS_EINVAL
+    assert e2.lib.qs_observe(e2._h, None, e2.obs.data_ptr() + 16, e2._stream()) == _lib.QS_EINVAL
+
+
 def test_cuda_graph_replay_advances_device_clock():
     """Steps captured in a CUDA graph keep drawing fresh Philox numbers on replay (device-resident clock)."""
     import torch
@@ -344,13 +405,15 @@ def test_per_env_dynamics_sampler_chain_fp32():
     env.close()
 
 
-@pytest.mark.parametrize("ctrl,oc", [("raw", 0), ("mellinger", 6)])
-def test_per_env_models_fast_kernel_fp32(ctrl, oc):
+@pytest.mark.parametrize("ctrl,oc,with_drag", [("raw", 0, False), ("mellinger", 6, False), ("raw", 0, True), ("mellinger", 6, True)])
+def test_per_env_models_fast_kernel_fp32(ctrl, oc, with_drag):
     """The specialised per-env-model variant of the TMA kernel (multi-tile persistent path), fp32, per step from a
-    re-synchronised state against the oracle run model by model: 1e-5 relative."""
+    re-synchronised state against the oracle run model by model: 1e-5 relative.  with_drag: one of the models has
+    linearity != 1 and rotor drag / damping - the specialised kernel compiles those terms out, so the host must route the
+    whole batch to the run-time-parameterised kernel (QS_MODELS_PLAIN not asserted) and the result must still match."""
     from gym_art_b200 import QuadVecEnv
     from oracle import quadsim_oracle as qo
-    zoo = [z for i, z in enumerate(_model_zoo()) if i != 4]      # the drag/linearity model belongs to the generic kernel
+    zoo = [z for i, z in enumerate(_model_zoo()) if with_drag or i != 4]
     K, per, T = len(zoo), 28000, 10
     n = K * per                                                   # 140,000 envs: enough tiles for the persistent pipeline
     index = np.arange(n) % K
@@ -377,7 +440,8 @@ def test_per_env_models_fast_kernel_fp32(ctrl, oc):
         obs_z = rng.standard_normal((n, qo.OBS_Z)).astype(np.float32).astype(np.float64)
         env.set_noise(ou_z=ou_z, obs_z=obs_z)
         o, r, d = env.step(a)
-        assert env.kernel_variant == "tma-%s-injected" % ctrl
+        assert env.models_plain == (not with_drag)
+        assert env.kernel_variant == ("tma-generic-permodel-injected" if with_drag else "tma-%s-injected" % ctrl)
         o, r = o.double().cpu().numpy(), r.double().cpu().numpy()
         for k in range(K):
             s = sel[k]
