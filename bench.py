@@ -206,7 +206,7 @@ NCU_TRAFFIC_SOURCE = ("profiles/r1_ncu_cfg2_65536.txt (ncu replays a cold-L2 lau
 
 
 def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None, chunk=501, repeats=1, launches_of=None,
-               start=0):
+               start=0, lead_in=0):
     """Captures `fn_steps(i)` for i in a chunk into CUDA graphs and times exactly n_steps steps with CUDA events on
     the launching stream, `repeats` times (each repeat bracketed by barrier + synchronize).  `reducer` (an
     EpisodeStatsReducer) is told after every chunk how many steps have been enqueued since the reset; it fires the
@@ -214,16 +214,35 @@ def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None
     rank, kernel launches inside one timed repeat counted through qs_launch_count at capture time)."""
     stream = torch.cuda.Stream(device=device)
     graphs, graph_launches = {}, {}
+    # lead_in > 0 (only when the K steps fit one graph): the graph holds `lead_in` untimed steps followed by the K timed
+    # steps, and the two timing events are event-record NODES of that graph - e0 on a forked branch behind the last
+    # lead-in step (so the chain of dependent launches is not interrupted), e1 behind the K-th timed step.  The interval
+    # is then completion of the step before the timed window -> completion of its K-th step: exactly K steps with the
+    # launch pipeline in its steady state, independent of K.  Without it a 20-step region also measures the idle-to-busy
+    # ramp of one graph launch (about 5 us, i.e. 4 % of 20 steps).
+    lead = int(lead_in) if n_steps <= chunk else 0
+    side = torch.cuda.Stream(device=device) if lead else None
+    ge0 = torch.cuda.Event(enable_timing=True, external=True) if lead else None
+    ge1 = torch.cuda.Event(enable_timing=True, external=True) if lead else None
+
     def graph_for(first, count):
         key = (first % RING_PERIOD[0], count)
         if key not in graphs:
             before = launches_of() if launches_of else 0
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
+                if lead:
+                    for i in range(first - lead, first):
+                        fn_steps(i)
+                    side.wait_stream(stream)
+                    ge0.record(side)
                 for i in range(first, first + count):
                     fn_steps(i)
+                if lead:
+                    ge1.record(stream)
+                    stream.wait_stream(side)
             graphs[key] = g
-            graph_launches[key] = (launches_of() - before) if launches_of else count
+            graph_launches[key] = ((launches_of() - before) if launches_of else count + lead) - lead
         return key
 
     with torch.cuda.stream(stream):
@@ -235,7 +254,7 @@ def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None
     def run_plan(plan):
         for key in plan:
             graphs[key].replay()
-            enq[0] += key[1]
+            enq[0] += key[1] + lead
             if reducer is not None:
                 reducer.after_steps(enq[0], stream)
 
@@ -247,7 +266,7 @@ def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None
             done += c
         return plan
 
-    first0 = enq[0]
+    first0 = enq[0] + lead
     plan = make_plan(first0)
     with torch.cuda.stream(stream):                  # one untimed pass (graph instantiation / upload stay outside)
         run_plan(plan)
@@ -255,10 +274,10 @@ def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None
     out = []
     for _ in range(repeats):
         with torch.cuda.stream(stream):              # untimed eager steps up to the ring phase the graphs were captured at
-            while (enq[0] - first0) % RING_PERIOD[0]:
+            while (enq[0] + lead - first0) % RING_PERIOD[0]:
                 fn_steps(enq[0])
                 enq[0] += 1
-        plan = make_plan(enq[0])
+        plan = make_plan(enq[0] + lead)
         stream.synchronize()
         if dist is not None:
             dist.barrier()
@@ -270,7 +289,7 @@ def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None
             e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize(device)
-        out.append(e0.elapsed_time(e1))
+        out.append(ge0.elapsed_time(ge1) if lead else e0.elapsed_time(e1))
     return out, sum(graph_launches[k] for k in plan)
 
 
@@ -393,9 +412,14 @@ def run_ours(args):
     # short timed regions (the driver's --steps 20 is 140 us) are repeated and the median reported; all repeats listed
     repeats = max(1, min(9, 4000 // max(K, 1)))
     ms_all, launches = time_graph(torch, step_ring, K, W, device, pg, reducer, chunk=EP_STEPS, repeats=repeats,
-                                  launches_of=ring_launches)
+                                  launches_of=ring_launches, lead_in=ring)
     ms_all = reduce_max(torch, pg, device, ms_all)            # per repeat: max over ranks
     ms_max = median(ms_all)
+    # for the record: the same K steps timed from an idle GPU (events around one graph replay, no lead-in steps)
+    cold = None
+    if K <= EP_STEPS:
+        ms_cold, _ = time_graph(torch, step_ring, K, 0, device, pg, None, chunk=EP_STEPS, repeats=repeats, start=1 << 20)
+        cold = median(reduce_max(torch, pg, device, ms_cold)) / K
     value = world * N_BATCH * K / (ms_max * 1e-3)
     step_us = ms_max * 1e3 / K
     achieved = N_BATCH * BYTES_PER_ENV_STEP / (step_us * 1e-6) / 1e9
@@ -491,17 +515,19 @@ def run_ours(args):
     o_h = torch.empty((N_BATCH, 18), dtype=torch.float32).pin_memory()
     r_h = torch.empty((N_BATCH,), dtype=torch.float32).pin_memory()
     d_h = torch.empty((N_BATCH,), dtype=torch.uint8).pin_memory()
-    for _ in range(5):
-        e0.step_host(a_h, o_h, r_h, d_h)
     KE = max(200, min(K, 2000))
-    e2e_launch0 = e0.launch_count
-    if multi:
-        dist.barrier()
-    torch.cuda.synchronize(device)
-    t0 = time.perf_counter()
-    for _ in range(KE):
-        e0.step_host(a_h, o_h, r_h, d_h)
-    torch.cuda.synchronize(device)
+    s_host = torch.cuda.Stream(device=device)         # the caller's stream the host-buffer steps are ordered on
+    with torch.cuda.stream(s_host):
+        for _ in range(5):
+            e0.step_host(a_h, o_h, r_h, d_h)
+        e2e_launch0 = e0.launch_count
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(KE):
+            e0.step_host(a_h, o_h, r_h, d_h)
+        torch.cuda.synchronize(device)
     te = reduce_max(torch, pg, device, [time.perf_counter() - t0])[0]
     e2e_value = world * N_BATCH * KE / te
     e2e_launches = e0.launch_count - e2e_launch0
@@ -548,10 +574,15 @@ def run_ours(args):
                        "l2": "ring of %d independent batches, %.0f MB footprint > 126 MB L2, cycled" % (ring, ring_bytes / 1e6),
                        "launch": "CUDA graph of qs_step launches (device-resident clock, programmatic dependent launch), "
                                  "one kernel per step",
-                       "timing": "CUDA events around exactly K steps, max over ranks; repeated %d times (each repeat bracketed by "
-                                 "barrier + synchronize), median reported, every repeat listed in ms_repeats" % repeats,
+                       "timing": ("CUDA events around exactly K steps, max over ranks; repeated %d times (each repeat bracketed by "
+                                  "barrier + synchronize), median reported, every repeat listed in ms_repeats. " % repeats) +
+                                 ("K fits one CUDA graph: the graph holds %d untimed lead-in steps and then the K timed steps, and the "
+                                  "two events are event-record nodes of that graph (e0 behind the last lead-in step, e1 behind the "
+                                  "K-th step), i.e. K steps completion-to-completion with the launch pipeline in steady state; the "
+                                  "same K steps timed from an idle GPU are in ms_per_step_from_idle" % ring if K <= EP_STEPS else
+                                  "K spans %d graph replays of <= %d steps, events recorded on the stream around them" % (-(-K // EP_STEPS), EP_STEPS)),
                        "kernel_variant": variant, "parallelism": "env-index sharding x%d, no data-path collective" % world},
-            "ms_repeats": ms_all,
+            "ms_repeats": ms_all, "ms_per_step_from_idle": cold,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N_BATCH * 16,
                     "d2h_bytes_per_step": N_BATCH * (72 + 4 + 1), "steps": KE, "gpu_launches": e2e_launches,
                     "api": "qs_step_host on pinned host tensors: the step kernel reads the actions and writes obs/reward/done "

@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 
-def run(n, steps, ring, cfg, repeats=3, **knobs):
+def run(n, steps, ring, cfg, repeats=3, lead_in=0, **knobs):
     for k, v in knobs.items():
         os.environ[k] = str(v)
     dev = torch.device("cuda", 0)
@@ -27,7 +27,7 @@ def run(n, steps, ring, cfg, repeats=3, **knobs):
         envs.append(e)
         acts.append(None if cfg == "cfg5" else torch.rand((n, 4), device=dev, generator=gen) * 2 - 1)
     bench.RING_PERIOD[0] = ring
-    ms, _ = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), steps, 20, dev, repeats=repeats)
+    ms, _ = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), steps, 20, dev, repeats=repeats, lead_in=lead_in)
     v = envs[0].kernel_variant
     for e in envs:
         e.check_finite()
@@ -41,10 +41,8 @@ if __name__ == "__main__":
     cfg = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
     ring = max(1, min(16, (256 << 20) // (n * 221)))
     print("n_envs %d, ring %d, %d steps per timing, %s" % (n, ring, steps, cfg))
-    combos = [(64, 3), (64, 5), (64, 7), (64, 3), (64, 5), (64, 7)]
-    for thr, pf in combos:
-        best, med, v = run(n, steps, ring, cfg, QUADSIM_OW_THREADS=thr, QUADSIM_PREFETCH=pf)
-        print("threads %3d prefetch %d : %.3f us/step (median %.3f)  frac %.3f  [%s]"
-              % (thr, pf, best, med, n * 349 / (best * 1e-6) / 1e9 / 6533.2, v), flush=True)
-    best, med, v = run(n, 20, ring, cfg, repeats=9, QUADSIM_OW_THREADS=64, QUADSIM_PREFETCH=3)     # the driver's regime
-    print("K=20 : %.3f us/step (median %.3f)" % (best, med), flush=True)
+    best, med, v = run(n, steps, ring, cfg, QUADSIM_OW_THREADS=64, QUADSIM_PREFETCH=3)
+    print("steady, %d steps : %.3f us/step (median %.3f)  frac %.3f  [%s]" % (steps, best, med, n * 349 / (best * 1e-6) / 1e9 / 6533.2, v), flush=True)
+    for lead in (0, 4, 16):                                                                           # the driver's regime
+        best, med, v = run(n, 20, ring, cfg, repeats=9, lead_in=lead, QUADSIM_OW_THREADS=64, QUADSIM_PREFETCH=3)
+        print("K=20 lead_in %2d : %.3f us/step (median %.3f)" % (lead, best, med), flush=True)
