@@ -71,6 +71,10 @@ class ReferenceRunner(object):
             self.env = mod.QuadrotorEnv(**env_kwargs)
             self.tape.attach_env(self.env)
         self.tape.take()                       # draws made by the ctor's own _reset() are not replayed
+        # ... and how many of them there were must not shift the stream the rollout is recorded from (the ctor's default
+        # spawn uses the env's own RandomState and a rejection loop on it): start the rollout's draws from a fresh,
+        # seeded generator, so that a fixture is a function of (case, seed) alone - whatever ran before in the process
+        self.tape.rs = np.random.RandomState(seed)
         self.noise_on = not self.env.sense_noise.bypass
         self.gyro_bias_mode = self.noise_on and self.env.sense_noise.gyro_norm_std != 0.0
         # optional controller the reference env cannot select itself

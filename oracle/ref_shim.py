@@ -56,7 +56,8 @@ def install_stubs():
             self.max_episode_steps = max_episode_steps
 
     def np_random(seed=None):
-        return np.random.RandomState(seed), seed
+        # (deterministic also without a seed: an unseeded generator made recorded rollouts differ from run to run)
+        return np.random.RandomState(0 if seed is None else seed), seed
 
     class _Err(Exception):
         pass

