@@ -10,27 +10,31 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QUADSIM_LIB") or os.path.join(HERE, "libquadsim.so")   # override: A/B builds only
 
-QS_ABI_VERSION = 7
+QS_ABI_VERSION = 8
 QS_MODELS_PLAIN = 1
 QS_OK, QS_EINVAL, QS_ECUDA, QS_ENONFINITE, QS_ESTATE, QS_EUNSUPPORTED, QS_EABI = 0, -1, -2, -3, -4, -5, -6
 QS_F32, QS_F64 = 0, 1
 (QS_CTRL_RAW, QS_CTRL_VERTICAL, QS_CTRL_VERTPLANE, QS_CTRL_SHIFTED, QS_CTRL_OMEGA_THRUST, QS_CTRL_VELOCITY_YAW,
  QS_CTRL_MELLINGER) = range(7)
 QS_NOISE_PHILOX, QS_NOISE_INJECTED = 0, 1
-QS_OBS_Z, QS_RESET_Z, QS_INFO_DIM, QS_MODEL_ROWS, QS_GOAL_Z = 30, 48, 48, 14, 4
+QS_OBS_Z, QS_RESET_Z, QS_INFO_DIM, QS_MODEL_ROWS, QS_GOAL_Z = 33, 51, 48, 14, 4
+QS_INIT_DEFAULT, QS_INIT_RANDOM, QS_INIT_PITCH_ROLL_RESTRICTED = 0, 1, 2
 (QS_INFO_ACC, QS_INFO_ACCELEROMETER, QS_INFO_TORQUE, QS_INFO_OMEGA_DOT, QS_INFO_CMDS, QS_INFO_CRASHED, QS_INFO_COLLIDED,
  QS_INFO_COSTS, QS_INFO_EP_RETURN, QS_INFO_TICK, QS_INFO_REWARD, QS_INFO_DONE, QS_INFO_COSTS_RAW) = (
     0, 3, 6, 9, 12, 16, 17, 18, 28, 29, 30, 31, 32)
 
 OBS_REPRS = ["xyz_vxyz_R_omega", "xyz_vxyz_R_omega_h", "xyzr_vxyzr_R_omega", "xyzr_vxyzr_R_omega_h",
-             "xyz_vxyz_R_omega_acc_act", "xyz_vxyz_R_omega_act"]
+             "xyz_vxyz_R_omega_acc_act", "xyz_vxyz_R_omega_act",
+             # get_state.py:276-382: run in the reference once the module is given the names it forgot to import
+             "xyz_vxyz_quat_omega", "xyzr_vxyzr_quat_omega", "xyzr_vxyzr_quat_omega_h", "xyzr_vxyzr_R_omega_t2w",
+             "xyz_vxyz_R_omega_t2w", "xyz_vxyz_R_omega_t2w_t2t"]
 
 STATUS_NAMES = {QS_EINVAL: "QS_EINVAL", QS_ECUDA: "QS_ECUDA", QS_ENONFINITE: "QS_ENONFINITE", QS_ESTATE: "QS_ESTATE",
                 QS_EUNSUPPORTED: "QS_EUNSUPPORTED", QS_EABI: "QS_EABI"}
 
 # every symbol include/quadsim.h declares (tests/test_abi.py checks the library exports each one)
 EXPORTS = ["qs_abi_version", "qs_state_layout", "qs_create", "qs_destroy", "qs_last_error", "qs_bind_state", "qs_bind_models", "qs_bind_terminal_obs", "qs_bind_info",
-           "qs_set_noise_injection", "qs_set_goal_injection", "qs_reset", "qs_observe", "qs_step", "qs_step_k", "qs_dynamics_step", "qs_step_host", "qs_get_stats",
+           "qs_set_noise_injection", "qs_set_goal_injection", "qs_reset", "qs_observe", "qs_step", "qs_step_k", "qs_dynamics_step", "qs_affine_fg", "qs_step_host", "qs_get_stats",
            "qs_stats_device_ptr", "qs_check", "qs_get_clock", "qs_set_clock", "qs_launch_count", "qs_last_variant", "qs_last_host_path"]
 
 
@@ -41,7 +45,7 @@ class QsModel(C.Structure):
                 ("damp_time_up", C.c_double), ("damp_time_down", C.c_double),
                 ("vel_damp", C.c_double), ("damp_omega_quadratic", C.c_double),
                 ("ou_theta", C.c_double), ("ou_sigma", C.c_double), ("arm", C.c_double), ("omega_max", C.c_double),
-                ("gravity", C.c_double), ("thrust_to_weight", C.c_double), ("Jinv", (C.c_double * 4) * 4)]
+                ("gravity", C.c_double), ("thrust_to_weight", C.c_double), ("torque_to_thrust", C.c_double), ("Jinv", (C.c_double * 4) * 4)]
 
 
 class QsReward(C.Structure):
@@ -65,7 +69,8 @@ class QsConfig(C.Structure):
                 ("dim_mode", C.c_int32), ("sim_steps", C.c_int32), ("ep_len", C.c_int32), ("per_env_goal", C.c_int32),
                 ("resample_goal", C.c_int32), ("excite", C.c_int32), ("_pad", C.c_int32), ("dt", C.c_double), ("svd_period", C.c_double), ("goal", C.c_double * 3),
                 ("spawn_box", C.c_double), ("spawn_z_min", C.c_double), ("room_box", (C.c_double * 3) * 2), ("max_init_vel", C.c_double),
-                ("max_init_omega", C.c_double), ("collision_k", C.c_double), ("use_formation", C.c_int32), ("per_env_model", C.c_int32),
+                ("max_init_omega", C.c_double), ("collision_k", C.c_double), ("pitch_max", C.c_double), ("roll_max", C.c_double),
+                ("yaw_max", C.c_double), ("t2w_std", C.c_double), ("t2t_std", C.c_double), ("use_formation", C.c_int32), ("per_env_model", C.c_int32),
                 ("formation", (C.c_double * 3) * 32), ("model", QsModel), ("reward", QsReward),
                 ("sense", QsSensorNoise)]
 
@@ -112,6 +117,7 @@ def load():
         "qs_step": (C.c_int, [H, P, P, P, P, P]),
         "qs_step_k": (C.c_int, [H, C.c_int, P, P, P, P, P]),
         "qs_dynamics_step": (C.c_int, [H, C.c_int, P, C.c_int, P]),
+        "qs_affine_fg": (C.c_int, [H, P, C.c_double, P, P, C.c_int64, P]),
         "qs_step_host": (C.c_int, [H, P, P, P, P, P]),
         "qs_get_stats": (C.c_int, [H, C.POINTER(C.c_double * 3), C.c_int, P]),
         "qs_stats_device_ptr": (C.c_int, [H, C.POINTER(C.c_void_p)]),

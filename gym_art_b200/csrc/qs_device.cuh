@@ -17,7 +17,9 @@ namespace qs {
 
 constexpr int BLOCK = 128;           // threads per CTA = envs per CTA
 constexpr int MAX_OBS = 25;
-constexpr int OBS_Z = 30, RESET_Z = 48, INFO_DIM = 48, MODEL_ROWS = 14;
+constexpr int OBS_Z = 33, RESET_Z = 51, INFO_DIM = 48, MODEL_ROWS = 14;
+constexpr int OBS_SCRATCH = 32;     // words build_obs leaves behind: 18 core | h | acc3 | act4 | quat4 | t2w | t2t
+enum InitMode { INIT_DEFAULT = 0, INIT_RANDOM = 1, INIT_PITCH_ROLL_RESTRICTED = 2 };   // QsInitMode
 
 enum Ctrl { CTRL_RAW = 0, CTRL_VERTICAL, CTRL_VERTPLANE, CTRL_SHIFTED, CTRL_OMEGA_THRUST, CTRL_VELOCITY_YAW, CTRL_MELLINGER };
 
@@ -69,7 +71,8 @@ struct Params {
   int k_steps, sim_steps, ep_len;
   int controller, zero_middle, n_agents, dim_mode;
   int obs_rel, obs_h, obs_acc, obs_act;
-  int init_random, auto_reset, sense_on, ou_on, gyro_bias_mode;
+  int obs_quat, obs_t2w, obs_t2t;     // get_state.py:276-382 (quaternion instead of R; thrust-to-weight / torque-to-thrust tail)
+  int init_random /* InitMode */, auto_reset, sense_on, ou_on, gyro_bias_mode;
   int resample_goal, excite;          // moving goals (quadrotor.py:1078-1081, :957-962); the goal row is then written back
   int dyn_controller, dyn_substeps;   // qs_dynamics_step
   int inject, need_rare;              // variant selection (host)
@@ -85,7 +88,9 @@ struct Params {
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
   R inertia[3], inv_inertia[3];
   R mass, inv_mass, lin, c_drag, c_roll, tau_up, tau_down, vel_damp, damp_omega_q;
-  R ou_theta, ou_sigma, arm, omega_max, gravity, t2w;
+  R ou_theta, ou_sigma, arm, omega_max, gravity, t2w, t2t;
+  R t2w_half_std, t2t_half_std;       // t2w_std / 2, t2t_std / 2 (get_state.py:334, :379)
+  R pitch_max, roll_max, yaw_max;     // INIT_PITCH_ROLL_RESTRICTED (quadrotor.py:243)
   R jinv[4][4];
   R room_lo[3], room_hi[3];
   R goal[3], spawn_box, spawn_z_min, max_init_vel, max_init_omega, coll_dist;
@@ -281,9 +286,11 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
   return c;
 }
 
-// Philox slot map (8 bits): obs groups 0..9 (step) / 16..25 (reset obs), reset draws 26..38, OU substeps 64+s
-enum Slot { SLOT_OBS = 0, SLOT_EXCITE = 12, SLOT_RESET_OBS = 16, SLOT_RESET_POS = 26, SLOT_RESET_VEL = 27, SLOT_RESET_OM = 28,
-            SLOT_RESET_UP = 29, SLOT_RESET_FWD = 30, SLOT_RESET_GOAL = 40, SLOT_OU = 64 };
+// Philox slot map (8 bits): obs groups 0..9 (step) / 16..25 (reset obs), t2w/t2t observation noise 11 (step) / 41 (reset),
+// reset draws 26..38, OU substeps 64+s
+enum Slot { SLOT_OBS = 0, SLOT_T2W = 11, SLOT_EXCITE = 12, SLOT_RESET_OBS = 16, SLOT_RESET_POS = 26, SLOT_RESET_VEL = 27, SLOT_RESET_OM = 28,
+            SLOT_RESET_UP = 29, SLOT_RESET_FWD = 30, SLOT_RESET_GOAL = 40, SLOT_RESET_T2W = 41,
+            SLOT_OU = 64 };
 
 template <typename R>
 struct Rng {
@@ -337,6 +344,7 @@ template <typename R> struct Mdl<R, false> {
   __device__ __forceinline__ R c_drag() const { return p.c_drag; }
   __device__ __forceinline__ R c_roll() const { return p.c_roll; }
   __device__ __forceinline__ R t2w() const { return p.t2w; }
+  __device__ __forceinline__ R t2t() const { return p.t2t; }
   __device__ __forceinline__ R vel_damp() const { return p.vel_damp; }
   __device__ __forceinline__ R damp_omega_q() const { return p.damp_omega_q; }
   __device__ __forceinline__ R jinv(int r, int c) const { return p.jinv[r][c]; }
@@ -367,6 +375,7 @@ template <typename R> struct Mdl<R, true> {
   __device__ __forceinline__ R t2w() const { return at(8, 3); }
   __device__ __forceinline__ R vel_damp() const { return at(9, 0); }
   __device__ __forceinline__ R damp_omega_q() const { return at(9, 1); }
+  __device__ __forceinline__ R t2t() const { return at(9, 2); }
   __device__ __forceinline__ R jinv(int r, int c) const { return at(10 + r, c); }
 };
 
@@ -849,6 +858,7 @@ struct NoiseSrc {
     } else {
       R t[4];
       int slot = (reset_obs ? SLOT_RESET_OBS : SLOT_OBS) + g;
+      if (g == 10) slot = reset_obs ? SLOT_RESET_T2W : SLOT_T2W;         // group 10: t2w, t2t (QS_Z_NT2W, QS_Z_NT2T)
       if (is_unif) rng.unif4(slot, t); else rng.normal4(slot, t);
       z[0] = t[0]; z[1] = t[1]; z[2] = t[2];
     }
@@ -893,9 +903,32 @@ __device__ __forceinline__ void rot2quat(const R* r, R* q) {            // senso
   }
 }
 
+// q <- q x quat_from_small_angle(theta), theta = quat_norm_std * n + quat_unif_range * u (sensor_noise.py:9-21, :134-151,
+// quad_utils.py:92-99)
 template <typename R, class T>
-__device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const NoiseSrc<R, T>& ns, bool reset_obs,
-                                          const R* act_prev, R* o, const R* zpre = nullptr) {
+__device__ __forceinline__ void noise_quat(const Params<R>& p, const NoiseSrc<R, T>& ns, bool reset_obs, R* q) {
+  R zn[3], zu[3];
+  ns.obs3(reset_obs, 6, false, zn);
+  ns.obs3(reset_obs, 7, true, zu);
+  R tx = p.sn_quat_std * zn[0] + p.sn_quat_unif * zu[0], ty = p.sn_quat_std * zn[1] + p.sn_quat_unif * zu[1];
+  R tz = p.sn_quat_std * zn[2] + p.sn_quat_unif * zu[2];
+  R qs = (tx * tx + ty * ty + tz * tz) / R(4);                          // sensor_noise.py:9-21
+  R t0, f;
+  if (qs < R(1)) { t0 = Mth<R>::sqrt(R(1) - qs); f = R(0.5); }
+  else { t0 = R(1) / Mth<R>::sqrt(R(1) + qs); f = R(0.5) * t0; }
+  R t1 = tx * f, t2 = ty * f, t3 = tz * f;
+  R tn = Mth<R>::sqrt(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3);
+  t0 /= tn; t1 /= tn; t2 /= tn; t3 /= tn;
+  R n0 = q[0] * t0 - q[1] * t1 - q[2] * t2 - q[3] * t3;                 // quad_utils.py:92-99
+  R n1 = q[0] * t1 + q[1] * t0 - q[2] * t3 + q[3] * t2;
+  R n2 = q[0] * t2 + q[1] * t3 + q[2] * t0 - q[3] * t1;
+  R n3 = q[0] * t3 - q[1] * t2 + q[2] * t1 + q[3] * t0;
+  q[0] = n0; q[1] = n1; q[2] = n2; q[3] = n3;
+}
+
+template <typename R, class T>
+__device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Mdl<R, T::PEM>& m, const NoiseSrc<R, T>& ns,
+                                          bool reset_obs, const R* act_prev, R* o, const R* zpre = nullptr) {
   const bool sense = T::SENSE >= 0 ? (T::SENSE != 0) : (p.sense_on != 0);
   R px = s.px, py = s.py, pz = s.pz, vx = s.vx, vy = s.vy, vz = s.vz, wx = s.wx, wy = s.wy, wz = s.wz;
   R rr[9];
@@ -903,7 +936,14 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
   for (int k = 0; k < 9; ++k) rr[k] = s.r[k];
   R acc[3] = {R(0), R(0), R(0)};
   const bool obs_acc = !T::PLAIN && p.obs_acc, obs_rel = !T::PLAIN && p.obs_rel;
+  const bool obs_quat = T::RARE && p.obs_quat;
   if (obs_acc) accelerometer(s, p, acc);
+  R qo[4] = {R(1), R(0), R(0), R(0)};
+  if (obs_quat) {                                                       // R2quat, quad_utils.py:101-109 (single branch)
+    R w = Mth<R>::sqrt(R(1) + s.r[0] + s.r[4] + s.r[8]) / R(2);
+    R w4 = R(4) * w;
+    qo[0] = w; qo[1] = (s.r[7] - s.r[5]) / w4; qo[2] = (s.r[2] - s.r[6]) / w4; qo[3] = (s.r[3] - s.r[1]) / w4;
+  }
   if (sense) {
     R z[3];
     if (zpre) { z[0] = zpre[0]; z[1] = zpre[1]; z[2] = zpre[2]; } else
@@ -935,31 +975,17 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
     // and the only case in the fast subset) the float64 reference's round trip returns R to 1e-15; an fp32 round trip
     // would only add rounding, so the fast kernels pass R through.
     if (!T::FASTM) {
-    R q[4];
-    rot2quat<R, T::FASTM>(s.r, q);
-    if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) {
-      R zn[3], zu[3];
-      ns.obs3(reset_obs, 6, false, zn);
-      ns.obs3(reset_obs, 7, true, zu);
-      R tx = p.sn_quat_std * zn[0] + p.sn_quat_unif * zu[0], ty = p.sn_quat_std * zn[1] + p.sn_quat_unif * zu[1];
-      R tz = p.sn_quat_std * zn[2] + p.sn_quat_unif * zu[2];
-      R qs = (tx * tx + ty * ty + tz * tz) / R(4);                      // sensor_noise.py:9-21
-      R t0, f;
-      if (qs < R(1)) { t0 = Mth<R>::sqrt(R(1) - qs); f = R(0.5); }
-      else { t0 = R(1) / Mth<R>::sqrt(R(1) + qs); f = R(0.5) * t0; }
-      R t1 = tx * f, t2 = ty * f, t3 = tz * f;
-      R tn = Mth<R>::sqrt(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3);
-      t0 /= tn; t1 /= tn; t2 /= tn; t3 /= tn;
-      R n0 = q[0] * t0 - q[1] * t1 - q[2] * t2 - q[3] * t3;             // quad_utils.py:92-99
-      R n1 = q[0] * t1 + q[1] * t0 - q[2] * t3 + q[3] * t2;
-      R n2 = q[0] * t2 + q[1] * t3 + q[2] * t0 - q[3] * t1;
-      R n3 = q[0] * t3 - q[1] * t2 + q[2] * t1 + q[3] * t0;
-      q[0] = n0; q[1] = n1; q[2] = n2; q[3] = n3;
-    }
-    R qw = q[0], qx = q[1], qy = q[2], qz = q[3];                       // quad_utils.py:82-87
-    rr[0] = R(1) - R(2) * qy * qy - R(2) * qz * qz; rr[1] = R(2) * qx * qy - R(2) * qz * qw; rr[2] = R(2) * qx * qz + R(2) * qy * qw;
-    rr[3] = R(2) * qx * qy + R(2) * qz * qw; rr[4] = R(1) - R(2) * qx * qx - R(2) * qz * qz; rr[5] = R(2) * qy * qz - R(2) * qx * qw;
-    rr[6] = R(2) * qx * qz - R(2) * qy * qw; rr[7] = R(2) * qy * qz + R(2) * qx * qw; rr[8] = R(1) - R(2) * qx * qx - R(2) * qy * qy;
+      if (obs_quat) {                                                   // rot.shape == (4,): quat x noise quaternion (:148-151)
+        if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) noise_quat<R, T>(p, ns, reset_obs, qo);
+      } else {
+        R q[4];
+        rot2quat<R, T::FASTM>(s.r, q);
+        if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) noise_quat<R, T>(p, ns, reset_obs, q);
+        R qw = q[0], qx = q[1], qy = q[2], qz = q[3];                   // quad_utils.py:82-87
+        rr[0] = R(1) - R(2) * qy * qy - R(2) * qz * qz; rr[1] = R(2) * qx * qy - R(2) * qz * qw; rr[2] = R(2) * qx * qz + R(2) * qy * qw;
+        rr[3] = R(2) * qx * qy + R(2) * qz * qw; rr[4] = R(1) - R(2) * qx * qx - R(2) * qz * qz; rr[5] = R(2) * qy * qz - R(2) * qx * qw;
+        rr[6] = R(2) * qx * qz - R(2) * qy * qw; rr[7] = R(2) * qy * qz + R(2) * qx * qw; rr[8] = R(1) - R(2) * qx * qx - R(2) * qy * qy;
+      }
     }
     if (obs_acc) {                                                      // :156-157
       R zs[3], zd[3];
@@ -986,18 +1012,48 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const No
   o[18] = pz;
   o[19] = acc[0]; o[20] = acc[1]; o[21] = acc[2];
   o[22] = act_prev[0]; o[23] = act_prev[1]; o[24] = act_prev[2]; o[25] = act_prev[3];
+  if (T::RARE) {
+    o[26] = qo[0]; o[27] = qo[1]; o[28] = qo[2]; o[29] = qo[3];
+    o[30] = R(0); o[31] = R(0);
+    if (p.obs_t2w) {            // get_state.py:334-337, :379-382: drawn by the builder itself, SensorNoise bypassed or not
+      R z[3];
+      ns.obs3(reset_obs, 10, false, z);
+      R w = m.t2w(), sc = p.t2w_half_std * w;
+      R nw = clampr(w + (sc < R(0) ? -sc : sc) * z[0], R(1.5), R(10));              // quadrotor.py:707-708
+      o[30] = (nw - R(1.5)) / (R(10) - R(1.5));
+      if (p.obs_t2t) {
+        w = m.t2t(); sc = p.t2t_half_std * w;
+        nw = clampr(w + (sc < R(0) ? -sc : sc) * z[1], R(0.005), R(1));             // quadrotor.py:711-712
+        o[31] = (nw - R(0.005)) / (R(1) - R(0.005));
+      }
+    }
+  }
 }
 
 // writes one env's observation row into the CTA's shared tile in final [obs_dim] order
-template <typename R, bool PLAIN = false>
+template <typename R, bool PLAIN = false, bool EXT = true>
 __device__ __forceinline__ void obs_to_tile(const Params<R>& p, const R* o, R* row) {
+  if (PLAIN) {
 #pragma unroll
-  for (int k = 0; k < 18; ++k) row[k] = o[k];
-  if (PLAIN) return;
+    for (int k = 0; k < 18; ++k) row[k] = o[k];
+    return;
+  }
   int n = 18;
+  if (EXT && p.obs_quat) {      // xyz vxyz quat omega: the quaternion takes the place of the nine matrix entries
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[k] = o[k];
+    row[6] = o[26]; row[7] = o[27]; row[8] = o[28]; row[9] = o[29];
+    row[10] = o[15]; row[11] = o[16]; row[12] = o[17];
+    n = 13;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 18; ++k) row[k] = o[k];
+  }
   if (p.obs_h) row[n++] = o[18];
   if (p.obs_acc) { row[n] = o[19]; row[n + 1] = o[20]; row[n + 2] = o[21]; n += 3; }
-  if (p.obs_act) { row[n] = o[22]; row[n + 1] = o[23]; row[n + 2] = o[24]; row[n + 3] = o[25]; }
+  if (p.obs_act) { row[n] = o[22]; row[n + 1] = o[23]; row[n + 2] = o[24]; row[n + 3] = o[25]; n += 4; }
+  if (EXT && p.obs_t2w) row[n++] = o[30];
+  if (EXT && p.obs_t2t) row[n++] = o[31];
 }
 
 // coalesced copy of the CTA's [BLOCK][obs_dim] tile to global memory
@@ -1044,7 +1100,31 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
   }
   if (z < p.spawn_z_min) z = p.spawn_z_min;                             // :1094 (0.25)
   s.px = x; s.py = y; s.pz = z;
-  if (p.init_random) {                                                  // :1113-1115 -> :227-239
+  const bool restricted = T::RARE && p.init_random == INIT_PITCH_ROLL_RESTRICTED;
+  if (T::RARE && p.init_random && p.dim_mode != 3) {                    // :1101-1110 (rand() = (1 + u) / 2 of a unit draw)
+    R a[4], b[4];
+    if (T::INJECT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = ns.reset_at(4 + k); b[k] = ns.reset_at(8 + k); }
+    } else {
+      ns.rng.unif4(SLOT_RESET_VEL, a);
+      ns.rng.unif4(SLOT_RESET_OM, b);
+    }
+    R vm = p.max_init_vel, om = p.max_init_omega;
+    s.wx = s.wy = s.wz = R(0);
+    s.vx = s.vy = R(0);
+    R sp = R(0), cp = R(1);
+    if (p.dim_mode == 1) {
+      s.vz = vm * (R(0.5) + R(0.5) * a[3]);                             // :1103
+    } else {
+      s.wy = om * (R(0.5) + R(0.5) * b[3]);                             // :1105
+      s.vx = vm * (R(0.5) + R(0.5) * a[0]); s.vz = vm * (R(0.5) + R(0.5) * a[2]);   // :1106-1107
+      Mth<R>::sincos(PI * (R(0.5) + R(0.5) * u[3]), &sp, &cp);          // :1108-1109
+    }
+    s.r[0] = cp; s.r[1] = R(0); s.r[2] = -sp;                           // :1110
+    s.r[3] = R(0); s.r[4] = R(1); s.r[5] = R(0);
+    s.r[6] = sp; s.r[7] = R(0); s.r[8] = cp;
+  } else if (p.init_random) {                                           // :1113-1115 -> :227-239 / :243-259
     R a[4], b[4], up[4], fw[4];
     if (T::INJECT) {
 #pragma unroll
@@ -1054,7 +1134,7 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
     } else {
       ns.rng.unif4(SLOT_RESET_VEL, a);
       ns.rng.unif4(SLOT_RESET_OM, b);
-      ns.rng.normal4(SLOT_RESET_UP, up);
+      if (restricted) ns.rng.unif4(SLOT_RESET_UP, up); else ns.rng.normal4(SLOT_RESET_UP, up);
     }
     R vm = p.max_init_vel, om = p.max_init_omega;
     R vx = vm * a[0], vy = vm * a[1], vz = vm * a[2];                   // :230
@@ -1065,6 +1145,15 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
     R wmag = om * (R(0.5) + R(0.5) * b[3]);                             // :235
     f = wmag / (Mth<R>::sqrt(wx * wx + wy * wy + wz * wz) + R(1e-6));   // :236
     s.wx = f * wx; s.wy = f * wy; s.wz = f * wz;
+    if (restricted) {           // :254-257: pitch, roll, yaw ~ U(-max, max); euler2mat 'sxyz' = Rz(yaw) Ry(pitch) Rx(roll)
+      R si, ci, sj, cj, sk, ck;
+      Mth<R>::sincos(p.roll_max * up[1], &si, &ci);
+      Mth<R>::sincos(p.pitch_max * up[0], &sj, &cj);
+      Mth<R>::sincos(p.yaw_max * up[2], &sk, &ck);
+      s.r[0] = cj * ck; s.r[1] = sj * si * ck - ci * sk; s.r[2] = sj * ci * ck + si * sk;
+      s.r[3] = cj * sk; s.r[4] = sj * si * sk + ci * ck; s.r[5] = sj * ci * sk - si * ck;
+      s.r[6] = -sj; s.r[7] = cj * si; s.r[8] = cj * ci;
+    } else {
     R ux = up[0], uy = up[1], uz = up[2];                               // quad_utils.py:47-57
     normalize3(ux, uy, uz);
     R fx, fy, fz;
@@ -1084,6 +1173,7 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
     s.r[0] = fx; s.r[1] = lx; s.r[2] = ux;                              // column_stack([fwd, left, up])
     s.r[3] = fy; s.r[4] = ly; s.r[5] = uy;
     s.r[6] = fz; s.r[7] = lz; s.r[8] = uz;
+    }
   } else {                                                              // :1118-1126
     s.vx = s.vy = s.vz = R(0);
     s.wx = s.wy = s.wz = R(0);
@@ -1283,13 +1373,13 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     const bool walk = T::RARE && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
     const bool resetting = done && p.auto_reset;
     const bool want_term = resetting && p.term_obs != nullptr;          // the obs the reference returns on its done step (:988)
-    if ((last && (!resetting || want_term)) || walk) build_obs<R, T>(s, p, ns, false, a_prev, o, (PRE && sense) ? dr.zobs : nullptr);
+    if ((last && (!resetting || want_term)) || walk) build_obs<R, T>(s, p, m, ns, false, a_prev, o, (PRE && sense) ? dr.zobs : nullptr);
     if (done) {
       if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
       if (resetting) {
-        if (want_term && last && active) obs_to_tile<R, T::PLAIN>(p, o, p.term_obs + i * (T::PLAIN ? 18 : p.obs_dim));
+        if (want_term && last && active) obs_to_tile<R, T::PLAIN, T::RARE>(p, o, p.term_obs + i * (T::PLAIN ? 18 : p.obs_dim));
         reset_env<R, T>(s, p, ns);
-        if (last || walk) build_obs<R, T>(s, p, ns, true, s.pa, o);     // :1143 (actions[1] = 0 after reset)
+        if (last || walk) build_obs<R, T>(s, p, m, ns, true, s.pa, o);     // :1143 (actions[1] = 0 after reset)
       }
     }
   }
@@ -1333,7 +1423,7 @@ __global__ void __launch_bounds__(BLOCK) env_step_kernel(const __grid_constant__
 
   St<R> s;
   load_state<R, T>(s, p, i, active);
-  R o[26];
+  R o[OBS_SCRATCH];
   StepOut<R> out;
   run_steps<R, T>(s, p, i, active, nullptr, p.clock->svd_timer, p.clock->step, o, out);
 
@@ -1658,7 +1748,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
 #ifdef QS_PHASE_TIMING
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1) : "f"(s.px + s.r[8] + a0[0] + s.cd[3]) : "memory");   // data arrived
 #endif
-    R o[26];
+    R o[OBS_SCRATCH];
     StepOut<R> out;
     run_steps<R, T>(s, p, i, active, has_act ? a0 : nullptr, svd_t0, step0, o, out, &pre);
     svd_end = out.svd_t;
@@ -1683,7 +1773,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       // its own 32 observation rows.  (Same run_steps instance as the pipelined path: results do not depend on which
       // path a batch size selects.)
       float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
-      obs_to_tile<R, T::PLAIN>(p, o, wtile + lane * obs_dim);
+      obs_to_tile<R, T::PLAIN, T::RARE>(p, o, wtile + lane * obs_dim);
       __syncwarp();
       const long long warp_first = i - lane;
       long long wrows = p.end - warp_first;
@@ -1720,7 +1810,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     }
     // observation rows: registers -> shared tile -> one bulk store per CTA
     float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
-    obs_to_tile<R, T::PLAIN>(p, o, tile_obs + tid * obs_dim);
+    obs_to_tile<R, T::PLAIN, T::RARE>(p, o, tile_obs + tid * obs_dim);
     if (multi) {
       fence_proxy_async();                       // generic-proxy tile writes -> async proxy
       if (tid == 0) bulk_wait_read0();           // last tile's store has drained the OTHER stage (it had a whole tile)
@@ -1762,8 +1852,9 @@ __global__ void __launch_bounds__(BLOCK) env_reset_kernel(const __grid_constant_
     NoiseSrc<R, T> ns(p, i);
     ns.begin_step(p.clock->step);
     reset_env<R, T>(s, p, ns);
-    R o[26];
-    build_obs<R, T>(s, p, ns, true, s.pa, o);
+    R o[OBS_SCRATCH];
+    const Mdl<R, T::PEM> m(p, i);
+    build_obs<R, T>(s, p, m, ns, true, s.pa, o);
     store_state<R, T>(s, p, i);
     obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
   }
@@ -1797,8 +1888,9 @@ __global__ void __launch_bounds__(BLOCK) env_observe_kernel(const __grid_constan
     } else {
       s.fresh = true;                 // (0, 0, GRAV), the reading set_state leaves behind (quadrotor.py:221)
     }
-    R o[26];
-    build_obs<R, T>(s, p, ns, true, s.pa, o);
+    R o[OBS_SCRATCH];
+    const Mdl<R, T::PEM> m(p, i);
+    build_obs<R, T>(s, p, m, ns, true, s.pa, o);
     if (T::RARE) { if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0)); }   // the bias walks on
     obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
   }
@@ -1851,6 +1943,99 @@ __global__ void __launch_bounds__(BLOCK) dynamics_step_kernel(const __grid_const
   finish_clock(p, svd_t, 1ull);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// QuadrotorDynamics.F(s, dt) / G(s) (quadrotor.py:461-518): the affine representation s' = dt (F(s) + G(s) u) for n
+// caller-supplied states s[n][21] = xyz, Vxyz, R (row-major), omega, goal.  One thread per state; the 21-word rows go
+// through shared memory so that every global access is coalesced.  G is 21 x C with C = 1 / 2 / 4 controls (control_mx,
+// :121-129); only its velocity and body-rate rows are non-zero.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct AffineArgs {
+  const R* s;
+  R* F;
+  R* G;
+  long long n;
+  R dt;
+  int C;
+};
+
+template <typename R, bool PEM>
+__global__ void __launch_bounds__(BLOCK) affine_fg_kernel(const __grid_constant__ Params<R> p, const AffineArgs<R> a) {
+  __shared__ R tile[BLOCK * 21];          // states in, then F out
+  __shared__ R gnz[BLOCK * 24];           // the six non-zero rows of G (x up to 4 controls) per state
+  const long long first = (long long)blockIdx.x * BLOCK;
+  long long rows = a.n - first;
+  if (rows > BLOCK) rows = BLOCK;
+  const int tid = threadIdx.x;
+  const int total = (int)rows * 21;
+  for (int k = tid; k < total; k += BLOCK) tile[k] = a.s[first * 21 + k];
+  __syncthreads();
+  const Mdl<R, PEM> m(p, 0);
+  const int C = a.C;
+  R f[21];
+  if (tid < rows) {
+    const R* x = tile + tid * 21;
+    const R vx = x[3], vy = x[4], vz = x[5];
+    R r[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[k] = x[6 + k];
+    const R ox = x[15], oy = x[16], oz = x[17];
+    f[0] = vx; f[1] = vy; f[2] = vz;                                                       // :471
+    const R vd = R(1) - m.vel_damp();
+    f[3] = (vd * vx - vx) / a.dt + R(0); f[4] = (vd * vy - vy) / a.dt + R(0); f[5] = (vd * vz - vz) / a.dt + R(-9.81);   // :475
+    const R wx = r[0] * ox + r[1] * oy + r[2] * oz, wy = r[3] * ox + r[4] * oy + r[5] * oz;  // :479 body -> world
+    const R wz = r[6] * ox + r[7] * oy + r[8] * oz;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                                                          // :481-484 dR = [w]x R
+      f[6 + c] = -wz * r[3 + c] + wy * r[6 + c];
+      f[9 + c] = wz * r[c] - wx * r[6 + c];
+      f[12 + c] = -wy * r[c] + wx * r[3 + c];
+    }
+    const R iwx = m.inertia(0) * ox, iwy = m.inertia(1) * oy, iwz = m.inertia(2) * oz;
+    const R gx = (-oy) * iwz - (-oz) * iwy, gy = (-oz) * iwx - (-ox) * iwz, gz = (-ox) * iwy - (-oy) * iwx;   // :488
+    const R dqx = R(1) - clampr(m.damp_omega_q() * (ox * ox), R(0), R(1));                  // :489
+    const R dqy = R(1) - clampr(m.damp_omega_q() * (oy * oy), R(0), R(1));
+    const R dqz = R(1) - clampr(m.damp_omega_q() * (oz * oz), R(0), R(1));
+    f[15] = dqx * (m.inv_inertia(0) * gx); f[16] = dqy * (m.inv_inertia(1) * gy); f[17] = dqz * (m.inv_inertia(2) * gz);   // :490
+    f[18] = f[19] = f[20] = R(0);
+    // G (:501-518): base matrix 21 x 4, then @ control_mx
+    R g[6][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const R tm = m.thrust_max(k);
+      g[0][k] = (r[2] / m.mass()) * tm; g[1][k] = (r[5] / m.mass()) * tm; g[2][k] = (r[8] / m.mass()) * tm;   // :509
+      g[3][k] = dqx * (m.inv_inertia(0) * (tm * m.pcx(k)));                                 // :188-191, :516
+      g[4][k] = dqy * (m.inv_inertia(1) * (tm * m.pcy(k)));
+      g[5][k] = dqz * (m.inv_inertia(2) * m.tz(k));
+    }
+    R* go = gnz + tid * 24;
+#pragma unroll
+    for (int row = 0; row < 6; ++row) {
+      if (C == 4) { go[row * 4] = g[row][0]; go[row * 4 + 1] = g[row][1]; go[row * 4 + 2] = g[row][2]; go[row * 4 + 3] = g[row][3]; }
+      else if (C == 2) { go[row * 2] = g[row][0] + g[row][1]; go[row * 2 + 1] = g[row][2] + g[row][3]; }
+      else go[row] = ((g[row][0] + g[row][1]) + g[row][2]) + g[row][3];
+    }
+  }
+  __syncthreads();                         // every state of the tile has been read
+  if (tid < rows) {
+#pragma unroll
+    for (int k = 0; k < 21; ++k) tile[tid * 21 + k] = f[k];
+  }
+  __syncthreads();
+  if (a.F != nullptr)
+    for (int k = tid; k < total; k += BLOCK) a.F[first * 21 + k] = tile[k];
+  if (a.G != nullptr) {
+    const int per = 21 * C;
+    for (int k = tid; k < (int)rows * per; k += BLOCK) {
+      const int st = k / per, rem = k - st * per, row = rem / C, c = rem - row * C;
+      R v = R(0);
+      if (row >= 3 && row < 6) v = gnz[st * 24 + (row - 3) * C + c];
+      else if (row >= 15 && row < 18) v = gnz[st * 24 + (row - 12) * C + c];
+      a.G[first * per + k] = v;
+    }
+  }
+}
+
 // advances the clock by one env step on behalf of a set of read-only (clock_advance = 0) chunk launches
 template <typename R>
 __global__ void clock_advance_kernel(const __grid_constant__ Params<R> p) {
@@ -1868,6 +2053,7 @@ template <typename R> cudaError_t launch_reset(const Params<R>& p, cudaStream_t 
 template <typename R> cudaError_t launch_dynamics(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_observe(const Params<R>& p, cudaStream_t st);
 template <typename R> cudaError_t launch_clock_advance(const Params<R>& p, cudaStream_t st);
+template <typename R> cudaError_t launch_affine(const Params<R>& p, const AffineArgs<R>& a, cudaStream_t st);
 // fp32 fast subset (qs_fast.inl, one translation unit per controller x noise source)
 #define QS_DECL_FAST(name) cudaError_t name(const Params<float>& p, cudaStream_t st, const char** variant_name)
 QS_DECL_FAST(launch_fast_raw_philox);

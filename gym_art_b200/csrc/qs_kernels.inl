@@ -78,6 +78,14 @@ cudaError_t launch_observe<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) {
 }
 
 template <>
+cudaError_t launch_affine<QS_REAL>(const Params<QS_REAL>& p, const AffineArgs<QS_REAL>& a, cudaStream_t st) {
+  const unsigned grid = (unsigned)((a.n + BLOCK - 1) / BLOCK);
+  if (p.models != nullptr) affine_fg_kernel<QS_REAL, true><<<grid, BLOCK, 0, st>>>(p, a);
+  else affine_fg_kernel<QS_REAL, false><<<grid, BLOCK, 0, st>>>(p, a);
+  return cudaGetLastError();
+}
+
+template <>
 cudaError_t launch_clock_advance<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st) {
   clock_advance_kernel<QS_REAL><<<1, 1, 0, st>>>(p);
   return cudaGetLastError();

@@ -16,7 +16,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-const int kObsDims[QS_OBS_COUNT] = {18, 19, 18, 19, 25, 22};
+const int kObsDims[QS_OBS_COUNT] = {18, 19, 18, 19, 25, 22, 13, 13, 14, 19, 19, 20};
 const int kActDims[QS_CTRL_COUNT] = {4, 1, 2, 4, 4, 4, 4};
 const int kHostStreams = 4;
 
@@ -100,7 +100,8 @@ int validate(const QsConfig* c, std::string* why) {
   if (c->obs_repr < 0 || c->obs_repr >= QS_OBS_COUNT) { *why = "unknown obs_repr"; return QS_EINVAL; }
   if (c->noise_mode != QS_NOISE_PHILOX && c->noise_mode != QS_NOISE_INJECTED) { *why = "unknown noise_mode"; return QS_EINVAL; }
   if (c->dim_mode < 1 || c->dim_mode > 3) { *why = "QuadEnv: Unknown dimensionality mode"; return QS_EINVAL; }   // quadrotor.py:131
-  if (c->dim_mode != 3 && c->init_random_state) { *why = "init_random_state is built for dim_mode 3D only"; return QS_EUNSUPPORTED; }
+  if (c->init_random_state < QS_INIT_DEFAULT || c->init_random_state > QS_INIT_PITCH_ROLL_RESTRICTED) { *why = "unknown init_random_state (QsInitMode)"; return QS_EINVAL; }
+  if (c->init_random_state == QS_INIT_PITCH_ROLL_RESTRICTED && c->dim_mode != 3) { *why = "QS_INIT_PITCH_ROLL_RESTRICTED is a 3D law"; return QS_EINVAL; }
   if (c->sim_steps < 1 || c->sim_steps > 64) { *why = "sim_steps must be in [1, 64]"; return QS_EINVAL; }
   if (c->ep_len < 0 || c->ep_len > (1 << 23)) { *why = "ep_len out of range"; return QS_EINVAL; }
   if (!(c->dt > 0.0)) { *why = "dt must be positive"; return QS_EINVAL; }
@@ -140,6 +141,7 @@ bool need_rare(const QsHandle* h) {
   if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
                     s.gyro_norm_std != 0.0)) return true;
   if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
+  if (c.obs_repr >= QS_OBS_XYZ_VXYZ_QUAT_OMEGA || c.init_random_state == QS_INIT_PITCH_ROLL_RESTRICTED) return true;
   // swarms (and the log-distance reward that comes with them) and per-env models have specialised kernels for the
   // common step shape only
   const bool plain = c.sim_steps == 2 && h->lay.obs_dim == 18 && h->lay.row_prev_action < 0 &&
@@ -185,8 +187,16 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.obs_dim = h->lay.obs_dim; p.act_dim = h->lay.act_dim;
   p.k_steps = 1; p.sim_steps = c.sim_steps; p.ep_len = c.ep_len;
   p.controller = c.controller; p.zero_middle = c.zero_middle; p.n_agents = c.n_agents; p.dim_mode = c.dim_mode;
-  p.obs_rel = (c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA || c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_H);
-  p.obs_h = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_H || c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_H);
+  p.obs_rel = (c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA || c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_H ||
+               c.obs_repr == QS_OBS_XYZR_VXYZR_QUAT_OMEGA || c.obs_repr == QS_OBS_XYZR_VXYZR_QUAT_OMEGA_H ||
+               c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_T2W);
+  p.obs_h = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_H || c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_H ||
+             c.obs_repr == QS_OBS_XYZR_VXYZR_QUAT_OMEGA_H);
+  p.obs_quat = (c.obs_repr == QS_OBS_XYZ_VXYZ_QUAT_OMEGA || c.obs_repr == QS_OBS_XYZR_VXYZR_QUAT_OMEGA ||
+                c.obs_repr == QS_OBS_XYZR_VXYZR_QUAT_OMEGA_H);
+  p.obs_t2w = (c.obs_repr == QS_OBS_XYZR_VXYZR_R_OMEGA_T2W || c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_T2W ||
+               c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_T2W_T2T);
+  p.obs_t2t = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_T2W_T2T);
   p.obs_acc = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT);
   p.obs_act = (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT || c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_ACT);
   p.init_random = c.init_random_state; p.auto_reset = c.auto_reset;
@@ -228,6 +238,8 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.vel_damp = (R)m.vel_damp; p.damp_omega_q = (R)m.damp_omega_quadratic;
   p.ou_theta = (R)m.ou_theta; p.ou_sigma = (R)m.ou_sigma;
   p.arm = (R)m.arm; p.omega_max = (R)m.omega_max; p.gravity = (R)m.gravity; p.t2w = (R)m.thrust_to_weight;
+  p.t2t = (R)m.torque_to_thrust; p.t2w_half_std = (R)(c.t2w_std / 2.0); p.t2t_half_std = (R)(c.t2t_std / 2.0);
+  p.pitch_max = (R)c.pitch_max; p.roll_max = (R)c.roll_max; p.yaw_max = (R)c.yaw_max;
   p.spawn_box = (R)c.spawn_box; p.spawn_z_min = (R)c.spawn_z_min; p.max_init_vel = (R)c.max_init_vel; p.max_init_omega = (R)c.max_init_omega;
   p.coll_dist = (R)(c.collision_k * 2.0 * m.arm);
   p.formation_on = (c.use_formation && c.n_agents > 1) ? 1 : 0;
@@ -501,6 +513,30 @@ int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_sub
     e = qs::launch_dynamics<double>(p, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return fail(h, QS_ECUDA, "dynamics_step launch: %s", cudaGetErrorString(e));
+  h->launches++;
+  return QS_OK;
+}
+
+int qs_affine_fg(QsHandle* h, const void* s, double dt, void* F, void* G, int64_t n, qs_stream_t stream) {
+  if (!h) return QS_EINVAL;
+  if (!s) return fail(h, QS_EINVAL, "s is NULL");
+  if (n < 0) return fail(h, QS_EINVAL, "n must be >= 0");
+  if (!(dt > 0.0)) return fail(h, QS_EINVAL, "dt must be positive");
+  if (h->cfg.per_env_model && !h->models) return fail(h, QS_ESTATE, "model buffer not bound (qs_bind_models)");
+  if (n == 0 || (!F && !G)) return QS_OK;
+  QS_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int C = h->cfg.dim_mode == 1 ? 1 : (h->cfg.dim_mode == 2 ? 2 : 4);           // control_mx, quadrotor.py:121-129
+  cudaError_t e;
+  if (h->cfg.dtype == QS_F32) {
+    qs::Params<float> p; fill_params<float>(h, &p);
+    qs::AffineArgs<float> a = {(const float*)s, (float*)F, (float*)G, (long long)n, (float)dt, C};
+    e = qs::launch_affine<float>(p, a, (cudaStream_t)stream);
+  } else {
+    qs::Params<double> p; fill_params<double>(h, &p);
+    qs::AffineArgs<double> a = {(const double*)s, (double*)F, (double*)G, (long long)n, dt, C};
+    e = qs::launch_affine<double>(p, a, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return fail(h, QS_ECUDA, "affine_fg launch: %s", cudaGetErrorString(e));
   h->launches++;
   return QS_OK;
 }

@@ -171,7 +171,7 @@ def model_rows_batch(b, dt):
     r[7, :, 2] = 0.2 * b["thrust_noise_ratio"]
     r[7, :, 3] = np.linalg.norm(mxyz[:, :2], axis=1)
     r[8] = np.stack([b["linearity"], b["C_drag"], b["C_roll"], b["thrust_to_weight"]], axis=1)
-    r[9, :, 0], r[9, :, 1] = b["vel_damp"], b["damp_omega_quadratic"]
+    r[9, :, 0], r[9, :, 1], r[9, :, 2] = b["vel_damp"], b["damp_omega_quadratic"], b["torque_to_thrust"]
     r[10:14] = np.transpose(Jinv, (1, 0, 2))
     return r
 

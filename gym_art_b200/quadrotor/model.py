@@ -72,7 +72,7 @@ class ModelConstants(object):
         r[7] = [min(1.0, 4.0 * dt / (self.motor_damp_time_up + EPS)), min(1.0, 4.0 * dt / (self.motor_damp_time_down + EPS)),
                 self.ou_sigma, self.arm]                                                   # quadrotor.py:284-288
         r[8] = [self.motor_linearity, self.C_rot_drag, self.C_rot_roll, self.thrust_to_weight]
-        r[9, :2] = [self.vel_damp, self.damp_omega_quadratic]
+        r[9, :3] = [self.vel_damp, self.damp_omega_quadratic, self.torque_to_thrust]
         r[10:14] = self.Jinv
         return r
 
@@ -95,4 +95,5 @@ class ModelConstants(object):
         m.ou_theta, m.ou_sigma = self.ou_theta, self.ou_sigma
         m.arm, m.omega_max, m.gravity = self.arm, self.omega_max, self.gravity
         m.thrust_to_weight = self.thrust_to_weight
+        m.torque_to_thrust = self.torque_to_thrust
         return m

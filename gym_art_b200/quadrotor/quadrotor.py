@@ -248,6 +248,34 @@ class QuadrotorDynamics(object):
         tmp.close()
         return tuple(v[0] for v in out) if self.num_envs == 1 else out
 
+    def pitch_roll_restricted_random_state(self, box, vel_max=15.0, omega_max=2 * np.pi, pitch_max=0.5, roll_max=0.5,
+                                           yaw_max=3.14):
+        """quadrotor.py:243-259, drawn by the device's spawn sampler like random_state: attitude from Euler angles
+        U(-pitch_max, pitch_max), U(-roll_max, roll_max), U(-yaw_max, yaw_max), R = Rz(yaw) Ry(pitch) Rx(roll)."""
+        tmp = QuadVecEnv(self.num_envs, dynamics_params=self.model_params, init_random_state="pitch_roll_restricted",
+                         goal=(0., 0., 0.), box=float(box), device=self._device, dtype=self._dtype, auto_reset=False,
+                         seed=int(np.random.randint(0, 2 ** 31 - 1)), spawn_z_min=-1e30, max_init_vel=vel_max,
+                         max_init_omega=omega_max, pitch_max=pitch_max, roll_max=roll_max, yaw_max=yaw_max)
+        tmp.reset()
+        out = tuple(tmp.get_field(k).double().cpu().numpy() for k in ("pos", "vel", "rot", "omega"))
+        tmp.close()
+        return tuple(v[0] for v in out) if self.num_envs == 1 else out
+
+    # ---- affine representation s' = dt (F(s) + G(s) u)  (quadrotor.py:457-518) --------------------------
+    def F(self, s, dt):
+        """Unforced dynamics F(s, dt) of one state vector s[21] = xyz, Vxyz, R, omega, goal (:461-497), or of a batch [n, 21]."""
+        s = np.asarray(s, dtype=np.float64)
+        F, _ = self._vec.affine_fg(s.reshape(-1, 21), dt, want_G=False)
+        out = F.double().cpu().numpy()
+        return out[0] if s.ndim == 1 else out
+
+    def G(self, s):
+        """Forced dynamics G(s) [21, C] (:501-518), C = columns of control_mx for this dim_mode; a batch gives [n, 21, C]."""
+        s = np.asarray(s, dtype=np.float64)
+        _, G = self._vec.affine_fg(s.reshape(-1, 21), 1.0, want_F=False)
+        out = G.double().cpu().numpy()
+        return out[0] if s.ndim == 1 else out
+
     def state_vector(self):                                                                  # :520-525
         return np.concatenate([self.pos, self.vel, self.rot.flatten(), self.omega])
 
@@ -411,7 +439,8 @@ class QuadrotorEnv(object):
                   gravity=self.gravity, device=self._device, dtype=self._dtype, seed=self._philox_seed,
                   noise_mode=self._noise_mode, auto_reset=False, info=True, multi_reward=self._multi_reward,
                   goals=np.asarray(self.goal, dtype=np.float64).reshape(1, 3), box=self.box, host_mapped=True,
-                  resample_goal=self.resample_goal, excite=self.excite, dynamics_simplification=self.dynamics_simplification)
+                  resample_goal=self.resample_goal, excite=self.excite, dynamics_simplification=self.dynamics_simplification,
+                  t2w_std=self.t2w_std, t2t_std=self.t2t_std)
         vec = QuadVecEnv(1, **kw)
         if old_state is not None:
             if old_state.shape == vec.state.shape:      # OU state, gyro bias and the SVD timer survive a model change

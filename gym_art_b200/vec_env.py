@@ -68,7 +68,8 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
                 rew_coeff=None, sense_noise=None, device_index=0, dtype="float32", seed=0, noise_mode="philox",
                 auto_reset=True, n_agents=1, per_env_goal=False, env_id_offset=0, multi_reward=False, collision_k=1.0,
                 goal=(0., 0., 2.), box=2.0, spawn_z_min=0.25, max_init_vel=1., max_init_omega=2 * np.pi, formation=None,
-                per_env_model=False, resample_goal=False, excite=False):
+                per_env_model=False, resample_goal=False, excite=False, t2w_std=0.005, t2t_std=0.0005, pitch_max=0.5,
+                roll_max=0.5, yaw_max=3.14):
     """Pure host function (no GPU): ctor arguments -> QsConfig.  Raises the reference's ValueErrors."""
     cfg = _lib.QsConfig()
     cfg.abi_version = _lib.QS_ABI_VERSION
@@ -87,7 +88,12 @@ def make_config(num_envs, model, controller="raw", raw_control_zero_middle=True,
         raise ValueError("QuadEnv: obs_repr %s is not one of the working representations %s" % (obs_repr, _lib.OBS_REPRS))
     cfg.obs_repr = _lib.OBS_REPRS.index(obs_repr)
     cfg.noise_mode = {"philox": _lib.QS_NOISE_PHILOX, "injected": _lib.QS_NOISE_INJECTED}[noise_mode]
-    cfg.init_random_state = int(bool(init_random_state))
+    # False / True (quadrotor.py:1100-1115), or "pitch_roll_restricted": the law of QuadrotorDynamics.pitch_roll_restricted_random_state
+    # (:243-259), which the reference env never selects itself
+    cfg.init_random_state = (_lib.QS_INIT_PITCH_ROLL_RESTRICTED if init_random_state == "pitch_roll_restricted"
+                             else (_lib.QS_INIT_RANDOM if init_random_state else _lib.QS_INIT_DEFAULT))
+    cfg.pitch_max, cfg.roll_max, cfg.yaw_max = float(pitch_max), float(roll_max), float(yaw_max)       # quadrotor.py:243
+    cfg.t2w_std, cfg.t2t_std = float(t2w_std), float(t2t_std)                                         # quadrotor.py:658
     cfg.auto_reset = int(bool(auto_reset))
     if dim_mode not in ("1D", "2D", "3D"):
         raise ValueError('QuadEnv: Unknown dimensionality mode %s' % dim_mode)       # quadrotor.py:131
@@ -154,7 +160,8 @@ class QuadVecEnv(object):
                  auto_reset=True, n_agents=1, goals=None, env_id_offset=0, multi_reward=False, collision_k=1.0,
                  info=False, goal=(0., 0., 2.), box=2.0, state=None, spawn_z_min=0.25, max_init_vel=1.,
                  max_init_omega=2 * np.pi, formation=None, per_env_dynamics=None, dyn_sampler_1=None, dyn_sampler_2=None,
-                 host_mapped=False, resample_goal=False, excite=False, dynamics_simplification=False, terminal_obs=False):
+                 host_mapped=False, resample_goal=False, excite=False, dynamics_simplification=False, terminal_obs=False,
+                 t2w_std=0.005, t2t_std=0.0005, pitch_max=0.5, roll_max=0.5, yaw_max=3.14):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -181,7 +188,8 @@ class QuadVecEnv(object):
             n_agents=n_agents, per_env_goal=goals is not None, env_id_offset=env_id_offset, multi_reward=multi_reward,
             collision_k=collision_k, goal=goal, box=box, spawn_z_min=spawn_z_min, max_init_vel=max_init_vel,
             max_init_omega=max_init_omega, formation=formation, per_env_model=per_env_dynamics is not None,
-            resample_goal=resample_goal, excite=excite)
+            resample_goal=resample_goal, excite=excite, t2w_std=t2w_std, t2t_std=t2t_std, pitch_max=pitch_max,
+            roll_max=roll_max, yaw_max=yaw_max)
         self.layout = _lib.state_layout(self.cfg)
         self.num_envs = int(num_envs)
         self.n_agents = int(n_agents)
@@ -234,7 +242,8 @@ class QuadVecEnv(object):
         rb = np.array([[-room_size, -room_size, 0.], [room_size, room_size, room_size]], dtype=np.float64)
         comp = {"xyz": (-(rb[1] - rb[0]), rb[1] - rb[0]), "vxyz": (-3. * np.ones(3), 3. * np.ones(3)), "R": (-np.ones(9), np.ones(9)),
                 "omega": (-40. * np.ones(3), 40. * np.ones(3)), "h": (np.zeros(1), rb[1][2] * np.ones(1)),
-                "acc": (-3. * GRAV * np.ones(3), 3. * GRAV * np.ones(3)), "act": (np.zeros(4), np.ones(4))}
+                "acc": (-3. * GRAV * np.ones(3), 3. * GRAV * np.ones(3)), "act": (np.zeros(4), np.ones(4)),
+                "quat": (-np.ones(4), np.ones(4)), "t2w": (np.zeros(1), 5. * np.ones(1)), "t2t": (np.zeros(1), np.ones(1))}
         comp["xyzr"], comp["vxyzr"] = comp["xyz"], comp["vxyz"]
         names = obs_repr.split("_")
         self.observation_space = Box(np.concatenate([comp[c][0] for c in names]), np.concatenate([comp[c][1] for c in names]),
@@ -426,7 +435,7 @@ class QuadVecEnv(object):
 
     # ---- noise injection (test mode) -----------------------------------------------------------------
     def set_noise(self, ou_z=None, obs_z=None, reset_z=None, goal_z=None):
-        """QS_NOISE_INJECTED: unit draws for the next reset()/step() calls; shapes [N,sim_steps,4], [N,30], [N,48]
+        """QS_NOISE_INJECTED: unit draws for the next reset()/step() calls; shapes [N,sim_steps,4], [N,QS_OBS_Z], [N,QS_RESET_Z]
         (+ goal_z [N,4] for the excite / resample_goal options)."""
         t = self.torch
 
@@ -538,6 +547,23 @@ class QuadVecEnv(object):
         n = self.sim_steps if n_substeps is None else int(n_substeps)
         _lib.check(self.lib.qs_dynamics_step(self._h, cid, None if a is None else a.data_ptr(), n, self._stream()), self._h)
         self._done_call()
+
+    def affine_fg(self, s, dt, want_F=True, want_G=True):
+        """QuadrotorDynamics.F(s, dt) / G(s) (quadrotor.py:461-518) for n states s [n, 21] = xyz, Vxyz, R (row-major), omega,
+        goal: returns (F [n, 21], G [n, 21, C]) device tensors, C = 1 / 2 / 4 controls for dim_mode 1D / 2D / 3D."""
+        t = self.torch
+        x = t.as_tensor(np.asarray(s) if not isinstance(s, t.Tensor) else s, dtype=self.tdtype, device=self.mem).reshape(-1, 21).contiguous()
+        n = int(x.shape[0])
+        C_ = {1: 1, 2: 2, 3: 4}[int(self.cfg.dim_mode)]
+        F = t.empty((n, 21), dtype=self.tdtype, device=self.mem, pin_memory=self.host_mapped) if want_F else None
+        G = t.empty((n, 21, C_), dtype=self.tdtype, device=self.mem, pin_memory=self.host_mapped) if want_G else None
+        if self.host_mapped:
+            x = x.pin_memory()
+        _lib.check(self.lib.qs_affine_fg(self._h, x.data_ptr(), float(dt), None if F is None else F.data_ptr(),
+                                         None if G is None else G.data_ptr(), n, self._stream()), self._h)
+        self._done_call()
+        self._affine_in = x                            # keep the input alive until the stream has consumed it
+        return F, G
 
     # ---- bookkeeping -----------------------------------------------------------------------------------
     def stats(self, clear=False):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 7
+#define QS_ABI_VERSION 8
 
 typedef struct QsHandle QsHandle;
 typedef void* qs_stream_t; /* cudaStream_t */
@@ -59,16 +59,34 @@ typedef enum QsController {
   QS_CTRL_COUNT = 7
 } QsController;
 
-/* get_state.py: the six observation builders that run in the reference (:5 :134 :147 :219 :236 :249) */
+/* get_state.py: the six observation builders that run in the reference as shipped (:5 :134 :147 :219 :236 :249) and
+ * the six that run once the module is given the names it uses without importing them (`normal`, `R2quat`: quaternion
+ * builders :276 :289 :307, thrust-to-weight / torque-to-thrust builders :325 :345 :363).  The remaining builders of that
+ * file cannot run at all (invalid np.array calls, undefined locals, components unknown to make_observation_space). */
 typedef enum QsObsRepr {
-  QS_OBS_XYZ_VXYZ_R_OMEGA = 0,         /* 18 */
-  QS_OBS_XYZ_VXYZ_R_OMEGA_H = 1,       /* 19 */
-  QS_OBS_XYZR_VXYZR_R_OMEGA = 2,       /* 18 */
-  QS_OBS_XYZR_VXYZR_R_OMEGA_H = 3,     /* 19 */
-  QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT = 4, /* 25 */
-  QS_OBS_XYZ_VXYZ_R_OMEGA_ACT = 5,     /* 22 */
-  QS_OBS_COUNT = 6
+  QS_OBS_XYZ_VXYZ_R_OMEGA = 0,          /* 18 */
+  QS_OBS_XYZ_VXYZ_R_OMEGA_H = 1,        /* 19 */
+  QS_OBS_XYZR_VXYZR_R_OMEGA = 2,        /* 18 */
+  QS_OBS_XYZR_VXYZR_R_OMEGA_H = 3,      /* 19 */
+  QS_OBS_XYZ_VXYZ_R_OMEGA_ACC_ACT = 4,  /* 25 */
+  QS_OBS_XYZ_VXYZ_R_OMEGA_ACT = 5,      /* 22 */
+  QS_OBS_XYZ_VXYZ_QUAT_OMEGA = 6,       /* 13: R2quat(R) (quad_utils.py:101-109) x small-angle noise quaternion */
+  QS_OBS_XYZR_VXYZR_QUAT_OMEGA = 7,     /* 13 */
+  QS_OBS_XYZR_VXYZR_QUAT_OMEGA_H = 8,   /* 14 */
+  QS_OBS_XYZR_VXYZR_R_OMEGA_T2W = 9,    /* 19: + noisy thrust_to_weight clipped to [1.5, 10] and scaled to [0, 1] */
+  QS_OBS_XYZ_VXYZ_R_OMEGA_T2W = 10,     /* 19 */
+  QS_OBS_XYZ_VXYZ_R_OMEGA_T2W_T2T = 11, /* 20: + noisy torque_to_thrust clipped to [0.005, 1], scaled to [0, 1] */
+  QS_OBS_COUNT = 12
 } QsObsRepr;
+
+/* QsConfig.init_random_state: which law a reset draws velocity, attitude and body rates from */
+typedef enum QsInitMode {
+  QS_INIT_DEFAULT = 0, /* at rest, yawed towards the goal (quadrotor.py:1118-1126) */
+  QS_INIT_RANDOM = 1,  /* init_random_state=True: QuadrotorDynamics.random_state in 3D (:227-239, :1113), the 1D / 2D
+                        * laws of :1101-1110 otherwise */
+  QS_INIT_PITCH_ROLL_RESTRICTED = 2 /* QuadrotorDynamics.pitch_roll_restricted_random_state (:243-259): Euler angles
+                        * U(-pitch_max, pitch_max), U(-roll_max, roll_max), U(-yaw_max, yaw_max), R = Rz Ry Rx (3D only) */
+} QsInitMode;
 
 typedef enum QsNoiseMode {
   QS_NOISE_PHILOX = 0,  /* on-device Philox4x32-10, counter = (global env id, step, slot), key = seed */
@@ -77,7 +95,7 @@ typedef enum QsNoiseMode {
 
 /* Injected-noise slot layout (unit normals "n", unit uniforms in [-1,1) "u").
  * obs_z  [n_envs][QS_OBS_Z]   : one SensorNoise.add_noise call, sensor_noise.py:116-157 */
-#define QS_OBS_Z 30
+#define QS_OBS_Z 33
 #define QS_Z_NPOS 0
 #define QS_Z_UPOS 3
 #define QS_Z_NVEL 6
@@ -88,15 +106,20 @@ typedef enum QsNoiseMode {
 #define QS_Z_UTHETA 21
 #define QS_Z_NACC_S 24
 #define QS_Z_NACC_D 27
+#define QS_Z_NT2W 30     /* unit normal of the thrust-to-weight observation noise (get_state.py:334); [31] torque-to-thrust */
+#define QS_Z_NT2T 31
 /* reset_z [n_envs][QS_RESET_Z] : QuadrotorEnv._reset, quadrotor.py:1087-1126 (+ :227-239, quad_utils.py:47-57,139) */
-#define QS_RESET_Z 48
+#define QS_RESET_Z 51
 #define QS_RZ_UPOS 0    /* spawn position = goal + box * u              (:1087) */
 #define QS_RZ_YAW 3     /* injected: accepted yaw / pi ; Philox: yaw = atan2(-y,-x) + (pi/3) u   (:1124-1126) */
 #define QS_RZ_UVEL 4    /* init_random_state: velocity direction        (:230) */
 #define QS_RZ_UVELMAG 7 /*                    velocity magnitude        (:231) */
 #define QS_RZ_UOM 8     /*                    omega direction           (:234) */
 #define QS_RZ_UOMMAG 11 /*                    omega magnitude           (:235) */
-#define QS_RZ_NUP 12    /*                    "up" Gaussian 3-vector    (quad_utils.py:49) */
+#define QS_RZ_NUP 12    /*                    "up" Gaussian 3-vector    (quad_utils.py:49);
+                         * QS_INIT_PITCH_ROLL_RESTRICTED: unit uniforms of pitch, roll, yaw (quadrotor.py:254-256);
+                         * 1D: [QS_RZ_UVELMAG] upward speed; 2D: [QS_RZ_UOMMAG] pitch rate, [QS_RZ_UVEL..] velocity,
+                         * [QS_RZ_YAW] pitch angle - unit symmetric draws u standing for rand() = (1 + u) / 2 (:1101-1110) */
 #define QS_RZ_NFWD 15   /*                    accepted "fwd" Gaussian   (quad_utils.py:50-52) */
 #define QS_RZ_OBS 18    /* obs_z of the observation returned by the reset (:1143) */
 /* ou_z   [n_envs][sim_steps][4] : OUNoise.noise() normals, one per substep (quad_utils.py:197-201) */
@@ -125,7 +148,7 @@ typedef enum QsNoiseMode {
  *   0 thrust_max[4]            1 torque_max[k] * prop_ccw[k]     2 prop_pos[k].y     3 -prop_pos[k].x     4 prop_pos[k].z
  *   5 inertia.xyz, mass        6 1/inertia.xyz, 1/mass
  *   7 tau_up, tau_down (= min(1, 4 dt / (damp_time + 1e-6)), quadrotor.py:284-288), ou_sigma, arm
- *   8 linearity, C_drag, C_roll, thrust_to_weight      9 vel_damp, damp_omega_quadratic, 0, 0
+ *   8 linearity, C_drag, C_roll, thrust_to_weight      9 vel_damp, damp_omega_quadratic, torque_to_thrust, 0
  *   10..13 rows of the inverse Jacobian (quadrotor_control.py:192-211) */
 #define QS_MODEL_ROWS 14
 
@@ -144,6 +167,7 @@ typedef struct QsModel {
   double arm, omega_max;
   double gravity;            /* self.gravity: accelerometer only (:436); the integrator uses GRAV = 9.81 (:426) */
   double thrust_to_weight;
+  double torque_to_thrust;   /* t2t observation component only (get_state.py:379) */
   double Jinv[4][4];
 } QsModel;
 
@@ -180,7 +204,7 @@ typedef struct QsConfig {
   int32_t zero_middle; /* raw_control_zero_middle */
   int32_t obs_repr;    /* QsObsRepr */
   int32_t noise_mode;  /* QsNoiseMode */
-  int32_t init_random_state;
+  int32_t init_random_state; /* QsInitMode */
   int32_t auto_reset;  /* fold reset() into step(): on done return the post-reset observation */
   int32_t dim_mode;    /* 1, 2 or 3 (quadrotor.py:1089-1092, :1120-1121) */
   int32_t sim_steps;
@@ -197,6 +221,8 @@ typedef struct QsConfig {
   double room_box[2][3];
   double max_init_vel, max_init_omega; /* quadrotor.py:717-718 */
   double collision_k;  /* swarm: contact when |p_i - p_j| < collision_k * 2 * arm */
+  double pitch_max, roll_max, yaw_max; /* QS_INIT_PITCH_ROLL_RESTRICTED (quadrotor.py:243: 0.5, 0.5, 3.14) */
+  double t2w_std, t2t_std; /* t2w / t2t observation noise (quadrotor.py:658: 0.005, 0.0005) */
   int32_t use_formation; /* swarm: drone a of every swarm flies to formation[a] (no goal row in the state buffer) */
   int32_t per_env_model; /* dynamics randomisation: model constants come from qs_bind_models, not from `model` */
   double formation[32][3];
@@ -275,6 +301,13 @@ int qs_step_k(QsHandle* h, int k, const void* actions, void* obs, void* rew, uin
  * (quadrotor_control.py, quadrotor.py:261): controller mixing + n_substeps x step1 on the bound state, no
  * reward/obs/tick.  controller = -1 passes `actions` straight through as normalized motor commands. */
 int qs_dynamics_step(QsHandle* h, int controller, const void* actions, int n_substeps, qs_stream_t stream);
+
+/* replaces QuadrotorDynamics.F(s, dt) / G(s) (quadrotor.py:461-518): the affine representation s' = dt (F(s) + G(s) u) of
+ * the dynamics, evaluated for n caller-supplied states s [n][21] = xyz, Vxyz, R (row-major), omega, goal with the handle's
+ * model (every state with model 0 of the model buffer on per_env_model handles).  F: real[n][21]; G: real[n][21][C], C = 1 /
+ * 2 / 4 controls for dim_mode 1D / 2D / 3D (quadrotor.py:121-129).  Either output may be NULL.  Does not touch the bound
+ * state. */
+int qs_affine_fg(QsHandle* h, const void* s, double dt, void* F, void* G, int64_t n, qs_stream_t stream);
 
 /* Same contract as qs_step but with HOST buffers; returns after the results are in host memory.  The step is ordered
  * after everything already queued on `stream` (resets, steps, state writes).  Pinned buffers (cudaHostAlloc /

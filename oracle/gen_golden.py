@@ -91,6 +91,20 @@ CASES = {
                              dict(dynamics_params="Crazyflie", ep_time=0.5, resample_goal=True)),
     "cf_raw_simplified": (qo.CTRL_RAW, None, _uni(-0.2, 0.8, 4), 300, 21, False,
                           dict(dynamics_params="Crazyflie", ep_time=1, dynamics_simplification=True, sense_noise="default")),
+    # observation builders that run once get_state.py is given the names it forgot to import (oracle/ref_shim.py)
+    "hb_quat_fullnoise": (qo.CTRL_RAW, None, _uni(-1, 1, 4), 300, 22, False,
+                          dict(dynamics_params="DefaultQuad", ep_time=1, sense_noise=FULL_NOISE, obs_repr="xyz_vxyz_quat_omega")),
+    "cf_xyzr_quat_h_rnd": (qo.CTRL_RAW, None, _uni(-0.2, 0.8, 4), 300, 23, False,
+                           dict(dynamics_params="Crazyflie", ep_time=1, sense_noise="default", init_random_state=True,
+                                obs_repr="xyzr_vxyzr_quat_omega_h")),
+    "hb_t2w_t2t_nonoise": (qo.CTRL_RAW, None, _uni(-1, 1, 4), 300, 24, False,
+                           dict(dynamics_params="DefaultQuad", ep_time=1, sense_noise=None, obs_repr="xyz_vxyz_R_omega_t2w_t2t")),
+    "hb_xyzr_t2w_mellinger": (qo.CTRL_MELLINGER, None, _uni(0, 0, 4), 450, 25, False,
+                              dict(dynamics_params="DefaultQuad", raw_control=False, ep_time=2, sense_noise="default",
+                                   obs_repr="xyzr_vxyzr_R_omega_t2w", t2w_std=0.4)),
+    # init_random_state outside 3D (quadrotor.py:1101-1103)
+    "hb_vertical_rnd": (qo.CTRL_VERTICAL, None, _uni(-1, 1, 1), 300, 26, False,
+                        dict(dynamics_params="DefaultQuad", dim_mode="1D", ep_time=0.5, init_random_state=True)),
     "mq_raw_simsteps4": (qo.CTRL_RAW, None, _uni(-0.5, 0.8, 4), 300, 15, False,
                          dict(dynamics_params="MediumQuad", ep_time=2, sim_steps=4, sim_freq=100.0)),
 }
@@ -231,6 +245,59 @@ def random_models():
     return out
 
 
+def affine_answers():
+    """F(s, dt) and G(s) of the live reference (quadrotor.py:461-518) on random states: both shipped models with the damping
+    terms switched on, all three dim_modes."""
+    import contextlib
+    import io
+    ref = rh.ref_shim.import_reference()
+    rng = np.random.RandomState(5)
+    out = {}
+    for tag, name in (("hb", "defaultquad_params"), ("cf", "crazyflie_params")):
+        params = getattr(ref.quad_models, name)()
+        params["damp"]["omega_quadratic"], params["damp"]["vel"] = 0.015, 0.001
+        out[tag + "_params_json"] = np.array(json.dumps(_plain(params)))
+        S = rng.uniform(-3, 3, (16, 21))
+        S[:, 15:18] *= 4.0
+        out[tag + "_s"] = S
+        for dm in ("1D", "2D", "3D"):
+            with contextlib.redirect_stdout(io.StringIO()):
+                d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2, dim_mode=dm)
+            out["%s_%s_F" % (tag, dm)] = np.stack([d.F(s, 0.005) for s in S])
+            out["%s_%s_G" % (tag, dm)] = np.stack([d.G(s) for s in S])
+    out["dt"] = np.array(0.005)
+    return out
+
+
+def restricted_state_answers():
+    """QuadrotorDynamics.pitch_roll_restricted_random_state (quadrotor.py:243-259) under a NoiseTape: the unit draws in
+    the reset_z layout (pitch, roll, yaw in the RZ_NUP slots) and what the reference returned."""
+    import contextlib
+    import io
+    ref = rh.ref_shim.import_reference()
+    params = ref.quad_models.crazyflie_params()
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2)
+    tape = rh.ref_shim.NoiseTape(ref, seed=65)
+    kw = dict(pitch_max=0.4, roll_max=0.7, yaw_max=2.5)
+    n = 64
+    rz, vel, rot, omega = np.zeros((n, qo.RESET_Z)), np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros((n, 3))
+    for i in range(n):
+        with tape:
+            _, vel[i], rot[i], omega[i] = d.pitch_roll_restricted_random_state(box=2.0, vel_max=3.0, omega_max=5.0, **kw)
+        log = [v for k, v in tape.take()]
+        rz[i, qo.RZ_UPOS:qo.RZ_UPOS + 3] = log[0]
+        rz[i, qo.RZ_UVEL:qo.RZ_UVEL + 3], rz[i, qo.RZ_UVELMAG] = log[1], log[2]
+        rz[i, qo.RZ_UOM:qo.RZ_UOM + 3], rz[i, qo.RZ_UOMMAG] = log[3], log[4]
+        rz[i, qo.RZ_NUP:qo.RZ_NUP + 3] = log[5], log[6], log[7]
+    return dict(reset_z=rz, vel=vel, rot=rot, omega=omega, params_json=np.array(json.dumps(_plain(params))),
+                vel_max=np.array(3.0), omega_max=np.array(5.0), **{k: np.array(v) for k, v in kw.items()})
+
+
+ANSWER_FILES = {"known_answer": known_answer, "model_answers": model_answers, "random_models": random_models,
+                "affine_answers": affine_answers, "restricted_state": restricted_state_answers}
+
+
 def main(argv):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     names = argv[1:] or list(CASES)
@@ -239,10 +306,9 @@ def main(argv):
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
         print("wrote", name, {k: v.shape for k, v in out.items() if k in ("obs", "reset_z")})
     if not argv[1:]:
-        np.savez_compressed(os.path.join(GOLDEN_DIR, "known_answer.npz"), **known_answer())
-        np.savez_compressed(os.path.join(GOLDEN_DIR, "model_answers.npz"), **model_answers())
-        np.savez_compressed(os.path.join(GOLDEN_DIR, "random_models.npz"), **random_models())
-        print("wrote known_answer, model_answers, random_models")
+        for name, fn in ANSWER_FILES.items():
+            np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **fn())
+        print("wrote", ", ".join(ANSWER_FILES))
 
 
 if __name__ == "__main__":

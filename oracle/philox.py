@@ -23,6 +23,7 @@ MASK = np.uint64(0xFFFFFFFF)
 # slot map (qs_device.cuh:281-283)
 SLOT_OBS, SLOT_EXCITE, SLOT_RESET_OBS, SLOT_RESET_POS, SLOT_RESET_VEL, SLOT_RESET_OM = 0, 12, 16, 26, 27, 28
 SLOT_RESET_UP, SLOT_RESET_FWD, SLOT_RESET_GOAL, SLOT_OU = 29, 30, 40, 64
+SLOT_T2W, SLOT_RESET_T2W = 11, 41      # group 10 of an observation call: t2w / t2t normals (QS_Z_NT2W, QS_Z_NT2T)
 # groups of one add_noise call, in OBS_Z order, and whether the group is uniform (quadsim.h QS_Z_*)
 OBS_GROUP_UNIFORM = (False, True, False, True, False, False, False, True, False, False)
 
@@ -82,7 +83,9 @@ class PhiloxTape(object):
 
     def __init__(self, seed, fp32=True, sim_steps=2, init_random_state=False, goal=(0.0, 0.0, 2.0), box=2.0, dim_mode="3D"):
         self.seed, self.fp32, self.sim_steps = int(seed), bool(fp32), int(sim_steps)
+        # False / True / "pitch_roll_restricted" (QsInitMode)
         self.init_random_state = bool(init_random_state)
+        self.restricted = init_random_state == "pitch_roll_restricted"
         self.goal, self.box, self.dim_mode = np.asarray(goal, dtype=np.float64), float(box), dim_mode
 
     def ou_z(self, gids, step):
@@ -92,10 +95,12 @@ class PhiloxTape(object):
     def obs_z(self, gids, step, reset_obs=False):
         """[n, OBS_Z]: group g of the add_noise call = first three words of slot (0 | 16) + g."""
         base = SLOT_RESET_OBS if reset_obs else SLOT_OBS
-        z = np.empty((len(gids), qo.OBS_Z))
+        z = np.zeros((len(gids), qo.OBS_Z))
         for g, is_unif in enumerate(OBS_GROUP_UNIFORM):
             w = raw(self.seed, gids, step, base + g)
             z[:, 3 * g:3 * g + 3] = (unif4(w) if is_unif else normal4(w, self.fp32))[:, :3]
+        w = raw(self.seed, gids, step, SLOT_RESET_T2W if reset_obs else SLOT_T2W)
+        z[:, 30:33] = normal4(w, self.fp32)[:, :3]
         return z
 
     def reset_z(self, gids, step, goals=None):
@@ -118,7 +123,15 @@ class PhiloxTape(object):
         # Philox mode draws the law of the reference's rejection loop directly: psi = atan2(-y, -x) + (pi / 3) u
         # (DESIGN.md section 5.2); the oracle's slot is "accepted yaw / pi"
         z[:, qo.RZ_YAW] = (np.arctan2(-y, -x) + (np.pi / 3.0) * u[:, 3]) / np.pi
-        if self.init_random_state:
+        if self.init_random_state and self.dim_mode != "3D":              # quadrotor.py:1101-1110: unit draws standing for rand()
+            z[:, qo.RZ_UVEL:qo.RZ_UVEL + 4] = unif4(raw(self.seed, gids, step, SLOT_RESET_VEL))
+            z[:, qo.RZ_UOM:qo.RZ_UOM + 4] = unif4(raw(self.seed, gids, step, SLOT_RESET_OM))
+            z[:, qo.RZ_YAW] = u[:, 3]                                     # 2D: the pitch angle draw
+        elif self.restricted:                                             # quadrotor.py:243-259: pitch, roll, yaw uniforms
+            z[:, qo.RZ_UVEL:qo.RZ_UVEL + 4] = unif4(raw(self.seed, gids, step, SLOT_RESET_VEL))
+            z[:, qo.RZ_UOM:qo.RZ_UOM + 4] = unif4(raw(self.seed, gids, step, SLOT_RESET_OM))
+            z[:, qo.RZ_NUP:qo.RZ_NUP + 3] = unif4(raw(self.seed, gids, step, SLOT_RESET_UP))[:, :3]
+        elif self.init_random_state:
             a = unif4(raw(self.seed, gids, step, SLOT_RESET_VEL))
             b = unif4(raw(self.seed, gids, step, SLOT_RESET_OM))
             z[:, qo.RZ_UVEL:qo.RZ_UVEL + 4] = a

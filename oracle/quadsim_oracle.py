@@ -20,29 +20,47 @@ GRAV = 9.81   # quadrotor.py:53
 EPS = 1e-6    # quadrotor.py:54
 
 # injected-noise slot layout, mirrored by include/quadsim.h ----------------------------------------
-OBS_Z = 30            # n_pos3 u_pos3 n_vel3 u_vel3 n_gyro3 n_gyro_rw3 n_theta3 u_theta3 n_accS3 n_accD3
+OBS_Z = 33            # n_pos3 u_pos3 n_vel3 u_vel3 n_gyro3 n_gyro_rw3 n_theta3 u_theta3 n_accS3 n_accD3 | n_t2w n_t2t (unused)
 RESET_Z = 18 + OBS_Z  # u_pos3 yaw1 u_vel3 u_velmag1 u_om3 u_ommag1 n_up3 n_fwd3 | obs_z for the post-reset obs
 GOAL_Z = 4            # excite goal u_xy2 u_z1 (quadrotor.py:957-962) | resample_goal u_z1 (:1078-1079)
 (Z_NPOS, Z_UPOS, Z_NVEL, Z_UVEL, Z_NGYRO, Z_NGYRO_RW, Z_NTHETA, Z_UTHETA, Z_NACC_S, Z_NACC_D) = range(0, 30, 3)
+Z_NT2W, Z_NT2T = 30, 31   # unit normals of the thrust-to-weight / torque-to-thrust observation noise (get_state.py:334, :379)
+INIT_DEFAULT, INIT_RANDOM, INIT_PITCH_ROLL_RESTRICTED = 0, 1, 2   # which law the reset draws (vel, rot, omega) from
 (RZ_UPOS, RZ_YAW, RZ_UVEL, RZ_UVELMAG, RZ_UOM, RZ_UOMMAG, RZ_NUP, RZ_NFWD, RZ_OBS) = (0, 3, 4, 7, 8, 11, 12, 15, 18)
 
 CTRL_RAW, CTRL_VERTICAL, CTRL_VERTPLANE, CTRL_SHIFTED, CTRL_OMEGA_THRUST, CTRL_VELOCITY_YAW, CTRL_MELLINGER = range(7)
 CTRL_ACT_DIM = {CTRL_RAW: 4, CTRL_VERTICAL: 1, CTRL_VERTPLANE: 2, CTRL_SHIFTED: 4, CTRL_OMEGA_THRUST: 4,
                 CTRL_VELOCITY_YAW: 4, CTRL_MELLINGER: 4}
 
-OBS_REPRS = {  # get_state.py:5,134,147,219,236,249  -> (relative frame, +h, +acc, +act)
+OBS_REPRS = {  # get_state.py:5,134,147,219,236,249 -> (relative frame, +h, +acc, +act); the rest of the table below
     "xyz_vxyz_R_omega": (False, False, False, False),
     "xyz_vxyz_R_omega_h": (False, True, False, False),
     "xyzr_vxyzr_R_omega": (True, False, False, False),
     "xyzr_vxyzr_R_omega_h": (True, True, False, False),
     "xyz_vxyz_R_omega_acc_act": (False, False, True, True),
     "xyz_vxyz_R_omega_act": (False, False, False, True),
+    # builders that only lack module-level names in the reference (`normal`, `R2quat`: get_state.py has no imports for
+    # them); oracle/ref_shim.py supplies the names, the reference code itself is untouched
+    "xyz_vxyz_quat_omega": (False, False, False, False),                 # :276
+    "xyzr_vxyzr_quat_omega": (True, False, False, False),                # :289
+    "xyzr_vxyzr_quat_omega_h": (True, True, False, False),               # :307
+    "xyzr_vxyzr_R_omega_t2w": (True, False, False, False),               # :325
+    "xyz_vxyz_R_omega_t2w": (False, False, False, False),                # :345
+    "xyz_vxyz_R_omega_t2w_t2t": (False, False, False, False),            # :363
 }
+T2W_MIN, T2W_MAX, T2T_MIN, T2T_MAX = 1.5, 10.0, 0.005, 1.0              # quadrotor.py:707-712
+
+
+def obs_layout(obs_repr):
+    """(relative frame, +h, +acc, +act, quaternion instead of R, +t2w, +t2t)"""
+    rel, h, acc, act = OBS_REPRS[obs_repr]
+    comps = obs_repr.split("_")
+    return rel, h, acc, act, "quat" in comps, "t2w" in comps, "t2t" in comps
 
 
 def obs_dim(obs_repr):
-    rel, h, acc, act = OBS_REPRS[obs_repr]
-    return 18 + int(h) + 3 * int(acc) + 4 * int(act)
+    rel, h, acc, act, quat, t2w, t2t = obs_layout(obs_repr)
+    return 9 + (4 if quat else 9) + int(h) + 3 * int(acc) + 4 * int(act) + int(t2w) + int(t2t)
 
 
 # ==================================================================================================
@@ -280,6 +298,24 @@ def rot2quat(R):                 # sensor_noise.py:26-55 (four-branch)
     return q
 
 
+def R2quat(R):                   # quad_utils.py:101-109 (single branch: needs 1 + trace > 0, as the reference)
+    w = np.sqrt(1.0 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]) / 2.0
+    w4 = 4.0 * w
+    return np.stack([w, (R[:, 2, 1] - R[:, 1, 2]) / w4, (R[:, 0, 2] - R[:, 2, 0]) / w4, (R[:, 1, 0] - R[:, 0, 1]) / w4], axis=1)
+
+
+def euler2mat_sxyz(ai, aj, ak):
+    """transforms3d.euler.euler2mat(ai, aj, ak) with its default axes 'sxyz' (transforms3d is not installed here; this
+    is its documented convention: static-frame rotations about x, then y, then z, R = Rz(ak) Ry(aj) Rx(ai)).  Used by
+    QuadrotorDynamics.pitch_roll_restricted_random_state, quadrotor.py:257."""
+    ci, si, cj, sj, ck, sk = np.cos(ai), np.sin(ai), np.cos(aj), np.sin(aj), np.cos(ak), np.sin(ak)
+    R = np.empty(np.shape(ai) + (3, 3))
+    R[..., 0, 0], R[..., 0, 1], R[..., 0, 2] = cj * ck, sj * si * ck - ci * sk, sj * ci * ck + si * sk
+    R[..., 1, 0], R[..., 1, 1], R[..., 1, 2] = cj * sk, sj * si * sk + ci * ck, sj * ci * sk - si * ck
+    R[..., 2, 0], R[..., 2, 1], R[..., 2, 2] = -sj, cj * si, cj * ci
+    return R
+
+
 def quat_from_small_angle(theta):  # sensor_noise.py:9-21
     q_squared = (theta[:, 0] ** 2 + theta[:, 1] ** 2 + theta[:, 2] ** 2) / 4.0
     lt = q_squared < 1
@@ -314,7 +350,8 @@ def gyro_bias_coeffs(sn, dt):    # sensor_noise.py:165-167
 
 
 def add_noise(sn, pos, vel, rot, omega, acc, dt, z, gyro_bias, n_calls=1):
-    """sensor_noise.py:100-159.  sn=None is bypass.  z: [N, OBS_Z] unit draws.
+    """sensor_noise.py:100-159.  sn=None is bypass.  z: [N, OBS_Z] unit draws.  rot: [N,3,3] rotation matrices, or
+    [N,4] quaternions (the quat observation builders pass R2quat(rot), sensor_noise.py:148-151).
 
     n_calls: how many times the reference invokes add_noise around this observable one
     (3 per env step - quadrotor.py:947,970,988 - and 1 at reset, :1143).  It only matters for the
@@ -336,10 +373,53 @@ def add_noise(sn, pos, vel, rot, omega, acc, dt, z, gyro_bias, n_calls=1):
     else:
         nomega = omega + sn["gyro_noise_density"] * z[:, Z_NGYRO:Z_NGYRO + 3]          # :130-131
     theta = sn["quat_norm_std"] * z[:, Z_NTHETA:Z_NTHETA + 3] + sn["quat_unif_range"] * z[:, Z_UTHETA:Z_UTHETA + 3]
-    nrot = quat2R(quatXquat(rot2quat(rot), quat_from_small_angle(theta)))             # :144-147
+    if rot.ndim == 2:
+        nrot = quatXquat(rot, quat_from_small_angle(theta))                           # :148-151
+    else:
+        nrot = quat2R(quatXquat(rot2quat(rot), quat_from_small_angle(theta)))         # :144-147
     nacc = acc + sn["acc_static_noise_std"] * z[:, Z_NACC_S:Z_NACC_S + 3] \
         + acc * (sn["acc_dynamic_noise_ratio"] * z[:, Z_NACC_D:Z_NACC_D + 3])          # :156-157
     return npos, nvel, nrot, nomega, nacc, gyro_bias
+
+
+# ==================================================================================================
+# affine dynamics representation s' = dt (F(s) + G(s) u)   (quadrotor.py:457-518)
+# ==================================================================================================
+CONTROL_MX = {"1D": np.ones((4, 1)), "2D": np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [0.0, 1.0]]), "3D": np.eye(4)}   # :121-129
+
+
+def affine_F(m, s, dt):
+    """quadrotor.py:461-497.  s: [N, 21] = xyz, Vxyz, R (row-major), omega, goal.  Returns [N, 21]."""
+    s = np.asarray(s, dtype=np.float64).reshape(-1, 21)
+    V, R, om = s[:, 3:6], s[:, 6:15].reshape(-1, 3, 3), s[:, 15:18]
+    dx = V.copy()                                                         # :471
+    dV = ((1.0 - m["vel_damp"]) * V - V) / dt + np.array([0.0, 0.0, -GRAV])   # :475
+    w = np.einsum("nij,nj->ni", R, om)                                    # :479 body -> world
+    W = np.zeros((len(s), 3, 3))                                          # :481
+    W[:, 0, 1], W[:, 0, 2], W[:, 1, 0], W[:, 1, 2], W[:, 2, 0], W[:, 2, 1] = -w[:, 2], w[:, 1], w[:, 2], -w[:, 0], -w[:, 1], w[:, 0]
+    dR = (W @ R).reshape(-1, 9)                                           # :484
+    inertia = m["inertia"]
+    F_omega = (1.0 / inertia) * _cross(-om, inertia * om)                 # :488
+    damp = np.clip(m["damp_omega_quadratic"] * om ** 2, 0.0, 1.0)         # :489
+    dOm = (1.0 - damp) * F_omega                                          # :490
+    return np.concatenate([dx, dV, dR, dOm, np.zeros((len(s), 3))], axis=1)
+
+
+def affine_G(m, s, dim_mode="3D"):
+    """quadrotor.py:501-518.  Returns [N, 21, C], C = 1 / 2 / 4 controls for dim_mode 1D / 2D / 3D."""
+    s = np.asarray(s, dtype=np.float64).reshape(-1, 21)
+    N = len(s)
+    R, om = s[:, 6:15].reshape(-1, 3, 3), s[:, 15:18]
+    thrust_sum = np.zeros((3, 4))
+    thrust_sum[2, :] = 1.0                                                # :194-195
+    dV = (R / m["mass"]) @ (m["thrust_max"] * thrust_sum)                 # :509
+    ccw_mx = np.zeros((3, 4))
+    ccw_mx[2, :] = m["prop_ccw"]                                          # :183-184
+    G_omega = (1.0 / m["inertia"])[:, None] * (m["thrust_max"] * m["prop_cross"].T + m["torque_max"] * ccw_mx)   # :188-191
+    damp = np.clip(m["damp_omega_quadratic"] * om ** 2, 0.0, 1.0)         # :515
+    dOm = (1.0 - damp)[:, :, None] * G_omega[None]                        # :516
+    G = np.concatenate([np.zeros((N, 3, 4)), dV, np.zeros((N, 9, 4)), dOm, np.zeros((N, 3, 4))], axis=1)
+    return G @ CONTROL_MX[dim_mode]                                       # :518
 
 
 # ==================================================================================================
@@ -391,14 +471,19 @@ class OracleVecEnv(object):
                  obs_repr="xyz_vxyz_R_omega", ep_time=7, room_size=10.0, init_random_state=False, rew_coeff=None,
                  sense_noise=None, gravity=GRAV, auto_reset=True, goal=(0.0, 0.0, 2.0), box=2.0,
                  multi_reward=False, n_agents=1, collision_k=1.0, collision_coeff=0.0, goals=None, dim_mode="3D",
-                 resample_goal=False, excite=False, dynamics_simplification=False):
+                 resample_goal=False, excite=False, dynamics_simplification=False, t2w_std=0.005, t2t_std=0.0005,
+                 pitch_max=0.5, roll_max=0.5, yaw_max=3.14):
         self.m = model_constants(params, simplified=dynamics_simplification)
         self.m["gravity"] = gravity
         self.N = int(n_envs)
         self.controller = controller
         self.dim_mode = dim_mode
-        if dim_mode != "3D" and init_random_state:
-            raise ValueError("oracle: init_random_state is restated for dim_mode='3D' only")
+        # init_random_state: False / True (quadrotor.py:1100-1115), or "pitch_roll_restricted" - the law of
+        # QuadrotorDynamics.pitch_roll_restricted_random_state (:243-259), which the reference env never selects itself
+        self.init_mode = (INIT_PITCH_ROLL_RESTRICTED if init_random_state == "pitch_roll_restricted"
+                          else (INIT_RANDOM if init_random_state else INIT_DEFAULT))
+        self.t2w_std, self.t2t_std = float(t2w_std), float(t2t_std)       # quadrotor.py:658, :706-712
+        self.pitch_max, self.roll_max, self.yaw_max = float(pitch_max), float(roll_max), float(yaw_max)
         self.zero_middle = zero_middle
         self.resample_goal, self.excite = bool(resample_goal), bool(excite)   # quadrotor.py:1078-1081, :957-962
         self.goal_default = np.array(goal, dtype=np.float64)
@@ -407,7 +492,7 @@ class OracleVecEnv(object):
         self.ep_len = int(ep_time / (self.dt * self.sim_steps))           # :792
         self.obs_repr = obs_repr
         self.room_box = np.array([[-room_size, -room_size, 0.0], [room_size, room_size, room_size]])   # :723
-        self.init_random_state = init_random_state
+        self.init_random_state = bool(init_random_state)
         self.max_init_vel = 1.0                                           # :717
         self.max_init_omega = 2 * np.pi                                   # :718
         self.box = box                                                    # :728
@@ -610,22 +695,31 @@ class OracleVecEnv(object):
 
     # ---------------------------------------------------------------------------------------------
     def observe(self, obs_z, n_calls):
-        rel, h, acc_, act = OBS_REPRS[self.obs_repr]
+        rel, h, acc_, act, quat, t2w, t2t = obs_layout(self.obs_repr)
+        rot_in = R2quat(self.rot) if quat else self.rot                   # get_state.py:277 (quat builders)
         pos, vel, rot, omega, acc, gyro_bias = add_noise(
-            self.sn, self.pos, self.vel, self.rot, self.omega, self.accelerometer, self.dt, obs_z, self.gyro_bias,
+            self.sn, self.pos, self.vel, rot_in, self.omega, self.accelerometer, self.dt, obs_z, self.gyro_bias,
             n_calls=n_calls)
         e = pos - self.goal
         v = vel
         if rel:                                                           # get_state.py:159-160 (true R)
             e = np.einsum("nji,nj->ni", self.rot, e)
             v = np.einsum("nji,nj->ni", self.rot, vel)
-        parts = [e, v, rot.reshape(self.N, 9), omega]
+        parts = [e, v, rot.reshape(self.N, -1), omega]
         if h:
             parts.append(pos[:, 2:3])                                     # get_state.py:143 (noisy z)
         if acc_:
             parts.append(acc)
         if act:
             parts.append(self.act_prev)                                   # get_state.py:246,259 -> actions[1]
+        if t2w:                                                           # get_state.py:334-337: drawn whether or not the
+            w = self.m["thrust_to_weight"]                                # SensorNoise is bypassed
+            nw = np.clip(w + abs((self.t2w_std / 2) * w) * obs_z[:, Z_NT2W:Z_NT2W + 1], T2W_MIN, T2W_MAX)
+            parts.append((nw - T2W_MIN) / (T2W_MAX - T2W_MIN))
+        if t2t:                                                           # get_state.py:379-382
+            w = self.m["torque_to_thrust"]
+            nw = np.clip(w + abs((self.t2t_std / 2) * w) * obs_z[:, Z_NT2T:Z_NT2T + 1], T2T_MIN, T2T_MAX)
+            parts.append((nw - T2T_MIN) / (T2T_MAX - T2T_MIN))
         return np.concatenate(parts, axis=1), gyro_bias
 
     # ---------------------------------------------------------------------------------------------
@@ -649,7 +743,19 @@ class OracleVecEnv(object):
         elif self.dim_mode == "2D":
             pos[:, 1] = goal[:, 1]
         pos[:, 2] = np.where(pos[:, 2] < 0.25, 0.25, pos[:, 2])           # :1094
-        if self.init_random_state:                                        # :1113-1115 -> :227-239
+        u01 = lambda k: 0.5 + 0.5 * reset_z[:, k]                         # np.random.rand() from a unit symmetric draw
+        if self.init_mode != INIT_DEFAULT and self.dim_mode == "1D":      # :1101-1103
+            omega = np.zeros((N, 3))
+            rot = np.tile(np.eye(3), (N, 1, 1))
+            vel = np.stack([np.zeros(N), np.zeros(N), self.max_init_vel * u01(RZ_UVELMAG)], axis=1)
+        elif self.init_mode != INIT_DEFAULT and self.dim_mode == "2D":    # :1104-1110 (draw order: omega, vel, theta)
+            omega = np.stack([np.zeros(N), self.max_init_omega * u01(RZ_UOMMAG), np.zeros(N)], axis=1)
+            vel = self.max_init_vel * np.stack([u01(RZ_UVEL), np.zeros(N), u01(RZ_UVEL + 2)], axis=1)
+            theta = np.pi * u01(RZ_YAW)
+            c, s_ = np.cos(theta), np.sin(theta)
+            rot = np.zeros((N, 3, 3))
+            rot[:, 0, 0], rot[:, 0, 2], rot[:, 1, 1], rot[:, 2, 0], rot[:, 2, 2] = c, -s_, 1.0, s_, c
+        elif self.init_mode != INIT_DEFAULT:                              # :1113-1115 -> :227-239 / :243-259
             vm, om_ = self.max_init_vel, self.max_init_omega
             vel = vm * reset_z[:, RZ_UVEL:RZ_UVEL + 3]                    # :230
             vel_magn = vm * (0.5 + 0.5 * reset_z[:, RZ_UVELMAG])          # :231 uniform(0, vel_max)
@@ -657,11 +763,15 @@ class OracleVecEnv(object):
             omega = om_ * reset_z[:, RZ_UOM:RZ_UOM + 3]                   # :234
             om_magn = om_ * (0.5 + 0.5 * reset_z[:, RZ_UOMMAG])           # :235
             omega = (om_magn / (np.sqrt(np.sum(omega ** 2, axis=1)) + EPS))[:, None] * omega   # :236
-            up = _normalize(reset_z[:, RZ_NUP:RZ_NUP + 3])                # quad_utils.py:47-57 (accepted draws)
-            fwd = _normalize(reset_z[:, RZ_NFWD:RZ_NFWD + 3])
-            left = _normalize(_cross(up, fwd))
-            up = _cross(fwd, left)
-            rot = np.stack([fwd, left, up], axis=2)
+            if self.init_mode == INIT_PITCH_ROLL_RESTRICTED:              # :254-257 (draw order: pitch, roll, yaw)
+                rot = euler2mat_sxyz(self.roll_max * reset_z[:, RZ_NUP + 1], self.pitch_max * reset_z[:, RZ_NUP],
+                                     self.yaw_max * reset_z[:, RZ_NUP + 2])
+            else:
+                up = _normalize(reset_z[:, RZ_NUP:RZ_NUP + 3])            # quad_utils.py:47-57 (accepted draws)
+                fwd = _normalize(reset_z[:, RZ_NFWD:RZ_NFWD + 3])
+                left = _normalize(_cross(up, fwd))
+                up = _cross(fwd, left)
+                rot = np.stack([fwd, left, up], axis=2)
         else:                                                             # :1118-1126
             vel = np.zeros((N, 3))
             omega = np.zeros((N, 3))

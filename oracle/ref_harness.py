@@ -42,9 +42,9 @@ class _TapeReader(object):
         return self.i == len(self.log)
 
 
-def _read_add_noise(tr, gyro_bias_mode):
+def _read_add_noise(tr, gyro_bias_mode, z=None):
     """One SensorNoise.add_noise call (sensor_noise.py:116-157) -> OBS_Z unit draws."""
-    z = np.zeros(qo.OBS_Z)
+    z = np.zeros(qo.OBS_Z) if z is None else z
     z[qo.Z_NPOS:qo.Z_NPOS + 3] = tr.pop("normal", (3,))
     z[qo.Z_UPOS:qo.Z_UPOS + 3] = tr.pop("uniform", (3,))
     z[qo.Z_NVEL:qo.Z_NVEL + 3] = tr.pop("normal", (3,))
@@ -77,6 +77,9 @@ class ReferenceRunner(object):
         self.tape.rs = np.random.RandomState(seed)
         self.noise_on = not self.env.sense_noise.bypass
         self.gyro_bias_mode = self.noise_on and self.env.sense_noise.gyro_norm_std != 0.0
+        comps = self.env.obs_repr.split("_")
+        self.obs_t2w, self.obs_t2t = "t2w" in comps, "t2t" in comps       # get_state.py:334, :379: one normal(size=1) each
+        self.obs_draws = self.noise_on or self.obs_t2w
         # optional controller the reference env cannot select itself
         self.ext_controller = None
         if controller == "omega_thrust":
@@ -103,6 +106,17 @@ class ReferenceRunner(object):
             # dict (reference bug: AttributeError on the first step).  Harness-only workaround.
             self.env.controller.action = np.zeros(4)
 
+    def _read_state_call(self, tr):
+        """One state_<obs_repr>(env) call: add_noise (unless bypassed), then the t2w / t2t normals -> OBS_Z unit draws."""
+        z = np.zeros(qo.OBS_Z)
+        if self.noise_on:
+            _read_add_noise(tr, self.gyro_bias_mode, z)
+        if self.obs_t2w:
+            z[qo.Z_NT2W] = tr.pop("normal", (1,))[0]
+        if self.obs_t2t:
+            z[qo.Z_NT2T] = tr.pop("normal", (1,))[0]
+        return z
+
     # ---------------------------------------------------------------------------------------------
     def _reset_z_from_tape(self, log, pos_goal):
         tr = _TapeReader(log)
@@ -112,7 +126,13 @@ class ReferenceRunner(object):
         if env.resample_goal:                                             # quadrotor.py:1078-1079, drawn before the spawn
             self.last_goal_z[3] = tr.pop("uniform", ())
         rz[qo.RZ_UPOS:qo.RZ_UPOS + 3] = tr.pop("uniform", (3,))            # quadrotor.py:1087
-        if env.init_random_state:                                         # quadrotor.py:227-239
+        if env.init_random_state and env.dim_mode == "1D":                # quadrotor.py:1101-1103
+            rz[qo.RZ_UVELMAG] = tr.pop("uniform", ())
+        elif env.init_random_state and env.dim_mode == "2D":              # :1104-1110: omega, vel (3 draws), theta
+            rz[qo.RZ_UOMMAG] = tr.pop("uniform", ())
+            rz[qo.RZ_UVEL:qo.RZ_UVEL + 3] = tr.pop("uniform", (3,))
+            rz[qo.RZ_YAW] = tr.pop("uniform", ())
+        elif env.init_random_state:                                       # quadrotor.py:227-239
             tr.pop("uniform", (3,))                                       # pos draw, discarded (:228, :1113 `_`)
             rz[qo.RZ_UVEL:qo.RZ_UVEL + 3] = tr.pop("uniform", (3,))
             rz[qo.RZ_UVELMAG] = tr.pop("uniform", ())
@@ -133,8 +153,8 @@ class ReferenceRunner(object):
                 if not (k == "uniform" and np.shape(v) == ()):
                     break
             rz[qo.RZ_YAW] = u
-        if self.noise_on:
-            rz[qo.RZ_OBS:qo.RZ_OBS + qo.OBS_Z] = _read_add_noise(tr, self.gyro_bias_mode)
+        if self.obs_draws:
+            rz[qo.RZ_OBS:qo.RZ_OBS + qo.OBS_Z] = self._read_state_call(tr)
         assert tr.done(), "unparsed reset draws"
         return rz
 
@@ -152,19 +172,19 @@ class ReferenceRunner(object):
         tr = _TapeReader(self.tape.take())
         zs = []
         self.last_goal_z = np.zeros(qo.GOAL_Z)
-        if self.noise_on:
-            zs.append(_read_add_noise(tr, self.gyro_bias_mode))           # quadrotor.py:947
+        if self.obs_draws:                                                # quadrotor.py:947: a bare add_noise call, no t2w draw
+            zs.append(_read_add_noise(tr, self.gyro_bias_mode) if self.noise_on else np.zeros(qo.OBS_Z))
         if env.excite and tick_before % 5 == 0:                           # :957-962
             self.last_goal_z[0:2] = tr.pop("uniform", (2,))
             self.last_goal_z[2] = tr.pop("uniform", (1,))[0]
-        if self.noise_on:
-            zs.append(_read_add_noise(tr, self.gyro_bias_mode))           # :970
+        if self.obs_draws:
+            zs.append(self._read_state_call(tr))                          # :970
         ou_z = np.zeros((env.sim_steps, 4))
         for s in range(env.sim_steps):
             ou_z[s] = tr.pop("randn", (4,))                               # quad_utils.py:199
         obs_z = np.zeros(qo.OBS_Z)
-        if self.noise_on:
-            zs.append(_read_add_noise(tr, self.gyro_bias_mode))           # :988
+        if self.obs_draws:
+            zs.append(self._read_state_call(tr))                          # :988
             obs_z = zs[2].copy()
             if self.gyro_bias_mode:
                 # fold the three bias-walk updates into one effective unit normal (see oracle add_noise)
@@ -193,4 +213,5 @@ def oracle_kwargs_from_env(env, controller_id):
                 init_random_state=env.init_random_state, rew_coeff=dict(env.rew_coeff), sense_noise=sn,
                 gravity=env.gravity, dim_mode=env.dim_mode, multi_reward="pos_log_weight" in env.rew_coeff,
                 resample_goal=bool(env.resample_goal), excite=bool(env.excite),
-                dynamics_simplification=bool(env.dynamics_simplification))
+                dynamics_simplification=bool(env.dynamics_simplification), t2w_std=float(getattr(env, "t2w_std", 0.005)),
+                t2t_std=float(getattr(env, "t2t_std", 0.0005)))

@@ -72,7 +72,14 @@ def install_stubs():
 
     pyplot = _mod("matplotlib.pyplot")
     _mod("matplotlib", pyplot=pyplot)
-    _mod("transforms3d")
+    # transforms3d is absent here; QuadrotorDynamics.pitch_roll_restricted_random_state (quadrotor.py:257) needs
+    # euler.euler2mat with its default 'sxyz' axes - restated from its documented convention in the oracle
+    def _euler2mat(ai, aj, ak, axes="sxyz"):
+        assert axes == "sxyz"
+        from . import quadsim_oracle as _qo
+        return _qo.euler2mat_sxyz(np.float64(ai), np.float64(aj), np.float64(ak))
+
+    _mod("transforms3d", euler=_mod("transforms3d.euler", euler2mat=_euler2mat))
     _mod("noise")
     _mod("tensorflow")
 
@@ -108,6 +115,14 @@ def import_reference():
         import gym_art.quadrotor.get_state as get_state
         import gym_art.quadrotor.quadrotor_randomization as quad_rand
         import gym_art.quadrotor_multi.quadrotor_multi as quadrotor_multi
+    # get_state.py uses three names it never imports (`normal` :334, `R2quat` :277, `copy` :217): supply them from where
+    # the rest of the reference takes them, so the quaternion and t2w / t2t observation builders run as written.  `normal`
+    # is looked up on np.random at call time, so a NoiseTape sees its draws.
+    if not hasattr(get_state, "normal"):
+        import copy as _copy
+        get_state.normal = lambda *a, **k: np.random.normal(*a, **k)
+        get_state.R2quat = quad_utils.R2quat
+        get_state.copy = _copy
     ns = types.SimpleNamespace(
         quadrotor=quadrotor, control=control, sensor_noise=sensor_noise, quad_utils=quad_utils,
         quad_models=quad_models, inertia=inertia, get_state=get_state, quad_rand=quad_rand,

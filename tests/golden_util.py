@@ -9,9 +9,11 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# fixtures that are not single-env rollouts
+ANSWER_FILES = ("known_answer.npz", "model_answers.npz", "random_models.npz", "affine_answers.npz", "restricted_state.npz")
 
 ROLLOUT_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                       if os.path.basename(p) not in ("known_answer.npz", "model_answers.npz", "random_models.npz"))
+                       if os.path.basename(p) not in ANSWER_FILES)
 
 
 class Golden(object):
@@ -39,3 +41,15 @@ class Golden(object):
 def load_npz(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     return {k: z[k] for k in z.files}
+
+
+def obs_tolerance(obs_repr, obs_row, base):
+    """Per-element absolute tolerance for one observation row.  The quaternion builders use the reference's single-branch
+    R2quat (quad_utils.py:101-109): w = sqrt(1 + trace) / 2, (x, y, z) = (...) / (4 w).  Near half-turn attitudes w -> 0 and
+    rounding of the matrix entries is amplified by ~1 / w^2 in all four components - a property of the formula, in the
+    reference as much as here - so those four elements get base * max(1, 1 / w^2)."""
+    tol = np.full(np.shape(obs_row), float(base))
+    if "quat" in obs_repr.split("_"):
+        w = np.abs(np.asarray(obs_row)[..., 6])
+        tol[..., 6:10] = (base * np.maximum(1.0, 1.0 / np.maximum(w, 1e-6) ** 2))[..., None]
+    return tol

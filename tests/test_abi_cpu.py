@@ -55,7 +55,9 @@ def test_state_layout_rows(lib):
     assert (lay.rows, lay.row_ou, lay.row_prev_action, lay.row_gyro_bias, lay.row_goal) == (11, 7, 8, 9, 10)
     assert (lay.obs_dim, lay.act_dim) == (22, 2)
     dims = {"xyz_vxyz_R_omega": 18, "xyz_vxyz_R_omega_h": 19, "xyzr_vxyzr_R_omega": 18, "xyzr_vxyzr_R_omega_h": 19,
-            "xyz_vxyz_R_omega_acc_act": 25, "xyz_vxyz_R_omega_act": 22}
+            "xyz_vxyz_R_omega_acc_act": 25, "xyz_vxyz_R_omega_act": 22, "xyz_vxyz_quat_omega": 13, "xyzr_vxyzr_quat_omega": 13,
+            "xyzr_vxyzr_quat_omega_h": 14, "xyzr_vxyzr_R_omega_t2w": 19, "xyz_vxyz_R_omega_t2w": 19, "xyz_vxyz_R_omega_t2w_t2t": 20}
+    assert sorted(dims) == sorted(_lib.OBS_REPRS)
     for rep, d in dims.items():
         assert _lib.state_layout(_cfg(obs_repr=rep)).obs_dim == d
 
@@ -73,8 +75,12 @@ def test_validation_errors(lib):
     cfg.sim_steps = 0
     assert lib.qs_state_layout(C.byref(cfg), C.byref(lay)) == _lib.QS_EINVAL
     cfg = _cfg(dim_mode="1D", controller="vertical")
-    cfg.init_random_state = 1
-    assert lib.qs_state_layout(C.byref(cfg), C.byref(lay)) == _lib.QS_EUNSUPPORTED
+    cfg.init_random_state = _lib.QS_INIT_RANDOM                          # quadrotor.py:1101-1103: legal in every dim_mode
+    assert lib.qs_state_layout(C.byref(cfg), C.byref(lay)) == _lib.QS_OK
+    cfg.init_random_state = _lib.QS_INIT_PITCH_ROLL_RESTRICTED           # a 3D law (Euler angles -> R)
+    assert lib.qs_state_layout(C.byref(cfg), C.byref(lay)) == _lib.QS_EINVAL
+    cfg.init_random_state = 7
+    assert lib.qs_state_layout(C.byref(cfg), C.byref(lay)) == _lib.QS_EINVAL
     with pytest.raises(_lib.QuadsimError):
         _lib.check(_lib.QS_EINVAL)
     # NULL handles are rejected, not dereferenced
@@ -88,7 +94,7 @@ def test_reference_value_errors():
     with pytest.raises(ValueError, match="sense_noise"):
         _cfg(sense_noise=3.0)
     with pytest.raises(ValueError):
-        _cfg(obs_repr="xyz_vxyz_quat_omega")
+        _cfg(obs_repr="xyz_vxyz_euler_omega")                             # cannot run in the reference (undefined local `euler`, get_state.py:426)
     with pytest.raises(AssertionError):
         _cfg(rew_coeff={"poss": 1.0})
 

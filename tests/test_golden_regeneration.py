@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import ref_shim
-from tests.golden_util import GOLDEN_DIR
+from tests.golden_util import ANSWER_FILES, GOLDEN_DIR
 
 pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="needs the reference tree (/root/reference)")
 
@@ -25,7 +25,7 @@ def test_every_rollout_fixture_regenerates_bit_for_bit_in_any_order():
     from oracle import gen_golden as gg
     names = list(gg.CASES)
     assert sorted(names) == sorted(os.path.splitext(f)[0] for f in os.listdir(GOLDEN_DIR)
-                                   if f.endswith(".npz") and f not in ("known_answer.npz", "model_answers.npz", "random_models.npz"))
+                                   if f.endswith(".npz") and f not in ANSWER_FILES)
     for name in reversed(names):                 # not the order the committed files were written in
         _same(name, gg.rollout(name))
     _same(names[0], gg.rollout(names[0]))        # and once more at the end of the process
@@ -33,14 +33,14 @@ def test_every_rollout_fixture_regenerates_bit_for_bit_in_any_order():
 
 def test_answer_files_regenerate():
     from oracle import gen_golden as gg
-    _same("known_answer", gg.known_answer())
-    _same("model_answers", gg.model_answers())
-    _same("random_models", gg.random_models())
+    assert sorted(n + ".npz" for n in gg.ANSWER_FILES) == sorted(ANSWER_FILES)
+    for name, fn in gg.ANSWER_FILES.items():
+        _same(name, fn())
 
 
 def test_all_fixtures_carry_every_key():
     for f in os.listdir(GOLDEN_DIR):
-        if f.endswith(".npz") and f not in ("known_answer.npz", "model_answers.npz", "random_models.npz"):
+        if f.endswith(".npz") and f not in ANSWER_FILES:
             z = np.load(os.path.join(GOLDEN_DIR, f))
             for k in ("goal", "goal_z", "reset_goal_z", "ou_z", "obs_z", "reset_z", "meta_json"):
                 assert k in z.files, (f, k)

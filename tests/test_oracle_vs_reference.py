@@ -127,3 +127,72 @@ def test_live_moving_goals_excite_and_resample():
              excite=True, sense_noise="default", act_fn=lambda rng: np.zeros(4))
     _compare(260, seed=51, dynamics_params="Crazyflie", ep_time=0.3, resample_goal=True, init_random_state=True)
     _compare(160, seed=52, dynamics_params="Crazyflie", ep_time=0.3, resample_goal=True, excite=True)
+
+
+def test_live_t2w_noise_is_drawn_even_when_sensor_noise_is_bypassed():
+    """get_state.py:334-337 draws the t2w / t2t normals itself, outside SensorNoise: they are there with sense_noise=None."""
+    _compare(150, seed=60, ep_time=0.4, sense_noise=None, obs_repr="xyz_vxyz_R_omega_t2w_t2t")
+    _compare(150, controller_id=qo.CTRL_MELLINGER, seed=61, raw_control=False, ep_time=0.4, sense_noise="default",
+             obs_repr="xyzr_vxyzr_R_omega_t2w", t2w_std=0.4)          # wide enough to hit the clip at t2w_min / t2w_max
+
+
+def test_live_random_init_in_1d_and_2d():
+    """quadrotor.py:1101-1110: init_random_state with dim_mode 1D (upward velocity only) and 2D (pitch plane)."""
+    _compare(200, controller_id=qo.CTRL_VERTICAL, seed=62, dim_mode="1D", ep_time=0.3, init_random_state=True)
+    from oracle import ref_harness as rh
+    rr = rh.ReferenceRunner(seed=63, dim_mode="2D", ep_time=0.3, init_random_state=True, sense_noise="default")
+    oe = qo.OracleVecEnv(rr.env.dynamics_params, 1, auto_reset=False, **rh.oracle_kwargs_from_env(rr.env, qo.CTRL_VERTPLANE))
+    for _ in range(20):                      # the 2D env cannot step in the reference (see the test above): resets only
+        obs_r, rz = rr.reset()
+        obs_o = oe.reset(reset_z=rz[None])
+        np.testing.assert_allclose(obs_o[0], obs_r, rtol=0, atol=ATOL)
+        d = rr.env.dynamics
+        for k, v in (("pos", d.pos), ("vel", d.vel), ("rot", d.rot), ("omega", d.omega)):
+            np.testing.assert_allclose(getattr(oe, k)[0], v, rtol=0, atol=ATOL)
+
+
+def test_live_affine_F_and_G():
+    """quadrotor.py:461-518 for both shipped models, all three dim_modes, with damping terms switched on."""
+    import contextlib
+    import io
+    ref = ref_shim.import_reference()
+    rng = np.random.RandomState(3)
+    for name in ("defaultquad_params", "crazyflie_params"):
+        params = getattr(ref.quad_models, name)()
+        params["damp"]["omega_quadratic"], params["damp"]["vel"] = 0.015, 0.001
+        m = qo.model_constants(params)
+        for dm in ("1D", "2D", "3D"):
+            with contextlib.redirect_stdout(io.StringIO()):
+                d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2, dim_mode=dm)
+            S = rng.uniform(-3, 3, (6, 21))
+            S[:, 15:18] *= 4.0
+            for s in S:
+                np.testing.assert_allclose(qo.affine_F(m, s, 0.005)[0], d.F(s, 0.005), rtol=0, atol=1e-12)
+                np.testing.assert_allclose(qo.affine_G(m, s, dm)[0], d.G(s), rtol=0, atol=1e-12)
+
+
+def test_live_pitch_roll_restricted_random_state():
+    """QuadrotorDynamics.pitch_roll_restricted_random_state (quadrotor.py:243-259) under the tape, against the oracle's
+    INIT_PITCH_ROLL_RESTRICTED reset fed with the same draws (transforms3d's euler2mat restated, see oracle/ref_shim.py)."""
+    import contextlib
+    import io
+    ref = ref_shim.import_reference()
+    params = ref.quad_models.crazyflie_params()
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = ref.quadrotor.QuadrotorDynamics(model_params=params, dynamics_steps_num=2)
+    tape = ref_shim.NoiseTape(ref, seed=64)
+    kw = dict(pitch_max=0.4, roll_max=0.7, yaw_max=2.5)
+    oe = qo.OracleVecEnv(params, 1, auto_reset=False, init_random_state="pitch_roll_restricted", **kw)
+    oe.max_init_vel, oe.max_init_omega = 3.0, 5.0
+    for _ in range(25):
+        with tape:
+            pos, vel, rot, omega = d.pitch_roll_restricted_random_state(box=2.0, vel_max=3.0, omega_max=5.0, **kw)
+        log = [v for k, v in tape.take()]
+        rz = np.zeros((1, qo.RESET_Z))
+        rz[0, qo.RZ_UVEL:qo.RZ_UVEL + 3], rz[0, qo.RZ_UVELMAG] = log[1], log[2]
+        rz[0, qo.RZ_UOM:qo.RZ_UOM + 3], rz[0, qo.RZ_UOMMAG] = log[3], log[4]
+        rz[0, qo.RZ_NUP:qo.RZ_NUP + 3] = log[5], log[6], log[7]             # pitch, roll, yaw
+        oe.reset(reset_z=rz)
+        np.testing.assert_allclose(oe.vel[0], vel, rtol=0, atol=ATOL)
+        np.testing.assert_allclose(oe.rot[0], rot, rtol=0, atol=ATOL)
+        np.testing.assert_allclose(oe.omega[0], omega.astype(np.float32).astype(np.float64), rtol=0, atol=ATOL)
