@@ -75,12 +75,13 @@ struct Params {
   int init_random /* InitMode */, auto_reset, sense_on, ou_on, gyro_bias_mode;
   int resample_goal, excite;          // moving goals (quadrotor.py:1078-1081, :957-962); the goal row is then written back
   int dyn_controller, dyn_substeps;   // qs_dynamics_step
-  int inject, need_rare;              // variant selection (host)
+  int inject, feat;                   // variant selection (host): noise source, Feat mask the configuration needs
   int tma_generic;                    // fp32 generic configuration through the TMA harness (A/B knob QUADSIM_TMA_GENERIC)
   int tma_rows;                       // rows of the state buffer (fast subset: 7 + OU + previous action)
   long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
   int pdl;                            // step kernel launched with programmatic dependent launch (see env_step_tma_kernel)
   int ow_threads;                     // threads per CTA of a one-wave launch (32, 64 or 128)
+  int ow_extra;                       // A/B knob QUADSIM_OW_EXTRA: CTA slots per SM a one-wave launch leaves to its dependent launch
   int prefetch;                       // L2 prefetch of the CTA's first tile ahead of griddepcontrol.wait: 0 off, 1 bulk, 3 lines
   int spec_draw;                      // draw the step's noise ahead of griddepcontrol.wait from a speculative clock read
   // model
@@ -93,7 +94,7 @@ struct Params {
   R pitch_max, roll_max, yaw_max;     // INIT_PITCH_ROLL_RESTRICTED (quadrotor.py:243)
   R jinv[4][4];
   R room_lo[3], room_hi[3];
-  R goal[3], spawn_box, spawn_z_min, max_init_vel, max_init_omega, coll_dist;
+  R goal[3], spawn_box, spawn_z_min, max_init_vel, max_init_omega, coll_dist, coll_k;
   int formation_on;
   R formation[32][3];                  // swarm: goal of drone a of every swarm
   // reward
@@ -106,25 +107,41 @@ struct Params {
   R gb_pi1, gb_sig1, gb_pi3, gb_sig3;   // gyro-bias walk folded over 1 (reset) / 3 (step) add_noise calls
 };
 
-// compile-time specialisation knobs; -1 = decided at run time from Params
-template <int CTRL_, int OU_, int SENSE_, bool INJECT_, bool RARE_, int SIM_ = -1, bool PLAIN_ = false, bool SWARM_ = false,
+// compile-time specialisation knobs; -1 = decided at run time from Params.
+// FEAT: which groups of rarely used features the instantiation carries (the host computes the mask a configuration needs,
+// feat_of() in quadsim_abi.cu, and picks the narrowest kernel that covers it):
+enum Feat {
+  F_NONE = 0,
+  F_DRAG = 1,     // rotor drag / rolling moment block, motor linearity != 1, velocity and omega^2 damping (quadrotor.py:302-349, :403, :431)
+  F_NOISEX = 2,   // uniform position / velocity noise, quaternion noise, gyro-bias random walk (sensor_noise.py:116-170)
+  F_MISC = 4,     // dim_mode 1D / 2D, per-env and moving goals, info buffer, swarms outside the common shape, quaternion / t2w /
+                  // t2t observations, pitch-roll-restricted spawn
+  F_ALL = 7
+};
+template <int CTRL_, int OU_, int SENSE_, bool INJECT_, int FEAT_, int SIM_ = -1, bool PLAIN_ = false, bool SWARM_ = false,
           bool PEM_ = false>
 struct Traits {
+  static_assert(FEAT_ >= 0 && FEAT_ <= F_ALL, "FEAT is a Feat mask");
   static constexpr bool PEM = PEM_;     // per-env model constants (dynamics randomisation), read from the model buffer
-  static constexpr bool SWARM = SWARM_ || RARE_;   // n_agents > 1 handled: contact stage, formation goals, log-distance reward
+  static constexpr int FEAT = FEAT_;
+  static constexpr bool DRAG = (FEAT_ & F_DRAG) != 0, NOISEX = (FEAT_ & F_NOISEX) != 0, MISC = (FEAT_ & F_MISC) != 0;
+  static constexpr bool SWARM = SWARM_ || MISC;    // n_agents > 1 handled: contact stage, formation goals, log-distance reward
   static constexpr int CTRL = CTRL_;
   static constexpr int SIM = SIM_;      // compile-time sim_steps (substep loop unrolled, OU draws hoisted), -1 = run time
   static constexpr bool PLAIN = PLAIN_; // one env step per launch, 18-word observation, no previous-action row
   static constexpr int OU = OU_;
   static constexpr int SENSE = SENSE_;
   static constexpr bool INJECT = INJECT_;
-#ifdef QS_EXP_NO_FASTM
+  // MUFU-based sqrt / rsqrt / small-angle sincos forms of the fp32 build (~2 ulp; the fp64 build never takes them).  The
+  // per-step parity tests run the injected-noise twins of the same instantiations.
+#if defined(QS_EXP_NO_FASTM)
   static constexpr bool FASTM = false;
+#elif defined(QS_EXP_GEN_NO_FASTM)
+  static constexpr bool FASTM = FEAT_ == F_NONE;
 #else
-  static constexpr bool FASTM = !RARE_; // MUFU-based sqrt / rsqrt / small-angle sincos forms (fp32 fast subset only)
+  static constexpr bool FASTM = true;
 #endif
-  static constexpr bool RARE = RARE_;   // drag/roll, linearity != 1, damping, uniform/quaternion/gyro-bias noise,
-                                        // log reward, swarm, dim_mode != 3, per-env goal, info buffer
+  static constexpr bool RARE = FEAT_ != F_NONE;
 };
 
 // replay of `since_last_svd += dt; if since_last_svd > limit: ...; since_last_svd = 0` in double (quadrotor.py:381-386)
@@ -476,10 +493,8 @@ __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long lo
   if (active) {
     if (ou_on) { V4<R> q = ld4(p.state, p.n, p.row_ou, i); s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
     if (!T::PLAIN && p.row_act >= 0) { V4<R> q = ld4(p.state, p.n, p.row_act, i); s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
-    if (T::RARE) {
-      if (p.row_gyro >= 0) { V4<R> q = ld4(p.state, p.n, p.row_gyro, i); s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; }
-      if (p.row_goal >= 0) { V4<R> q = ld4(p.state, p.n, p.row_goal, i); s.gx = q.x; s.gy = q.y; s.gz = q.z; }
-    }
+    if (T::NOISEX) { if (p.row_gyro >= 0) { V4<R> q = ld4(p.state, p.n, p.row_gyro, i); s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; } }
+    if (T::MISC) { if (p.row_goal >= 0) { V4<R> q = ld4(p.state, p.n, p.row_goal, i); s.gx = q.x; s.gy = q.y; s.gz = q.z; } }
   }
   finish_load(s);
 }
@@ -514,11 +529,9 @@ __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, 
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (ou_on) st4(p.state, p.n, p.row_ou, i, s.ou[0], s.ou[1], s.ou[2], s.ou[3]);
   if (!T::PLAIN && p.row_act >= 0) st4(p.state, p.n, p.row_act, i, s.pa[0], s.pa[1], s.pa[2], s.pa[3]);
-  if (T::RARE) {
-    if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0));
-    // the goal row is read-only for the step path unless the goal moves
-    if (p.row_goal >= 0 && (p.resample_goal || p.excite)) st4(p.state, p.n, p.row_goal, i, s.gx, s.gy, s.gz, R(0));
-  }
+  if (T::NOISEX) { if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0)); }
+  // the goal row is read-only for the step path unless the goal moves
+  if (T::MISC) { if (p.row_goal >= 0 && (p.resample_goal || p.excite)) st4(p.state, p.n, p.row_goal, i, s.gx, s.gy, s.gz, R(0)); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -564,7 +577,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     cd = clampr(cd, R(0), R(1));                                        // :300
     s.cd[k] = cd;
     R t;
-    if (T::RARE) t = m.thrust_max(k) * ((R(1) - m.lin()) * cd * cd + m.lin() * cd);   // :302, :140
+    if (T::DRAG) t = m.thrust_max(k) * ((R(1) - m.lin()) * cd * cd + m.lin() * cd);   // :302, :140
     else t = m.thrust_max(k) * cd;                                      // linearity == 1
     tqx += m.pcx(k) * t;                                                // :304, :310
     tqy += m.pcy(k) * t;
@@ -572,7 +585,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     tsum += t;                                                          // :362
   }
   R fdx = R(0), fdy = R(0), fdz = R(0);                                 // rotor drag force (body frame)
-  if (T::RARE) {
+  if (T::DRAG) {
     if (m.c_drag() != R(0) || m.c_roll() != R(0)) {                         // :318-349
       R vbx = s.r[0] * s.vx + s.r[3] * s.vy + s.r[6] * s.vz;            // rot.T @ vel
       R vby = s.r[1] * s.vx + s.r[4] * s.vy + s.r[7] * s.vz;
@@ -645,7 +658,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     s.ody = m.inv_inertia(1) * (gy + tqy);
     s.odz = m.inv_inertia(2) * (gz + tqz);
     R fx = dt, fy = dt, fz = dt;
-    if (T::RARE) {
+    if (T::DRAG) {
       R w2x = s.wx * s.wx, w2y = s.wy * s.wy, w2z = s.wz * s.wz;
       if (sizeof(R) == 8 && s.w_is_f32) {   // omega ** 2 on the float32 array set_state left behind (:223, :403)
         w2x = (R)((float)s.wx * (float)s.wx); w2y = (R)((float)s.wy * (float)s.wy); w2z = (R)((float)s.wz * (float)s.wz);
@@ -665,7 +678,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
   s.pz = clampr(s.pz + dt * s.vz, p.room_lo[2], p.room_hi[2]);
   R bx = fdx, by = fdy, bz = tsum + fdz;                                // thrust + rotor_drag_force (body)
   R ax, ay, az;
-  if (T::RARE) {
+  if (T::DRAG) {
     ax = m.inv_mass() * (s.r[0] * bx + s.r[1] * by + s.r[2] * bz);
     ay = m.inv_mass() * (s.r[3] * bx + s.r[4] * by + s.r[5] * bz);
     az = m.inv_mass() * (s.r[6] * bx + s.r[7] * by + s.r[8] * bz) - R(9.81);
@@ -675,7 +688,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
     az = m.inv_mass() * (s.r[8] * bz) - R(9.81);                          // GRAV constant, not self.gravity (:426)
   }
   s.ax = ax; s.ay = ay; s.az = az;
-  if (T::RARE) {
+  if (T::DRAG) {
     R vd = R(1) - m.vel_damp();
     s.vx = vd * s.vx + dt * ax; s.vy = vd * s.vy + dt * ay; s.vz = vd * s.vz + dt * az;   // :431
   } else {
@@ -936,7 +949,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Md
   for (int k = 0; k < 9; ++k) rr[k] = s.r[k];
   R acc[3] = {R(0), R(0), R(0)};
   const bool obs_acc = !T::PLAIN && p.obs_acc, obs_rel = !T::PLAIN && p.obs_rel;
-  const bool obs_quat = T::RARE && p.obs_quat;
+  const bool obs_quat = T::MISC && p.obs_quat;
   if (obs_acc) accelerometer(s, p, acc);
   R qo[4] = {R(1), R(0), R(0), R(0)};
   if (obs_quat) {                                                       // R2quat, quad_utils.py:101-109 (single branch)
@@ -949,20 +962,20 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Md
     if (zpre) { z[0] = zpre[0]; z[1] = zpre[1]; z[2] = zpre[2]; } else
     ns.obs3(reset_obs, 0, false, z);                                    // :116-118
     px += p.sn_pos_std * z[0]; py += p.sn_pos_std * z[1]; pz += p.sn_pos_std * z[2];
-    if (T::RARE && p.sn_pos_unif != R(0)) {
+    if (T::NOISEX && p.sn_pos_unif != R(0)) {
       ns.obs3(reset_obs, 1, true, z);
       px += p.sn_pos_unif * z[0]; py += p.sn_pos_unif * z[1]; pz += p.sn_pos_unif * z[2];
     }
     if (zpre) { z[0] = zpre[3]; z[1] = zpre[4]; z[2] = zpre[5]; } else
     ns.obs3(reset_obs, 2, false, z);                                    // :122-124
     vx += p.sn_vel_std * z[0]; vy += p.sn_vel_std * z[1]; vz += p.sn_vel_std * z[2];
-    if (T::RARE && p.sn_vel_unif != R(0)) {
+    if (T::NOISEX && p.sn_vel_unif != R(0)) {
       ns.obs3(reset_obs, 3, true, z);
       vx += p.sn_vel_unif * z[0]; vy += p.sn_vel_unif * z[1]; vz += p.sn_vel_unif * z[2];
     }
     if (zpre) { z[0] = zpre[6]; z[1] = zpre[7]; z[2] = zpre[8]; } else
     ns.obs3(reset_obs, 4, false, z);
-    if (T::RARE && p.gyro_bias_mode) {                                  // :127-128, :162-170 (walk folded over the calls)
+    if (T::NOISEX && p.gyro_bias_mode) {                                  // :127-128, :162-170 (walk folded over the calls)
       R pi_ = reset_obs ? p.gb_pi1 : p.gb_pi3, sg = reset_obs ? p.gb_sig1 : p.gb_sig3;
       s.gb[0] = pi_ * s.gb[0] + sg * z[0]; s.gb[1] = pi_ * s.gb[1] + sg * z[1]; s.gb[2] = pi_ * s.gb[2] + sg * z[2];
       R z2[3];
@@ -974,13 +987,14 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Md
     // rotation: R -> quaternion -> (x small-angle quaternion) -> R (:134-147).  Without quaternion noise (the default,
     // and the only case in the fast subset) the float64 reference's round trip returns R to 1e-15; an fp32 round trip
     // would only add rounding, so the fast kernels pass R through.
-    if (!T::FASTM) {
+    const bool quat_noise = T::NOISEX && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0));
+    if (sizeof(R) == 8 || !T::FASTM || quat_noise || obs_quat) {
       if (obs_quat) {                                                   // rot.shape == (4,): quat x noise quaternion (:148-151)
-        if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) noise_quat<R, T>(p, ns, reset_obs, qo);
+        if (quat_noise) noise_quat<R, T>(p, ns, reset_obs, qo);
       } else {
         R q[4];
         rot2quat<R, T::FASTM>(s.r, q);
-        if (T::RARE && (p.sn_quat_std != R(0) || p.sn_quat_unif != R(0))) noise_quat<R, T>(p, ns, reset_obs, q);
+        if (quat_noise) noise_quat<R, T>(p, ns, reset_obs, q);
         R qw = q[0], qx = q[1], qy = q[2], qz = q[3];                   // quad_utils.py:82-87
         rr[0] = R(1) - R(2) * qy * qy - R(2) * qz * qz; rr[1] = R(2) * qx * qy - R(2) * qz * qw; rr[2] = R(2) * qx * qz + R(2) * qy * qw;
         rr[3] = R(2) * qx * qy + R(2) * qz * qw; rr[4] = R(1) - R(2) * qx * qx - R(2) * qz * qz; rr[5] = R(2) * qy * qz - R(2) * qx * qw;
@@ -1012,7 +1026,7 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Md
   o[18] = pz;
   o[19] = acc[0]; o[20] = acc[1]; o[21] = acc[2];
   o[22] = act_prev[0]; o[23] = act_prev[1]; o[24] = act_prev[2]; o[25] = act_prev[3];
-  if (T::RARE) {
+  if (T::MISC) {
     o[26] = qo[0]; o[27] = qo[1]; o[28] = qo[2]; o[29] = qo[3];
     o[30] = R(0); o[31] = R(0);
     if (p.obs_t2w) {            // get_state.py:334-337, :379-382: drawn by the builder itself, SensorNoise bypassed or not
@@ -1080,7 +1094,7 @@ __device__ __forceinline__ void flush_tile(const Params<R>& p, const R* tile, lo
 template <typename R, class T>
 __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const NoiseSrc<R, T>& ns) {
   const R PI = R(3.14159265358979323846);
-  if (T::RARE) {
+  if (T::MISC) {
     if (p.resample_goal || p.excite) {                                  // :1078-1081: the goal is re-made at every reset
       s.gx = p.goal[0]; s.gy = p.goal[1]; s.gz = p.goal[2];
       if (p.resample_goal) {
@@ -1094,14 +1108,14 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
   if (T::INJECT) { u[0] = ns.reset_at(0); u[1] = ns.reset_at(1); u[2] = ns.reset_at(2); u[3] = ns.reset_at(3); }
   else ns.rng.unif4(SLOT_RESET_POS, u);
   R x = p.spawn_box * u[0] + s.gx, y = p.spawn_box * u[1] + s.gy, z = p.spawn_box * u[2] + s.gz;   // :1087
-  if (T::RARE) {
+  if (T::MISC) {
     if (p.dim_mode == 1) { x = s.gx; y = s.gy; }                        // :1089-1092
     else if (p.dim_mode == 2) { y = s.gy; }
   }
   if (z < p.spawn_z_min) z = p.spawn_z_min;                             // :1094 (0.25)
   s.px = x; s.py = y; s.pz = z;
-  const bool restricted = T::RARE && p.init_random == INIT_PITCH_ROLL_RESTRICTED;
-  if (T::RARE && p.init_random && p.dim_mode != 3) {                    // :1101-1110 (rand() = (1 + u) / 2 of a unit draw)
+  const bool restricted = T::MISC && p.init_random == INIT_PITCH_ROLL_RESTRICTED;
+  if (T::MISC && p.init_random && p.dim_mode != 3) {                    // :1101-1110 (rand() = (1 + u) / 2 of a unit draw)
     R a[4], b[4];
     if (T::INJECT) {
 #pragma unroll
@@ -1180,7 +1194,7 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
     R psi;
     if (T::INJECT) psi = PI * u[3];                                     // the accepted randyaw() draw
     else psi = Mth<R>::atan2(-y, -x) + (PI / R(3)) * u[3];              // same law as the rejection loop :1124-1126
-    if (T::RARE) { if (p.dim_mode != 3) psi = R(0); }                   // :1120-1121
+    if (T::MISC) { if (p.dim_mode != 3) psi = R(0); }                   // :1120-1121
     R sp, cp;
     Mth<R>::sincos(psi, &sp, &cp);
     s.r[0] = cp; s.r[1] = -sp; s.r[2] = R(0);
@@ -1206,8 +1220,11 @@ __device__ __forceinline__ void reset_env(St<R>& s, const Params<R>& p, const No
 template <typename R>
 __device__ __forceinline__ R shfl(R v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-template <typename R>
-__device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p) {
+// half_thr: this drone's half of the contact distance, collision_k * arm.  One model per handle: every pair touches at
+// collision_k * 2 * arm (p.coll_dist).  Per-env models (PEM): drones of one swarm may have different arms, the pair (i, j)
+// touches at collision_k * (arm_i + arm_j) - the partner's half arrives by shuffle.
+template <typename R, bool PEM>
+__device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p, R half_thr) {
   const int M = p.n_agents;
   const int lane = threadIdx.x & 31;
   const int base = lane & ~(M - 1);
@@ -1219,7 +1236,7 @@ __device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p) {
     R qx = shfl(s.px, src), qy = shfl(s.py, src), qz = shfl(s.pz, src);
     R dx = s.px - qx, dy = s.py - qy, dz = s.pz - qz;
     R dist = Mth<R>::sqrt(dx * dx + dy * dy + dz * dz);
-    bool c = dist < p.coll_dist;
+    bool c = dist < (PEM ? half_thr + shfl(half_thr, src) : p.coll_dist);
     hit = hit || c;
     // contacts are rare: the partner's velocity is fetched (warp-convergent shuffles) only when some lane needs it
     if (__any_sync(0xffffffffu, c)) {
@@ -1310,7 +1327,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
       }
     }
     R a_prev[4] = {s.pa[0], s.pa[1], s.pa[2], s.pa[3]};                 // actions[1]
-    if (T::RARE) {
+    if (T::MISC) {
       if (p.excite) {                                                   // :957-962: a new goal every 5th tick
         const int tk = (int)s.tick;
         if (tk % 5 == 0) {
@@ -1339,11 +1356,11 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
       }
     }
     bool collided = false;
-    if (T::SWARM) { if (p.n_agents > 1) collided = swarm_collide(s, p); }
+    if (T::SWARM) { if (p.n_agents > 1) collided = swarm_collide<R, T::PEM>(s, p, T::PEM ? p.coll_k * m.arm() : R(0)); }
     // ---- crash, reward, tick, done (:974-987) ----
     bool crashed = s.pz <= m.arm();                                     // :977
     R costs[20];
-    R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::RARE && p.info) ? costs : nullptr);
+    R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::MISC && p.info) ? costs : nullptr);
     if (!Mth<R>::finite(rew) && active) atomicOr(p.status, 1);          // :633-636
     s.tick += R(1);                                                     // :986
     bool done = s.tick > (R)p.ep_len;                                   // :987
@@ -1353,7 +1370,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
 #pragma unroll
     for (int k = 0; k < 4; ++k) s.pa[k] = a[k];                         // becomes actions[1] of the next step
     const bool last = (ks == k_steps - 1);
-    if (T::RARE) {
+    if (T::MISC) {
       if (p.info != nullptr && last && active) {
         R* inf = p.info + i * INFO_DIM;
         R am[3];
@@ -1370,14 +1387,14 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
       }
     }
     // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----
-    const bool walk = T::RARE && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
+    const bool walk = T::NOISEX && p.gyro_bias_mode;                      // the gyro-bias walk advances on every call
     const bool resetting = done && p.auto_reset;
     const bool want_term = resetting && p.term_obs != nullptr;          // the obs the reference returns on its done step (:988)
     if ((last && (!resetting || want_term)) || walk) build_obs<R, T>(s, p, m, ns, false, a_prev, o, (PRE && sense) ? dr.zobs : nullptr);
     if (done) {
       if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
       if (resetting) {
-        if (want_term && last && active) obs_to_tile<R, T::PLAIN, T::RARE>(p, o, p.term_obs + i * (T::PLAIN ? 18 : p.obs_dim));
+        if (want_term && last && active) obs_to_tile<R, T::PLAIN, T::MISC>(p, o, p.term_obs + i * (T::PLAIN ? 18 : p.obs_dim));
         reset_env<R, T>(s, p, ns);
         if (last || walk) build_obs<R, T>(s, p, m, ns, true, s.pa, o);     // :1143 (actions[1] = 0 after reset)
       }
@@ -1516,7 +1533,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 constexpr int TMA_MIN_CTAS = 4;   // resident CTAs per SM the fast kernel is tuned for (registers <= 128)
-constexpr int TMA_MIN_CTAS_RARE = 3;   // the run-time-parameterised generic configuration needs ~160 registers
+constexpr int TMA_MIN_CTAS_RARE = 3;   // the catch-all configuration (every feature group, everything at run time) needs ~160 registers
+template <class T> constexpr int tma_min_ctas() { return T::FEAT == F_ALL ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS; }
 constexpr int WARPS = BLOCK / 32;
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -1552,7 +1570,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // own instantiation with the ring, the mbarriers and every CTA barrier compiled out: direct vector loads, per-warp
 // observation flush.  (tests/test_gpu_fullsize.py holds both instantiations to bit-identical results.)
 template <class T, bool ONEWAVE>
-__global__ void __launch_bounds__(BLOCK, T::RARE ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS)
+__global__ void __launch_bounds__(BLOCK, tma_min_ctas<T>())
 env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   typedef float R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1727,10 +1745,8 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       if (ou_row) { float4 q = buf[p.row_ou * BLOCK]; s.ou[0] = q.x; s.ou[1] = q.y; s.ou[2] = q.z; s.ou[3] = q.w; }
       if (act_row) { float4 q = buf[p.row_act * BLOCK]; s.pa[0] = q.x; s.pa[1] = q.y; s.pa[2] = q.z; s.pa[3] = q.w; }
       if (has_act) { float4 q = buf[rows_in * BLOCK]; a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
-      if (T::RARE) {
-        if (p.row_gyro >= 0) { float4 q = buf[p.row_gyro * BLOCK]; s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; }
-        if (p.row_goal >= 0) { float4 q = buf[p.row_goal * BLOCK]; s.gx = q.x; s.gy = q.y; s.gz = q.z; }
-      }
+      if (T::NOISEX) { if (p.row_gyro >= 0) { float4 q = buf[p.row_gyro * BLOCK]; s.gb[0] = q.x; s.gb[1] = q.y; s.gb[2] = q.z; } }
+      if (T::MISC) { if (p.row_goal >= 0) { float4 q = buf[p.row_goal * BLOCK]; s.gx = q.x; s.gy = q.y; s.gz = q.z; } }
       finish_load(s);
 
       __syncwarp();
@@ -1773,7 +1789,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       // its own 32 observation rows.  (Same run_steps instance as the pipelined path: results do not depend on which
       // path a batch size selects.)
       float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
-      obs_to_tile<R, T::PLAIN, T::RARE>(p, o, wtile + lane * obs_dim);
+      obs_to_tile<R, T::PLAIN, T::MISC>(p, o, wtile + lane * obs_dim);
       __syncwarp();
       const long long warp_first = i - lane;
       long long wrows = p.end - warp_first;
@@ -1810,7 +1826,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     }
     // observation rows: registers -> shared tile -> one bulk store per CTA
     float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
-    obs_to_tile<R, T::PLAIN, T::RARE>(p, o, tile_obs + tid * obs_dim);
+    obs_to_tile<R, T::PLAIN, T::MISC>(p, o, tile_obs + tid * obs_dim);
     if (multi) {
       fence_proxy_async();                       // generic-proxy tile writes -> async proxy
       if (tid == 0) bulk_wait_read0();           // last tile's store has drained the OTHER stage (it had a whole tile)
@@ -1891,7 +1907,7 @@ __global__ void __launch_bounds__(BLOCK) env_observe_kernel(const __grid_constan
     R o[OBS_SCRATCH];
     const Mdl<R, T::PEM> m(p, i);
     build_obs<R, T>(s, p, m, ns, true, s.pa, o);
-    if (T::RARE) { if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0)); }   // the bias walks on
+    if (T::NOISEX) { if (p.row_gyro >= 0) st4(p.state, p.n, p.row_gyro, i, s.gb[0], s.gb[1], s.gb[2], R(0)); }   // the bias walks on
     obs_to_tile(p, o, tile + threadIdx.x * p.obs_dim);
   }
   __syncthreads();
@@ -2066,8 +2082,14 @@ QS_DECL_FAST(launch_fast_shifted_philox);
 QS_DECL_FAST(launch_fast_shifted_inject);
 QS_DECL_FAST(launch_fast_velyaw_philox);
 QS_DECL_FAST(launch_fast_velyaw_inject);
-QS_DECL_FAST(launch_tma_generic_philox);     // every other fp32 configuration (qs_tma_generic.inl)
-QS_DECL_FAST(launch_tma_generic_inject);
+QS_DECL_FAST(launch_tma_generic_all_philox);    // every other fp32 configuration (qs_tma_generic.inl): catch-all ...
+QS_DECL_FAST(launch_tma_generic_all_inject);
+QS_DECL_FAST(launch_tma_generic_drag_philox);   // ... and one kernel per feature group (Feat) at sim_steps = 2
+QS_DECL_FAST(launch_tma_generic_drag_inject);
+QS_DECL_FAST(launch_tma_generic_noise_philox);
+QS_DECL_FAST(launch_tma_generic_noise_inject);
+QS_DECL_FAST(launch_tma_generic_misc_philox);
+QS_DECL_FAST(launch_tma_generic_misc_inject);
 #undef QS_DECL_FAST
 
 }  // namespace qs

@@ -12,16 +12,16 @@ static cudaError_t launch_step_t(const Params<R>& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-typedef Traits<-1, -1, -1, true, true> TGenInject;
-typedef Traits<-1, -1, -1, false, true> TGenPhilox;
-typedef Traits<-1, -1, -1, true, true, -1, false, false, true> TGenInjectPEM;     // per-env model constants
-typedef Traits<-1, -1, -1, false, true, -1, false, false, true> TGenPhiloxPEM;
+typedef Traits<-1, -1, -1, true, F_ALL> TGenInject;
+typedef Traits<-1, -1, -1, false, F_ALL> TGenPhilox;
+typedef Traits<-1, -1, -1, true, F_ALL, -1, false, false, true> TGenInjectPEM;     // per-env model constants
+typedef Traits<-1, -1, -1, false, F_ALL, -1, false, false, true> TGenPhiloxPEM;
 
 template <>
 cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, const char** name) {
   typedef QS_REAL R;
 #ifdef QS_FAST_VARIANTS
-  if (!p.need_rare && p.act_dim == 4 &&
+  if (p.feat == F_NONE && p.act_dim == 4 &&
       (p.controller == CTRL_RAW || p.controller == CTRL_OMEGA_THRUST || p.controller == CTRL_MELLINGER ||
        p.controller == CTRL_SHIFTED || p.controller == CTRL_VELOCITY_YAW)) {
     if (p.controller == CTRL_RAW) return p.inject ? launch_fast_raw_inject(p, st, name) : launch_fast_raw_philox(p, st, name);
@@ -32,8 +32,16 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
   }
 #endif
 #ifdef QS_FAST_VARIANTS
-  // fp32: everything outside the specialised subset still runs through the persistent TMA harness
-  if (p.tma_generic) return p.inject ? launch_tma_generic_inject(p, st, name) : launch_tma_generic_philox(p, st, name);
+  // fp32: everything outside the specialised subset still runs through the persistent TMA harness - a kernel that carries
+  // just the feature group the configuration needs when it is a single group at the default sim_steps, the catch-all otherwise
+  if (p.tma_generic) {
+    if (p.models == nullptr && p.sim_steps == 2) {
+      if (p.feat == F_DRAG) return p.inject ? launch_tma_generic_drag_inject(p, st, name) : launch_tma_generic_drag_philox(p, st, name);
+      if (p.feat == F_NOISEX) return p.inject ? launch_tma_generic_noise_inject(p, st, name) : launch_tma_generic_noise_philox(p, st, name);
+      if (p.feat == F_MISC || p.feat == F_NONE) return p.inject ? launch_tma_generic_misc_inject(p, st, name) : launch_tma_generic_misc_philox(p, st, name);
+    }
+    return p.inject ? launch_tma_generic_all_inject(p, st, name) : launch_tma_generic_all_philox(p, st, name);
+  }
 #endif
   if (p.models != nullptr) {
     if (p.inject) { if (name) *name = "generic-permodel-injected"; return launch_step_t<R, TGenInjectPEM>(p, st); }

@@ -1,0 +1,7 @@
+// fp32 run-time-parameterised configuration through the TMA harness: family "drag", inject noise
+#define QS_GEN_INJECT 1
+#define QS_GEN_FEAT 1
+#define QS_GEN_LABEL "drag"
+#define QS_GEN_NAME launch_tma_generic_drag_inject
+#define QS_GEN_SUFFIX "-injected"
+#include "qs_tma_generic.inl"

@@ -52,7 +52,7 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
   const long long tiles = (n + BLOCK - 1) / BLOCK;
   const size_t smem = (size_t)2 * (p.tma_rows + 1) * BLOCK * sizeof(float4) + (size_t)2 * BLOCK * p.obs_dim * sizeof(float);
   int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_RESERVED));
-  const int cap = T::RARE ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS;
+  const int cap = tma_min_ctas<T>();
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   const int sms = sm_count();
@@ -74,7 +74,9 @@ static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
     const long long ctas = (n + threads - 1) / threads;
     long long want = (ctas + sms - 1) / sms;
     const long long reg_cap = (long long)cap * (BLOCK / threads);
-    if (want > reg_cap) want = reg_cap;
+    const int extra = p.ow_extra;                      // A/B knob: CTA slots per SM left free for the dependent launch
+    want += extra;
+    if (want > reg_cap + extra) want = reg_cap + extra;
     if (want < 1) want = 1;
     size_t dyn = (SMEM_PER_SM / (size_t)want) - SMEM_RESERVED;
     dyn &= ~(size_t)127;

@@ -47,7 +47,7 @@ struct QsHandle {
   int host_streams_made;     // staged path resources, created one by one (a failed setup resumes where it stopped)
   int host_zero_copy;        // A/B knob QUADSIM_HOST_ZEROCOPY (default 1)
   int tma_generic;           // A/B knob QUADSIM_TMA_GENERIC (default 1)
-  int ow_threads, prefetch, spec_draw;   // A/B knobs QUADSIM_OW_THREADS / QUADSIM_PREFETCH / QUADSIM_SPEC_DRAW (see Params)
+  int ow_threads, ow_extra, prefetch, spec_draw;   // A/B knobs QUADSIM_OW_THREADS / QUADSIM_PREFETCH / QUADSIM_SPEC_DRAW (see Params)
 #ifdef QS_PHASE_TIMING
   unsigned long long* timing;   // QUADSIM_TIMING_PTR: stamp buffer of the experiment build (tools/build_timing.sh)
 #endif
@@ -108,7 +108,6 @@ int validate(const QsConfig* c, std::string* why) {
   if (c->n_agents < 1 || c->n_agents > 32 || !is_pow2(c->n_agents)) { *why = "n_agents must be 1, 2, 4, 8, 16 or 32"; return QS_EINVAL; }
   if (c->n_envs % c->n_agents != 0) { *why = "n_envs must be a multiple of n_agents"; return QS_EINVAL; }
   if ((c->resample_goal || c->excite) && !c->per_env_goal) { *why = "resample_goal / excite need per_env_goal (a goal row)"; return QS_EINVAL; }
-  if (c->per_env_model && c->n_agents > 1) { *why = "per-env models are not built for swarms"; return QS_EUNSUPPORTED; }
   if (c->use_formation && c->per_env_goal) { *why = "use_formation and per_env_goal are mutually exclusive"; return QS_EINVAL; }
   if (!(c->model.mass > 0.0) || !(c->model.inertia[0] > 0.0) || !(c->model.inertia[1] > 0.0) || !(c->model.inertia[2] > 0.0)) {
     *why = "model mass/inertia must be positive"; return QS_EINVAL;
@@ -133,25 +132,27 @@ void layout_of(const QsConfig* c, QsStateLayout* o) {
   o->_pad = 0;
 }
 
-bool need_rare(const QsHandle* h) {
+// which rarely used feature groups (qs::Feat) the configuration needs; 0 = the specialised fast subset
+int feat_of(const QsHandle* h) {
   const QsConfig& c = h->cfg;
   const QsModel& m = c.model;
   const QsSensorNoise& s = c.sense;
-  if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) return true;
+  int f = qs::F_NONE;
+  if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) f |= qs::F_DRAG;
   if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
-                    s.gyro_norm_std != 0.0)) return true;
-  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) return true;
-  if (c.obs_repr >= QS_OBS_XYZ_VXYZ_QUAT_OMEGA || c.init_random_state == QS_INIT_PITCH_ROLL_RESTRICTED) return true;
+                    s.gyro_norm_std != 0.0)) f |= qs::F_NOISEX;
+  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) f |= qs::F_MISC;
+  if (c.obs_repr >= QS_OBS_XYZ_VXYZ_QUAT_OMEGA || c.init_random_state == QS_INIT_PITCH_ROLL_RESTRICTED) f |= qs::F_MISC;
   // swarms (and the log-distance reward that comes with them) and per-env models have specialised kernels for the
   // common step shape only
   const bool plain = c.sim_steps == 2 && h->lay.obs_dim == 18 && h->lay.row_prev_action < 0 &&
                      c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA;
-  if ((c.n_agents > 1 || c.reward.log_pos || c.per_env_model) && !plain) return true;
-  if (c.per_env_model && c.reward.log_pos) return true;
+  if ((c.n_agents > 1 || c.reward.log_pos || c.per_env_model) && !plain) f |= qs::F_MISC;
+  if (c.per_env_model && (c.reward.log_pos || c.n_agents > 1)) f |= qs::F_MISC;   // per-env models in swarms: the catch-all twin
   // the specialised per-env-model kernels compile out linearity / rotor drag / damping (rows 8 and 9 of the model buffer):
   // they are taken only when the caller has asserted that every bound model is plain in that sense
-  if (c.per_env_model && !h->models_plain) return true;
-  return false;
+  if (c.per_env_model && !h->models_plain) f |= qs::F_DRAG;
+  return f;
 }
 
 template <typename R>
@@ -205,12 +206,12 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.gyro_bias_mode = (c.sense.enabled && c.sense.gyro_norm_std != 0.0) ? 1 : 0;
   p.dyn_controller = -1; p.dyn_substeps = c.sim_steps;
   p.inject = (c.noise_mode == QS_NOISE_INJECTED) ? 1 : 0;
-  p.need_rare = need_rare(h) ? 1 : 0;
+  p.feat = feat_of(h);
   p.tma_generic = h->tma_generic;
   p.tma_rows = h->lay.rows;
   p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
   p.pdl = h->pdl;
-  p.ow_threads = h->ow_threads; p.prefetch = 0; p.spec_draw = h->spec_draw;
+  p.ow_threads = h->ow_threads; p.ow_extra = h->ow_extra; p.prefetch = 0; p.spec_draw = h->spec_draw;
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
@@ -241,7 +242,7 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.t2t = (R)m.torque_to_thrust; p.t2w_half_std = (R)(c.t2w_std / 2.0); p.t2t_half_std = (R)(c.t2t_std / 2.0);
   p.pitch_max = (R)c.pitch_max; p.roll_max = (R)c.roll_max; p.yaw_max = (R)c.yaw_max;
   p.spawn_box = (R)c.spawn_box; p.spawn_z_min = (R)c.spawn_z_min; p.max_init_vel = (R)c.max_init_vel; p.max_init_omega = (R)c.max_init_omega;
-  p.coll_dist = (R)(c.collision_k * 2.0 * m.arm);
+  p.coll_dist = (R)(c.collision_k * 2.0 * m.arm); p.coll_k = (R)c.collision_k;
   p.formation_on = (c.use_formation && c.n_agents > 1) ? 1 : 0;
   for (int a = 0; a < 32; ++a)
     for (int k = 0; k < 3; ++k) p.formation[a][k] = (R)c.formation[a][k];
@@ -274,7 +275,7 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
   p.k_steps = k;
   if (device_buffers) p.prefetch = h->prefetch;   // the L2 prefetch hint is for device memory (not for pinned host aliases)
   p.clock_advance = advance;
-  if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos || h->cfg.per_env_model)) p.need_rare = 1;   // specialised kernels: k == 1 only
+  if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos || h->cfg.per_env_model)) p.feat |= qs::F_MISC;   // specialised kernels: k == 1 only
   if (!advance) p.pdl = 0;                       // chunk launches of the host pipeline follow copies on side streams
   p.launch_ticket = h->d_ticket + 1 + 2 * slot;
   p.tile_counter = h->d_ticket + 2 + 2 * slot;
@@ -340,6 +341,7 @@ int qs_create(const QsConfig* cfg, QsHandle** out) {
   { const char* e = getenv("QUADSIM_HOST_ZEROCOPY"); h->host_zero_copy = e ? atoi(e) : 1; }
   { const char* e = getenv("QUADSIM_TMA_GENERIC"); h->tma_generic = e ? atoi(e) : 1; }
   { const char* e = getenv("QUADSIM_OW_THREADS"); h->ow_threads = e ? atoi(e) : 64; }
+  { const char* e = getenv("QUADSIM_OW_EXTRA"); h->ow_extra = e ? atoi(e) : 0; }
   { const char* e = getenv("QUADSIM_PREFETCH"); h->prefetch = e ? atoi(e) : 3; }
   { const char* e = getenv("QUADSIM_SPEC_DRAW"); h->spec_draw = e ? atoi(e) : 1; }
 #ifdef QS_PHASE_TIMING

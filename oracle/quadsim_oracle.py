@@ -835,7 +835,10 @@ class OracleVecEnv(object):
         E = self.N // M
         p = self.pos.reshape(E, M, 3)
         v = self.vel.reshape(E, M, 3)
-        thr = self.collision_k * 2.0 * self.m["arm"]
+        # one model per oracle env: every pair touches at collision_k * 2 * arm.  arm_env ([N], optional): drones with their
+        # own models (per-env dynamics) - the pair (i, j) touches at collision_k * (arm_i + arm_j)
+        arm = getattr(self, "arm_env", None)
+        arm = np.full((E, M), self.m["arm"]) if arm is None else np.asarray(arm, dtype=np.float64).reshape(E, M)
         dv = np.zeros_like(v)
         hit = np.zeros((E, M), dtype=bool)
         for i in range(M):
@@ -846,7 +849,7 @@ class OracleVecEnv(object):
                 dist = np.sqrt(np.sum(d ** 2, axis=1))
                 n = d / np.maximum(dist, 1e-5)[:, None]
                 delta = np.sum((v[:, j] - v[:, i]) * n, axis=1)
-                c = dist < thr
+                c = dist < self.collision_k * arm[:, i] + self.collision_k * arm[:, j]
                 hit[:, i] |= c
                 dv[:, i] += np.where((c & (delta > 0))[:, None], delta[:, None] * n, 0.0)
         self.vel = (v + dv).reshape(self.N, 3)

@@ -138,3 +138,92 @@ def test_swarm_facade_shapes_and_contact_flags():
     single = QuadrotorEnvMulti(num_agents=4, seed=1)
     assert tuple(single.reset().shape) == (4, 18)
     env.close(); single.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-8), ("float32", 1e-5)])
+def test_swarm_with_per_env_models_matches_oracle(dtype, tol):
+    """Dynamics randomisation in swarms (resample_dynamics, quadrotor.py:1030-1056, has no single-drone restriction): every
+    swarm of 4 flies its own model (Hummingbird / CrazyFlie / a RandomQuad), the oracle runs the swarms of each model; fp64
+    free-running, fp32 per step from the device's state.  The contact distance follows each swarm's own arm."""
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
+    np.random.seed(4)
+    zoo = [quad_models.defaultquad_params(), quad_models.crazyflie_params(), qr.RandomQuad().sample()]
+    K, M, E, T = len(zoo), 4, 45, 80
+    n = E * M
+    index = (np.arange(n) // M) % K                               # model of a drone = model of its swarm
+    goals = np.tile(ring_goals(M, radius=0.12), (E, 1))
+    kw = dict(ep_time=0.3, sim_steps=2, collision_k=2.5, box=0.3, multi_reward=True)
+    env = QuadVecEnv(n, dynamics_params=zoo[0], controller="raw", dtype=dtype, noise_mode="injected", auto_reset=True, n_agents=M,
+                     goals=goals, rew_coeff={"collision": 0.7}, info=True, per_env_dynamics=K, **kw)
+    env.set_models(zoo, index=index)
+    sel = [np.where(index == k)[0] for k in range(K)]
+    oes = [qo.OracleVecEnv(zoo[k], len(sel[k]), controller=qo.CTRL_RAW, auto_reset=True, n_agents=M, goals=goals[sel[k]],
+                           collision_coeff=0.7, **kw) for k in range(K)]
+    rng = np.random.RandomState(21)
+    cast = (lambda x: x.astype(np.float32).astype(np.float64)) if dtype == "float32" else (lambda x: x)
+    rz = cast(rng.uniform(-1, 1, (n, qo.RESET_Z)))
+    env.set_noise(reset_z=rz)
+    o = env.reset().double().cpu().numpy()
+    for k in range(K):
+        np.testing.assert_allclose(o[sel[k]], oes[k].reset(reset_z=rz[sel[k]]), rtol=0, atol=max(tol, 1e-12))
+    fields = (("pos", "pos"), ("vel", "vel"), ("rot", "rot"), ("omega", "omega"), ("thrust_rot_damp", "rot_damp"),
+              ("thrust_cmds_damp", "cmds_damp"), ("ou_state", "ou"))
+    hits = 0
+    for t in range(T):
+        if dtype == "float32":
+            dev = {f: env.get_field(f).double().cpu().numpy() for f, _ in fields}
+            for k in range(K):
+                for f, of in fields:
+                    setattr(oes[k], of, dev[f][sel[k]].copy())
+        a, ou_z, rz = cast(rng.uniform(-0.2, 0.4, (n, 4))), cast(rng.standard_normal((n, 2, 4))), cast(rng.uniform(-1, 1, (n, qo.RESET_Z)))
+        env.set_noise(ou_z=ou_z, reset_z=rz)
+        o, r, d = env.step(a)
+        o, r, d = o.double().cpu().numpy(), r.double().cpu().numpy(), d.cpu().numpy()
+        coll = env.info[:, 17].cpu().numpy() != 0
+        for k in range(K):
+            s = sel[k]
+            oo, ro, do = oes[k].step(a[s], ou_z=ou_z[s], reset_z=rz[s])
+            assert np.array_equal(d[s], do)
+            same = coll[s] == oes[k].collided                     # fp32: a pair within an ulp of the contact distance may differ
+            assert same.all() if dtype == "float64" else same.mean() > 0.99
+            ok = np.repeat(same.reshape(-1, M).all(axis=1), M)
+            assert np.max(np.abs(o[s] - oo)[ok] / np.maximum(np.abs(oo[ok]), 1.0)) < tol, (k, t)
+            assert np.max(np.abs(r[s] - ro)[ok]) < max(tol * 0.1, 1e-9)
+        hits += int(coll.sum())
+    assert hits > 0, "the scenario must exercise the contact branch"
+    assert env.kernel_variant == ("generic-permodel-injected" if dtype == "float64" else "tma-generic-permodel-injected")
+    env.close()
+
+
+def test_mixed_model_swarm_contact_distance_is_the_sum_of_the_arms():
+    """Known answer for drones of different size in one swarm: the pair (i, j) touches iff d < collision_k (arm_i + arm_j).
+    Two drones 0.2 m apart on x, closing at 1 m/s each: arms 0.17 (Hummingbird) and 0.046 (CrazyFlie).  collision_k = 1:
+    0.216 > 0.2 -> contact, equal-mass exchange swaps the velocities; collision_k = 0.9: 0.194 < 0.2 -> nothing happens."""
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    zoo = [quad_models.defaultquad_params(), quad_models.crazyflie_params()]
+    arms = [qo.model_constants(z)["arm"] for z in zoo]
+    assert 0.9 * sum(arms) < 0.2 < sum(arms)
+    for k, swapped in ((1.0, True), (0.9, False)):
+        env = QuadVecEnv(8, dynamics_params=zoo[0], controller="raw", dtype="float64", noise_mode="injected", auto_reset=False,
+                         n_agents=2, sim_freq=1e9, sim_steps=1, ep_time=1e-6, collision_k=k, info=True, per_env_dynamics=2,
+                         goals=np.tile([0.0, 0.0, 2.0], (8, 1)))
+        env.set_models(zoo, index=np.arange(8) % 2)
+        pos = np.tile(np.array([[0.0, 0.0, 2.0], [0.2, 0.0, 2.0]]), (4, 1))
+        vel = np.tile(np.array([[1.0, 0.0, 0.0], [-1.0, 0.0, 0.0]]), (4, 1))
+        env.set_state(pos, vel, np.tile(np.eye(3), (8, 1, 1)), np.zeros((8, 3)))
+        env.step(-np.ones((8, 4)))
+        v = env.vel.cpu().numpy()
+        want = -vel if swapped else vel
+        np.testing.assert_allclose(v[:, 0], want[:, 0], rtol=0, atol=1e-6)
+        assert ((env.info[:, 17].cpu().numpy() != 0) == swapped).all()
+        # the oracle's statement of the same rule
+        oe = qo.OracleVecEnv(zoo[0], 2, n_agents=2, auto_reset=False, collision_k=k)
+        oe.arm_env = np.array(arms)
+        oe.pos, oe.vel = pos[:2].copy(), vel[:2].copy()
+        oe.collide_swarm()
+        np.testing.assert_allclose(oe.vel, want[:2], rtol=0, atol=1e-12)
+        env.close()

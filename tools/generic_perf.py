@@ -15,6 +15,10 @@ cases = [
     ("generic: rotor drag + linearity + damping", dict(controller="raw", dynamics_change=DRAG), 349, "float32"),
     ("generic: full sensor noise (uniform, quaternion, gyro bias)", dict(controller="raw", sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1)), 349 + 24, "float32"),
     ("generic: vertical controller (1D)", dict(controller="vertical", dim_mode="1D"), 349 - 12, "float32"),
+    ("misc: info buffer bound (+192 B)", dict(controller="raw", info=True), 349 + 192, "float32"),
+    ("misc: quaternion observation xyz_vxyz_quat_omega (O=13: 329 B)", dict(controller="raw", obs_repr="xyz_vxyz_quat_omega"), 329, "float32"),
+    ("misc: xyz_vxyz_R_omega_t2w_t2t + default noise (O=20: 357 B)", dict(controller="raw", obs_repr="xyz_vxyz_R_omega_t2w_t2t", sense_noise="default"), 357, "float32"),
+    ("catch-all: drag + full sensor noise", dict(controller="raw", dynamics_change=DRAG, sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1)), 349 + 24, "float32"),
     ("generic fp64 (verification build), raw", dict(controller="raw"), 2 * 349 - 1, "float64"),
 ]
 for name, kw, nbytes, dtype in cases:
@@ -23,7 +27,7 @@ for name, kw, nbytes, dtype in cases:
     env.reset()
     a = None if env.controller_name == "mellinger" else torch.rand((m, env.act_dim), device=dev, dtype=env.tdtype) * 2 - 1
     bench.RING_PERIOD[0] = 1
-    ms = bench.time_graph(torch, lambda i: env.step(a), 20, 4, dev, chunk=20)
-    us = ms * 1e3 / 20
+    ms, _ = bench.time_graph(torch, lambda i: env.step(a), 20, 4, dev, chunk=20)
+    us = ms[0] * 1e3 / 20
     print("%-78s %-22s %8.1f us  %.3e env-steps/s  frac %.2f" % (name, env.kernel_variant, us, m / us * 1e6, m * nbytes / us * 1e-3 / peak), flush=True)
     env.close()

@@ -15,7 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg4"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg4", "drag", "noise", "vertical", "info"])
     ap.add_argument("--copy", action="store_true")
     a = ap.parse_args()
     kw = dict(device="cuda:0", ep_time=5, seed=1)
@@ -26,6 +26,16 @@ def main():
                          init_random_state=True, **kw)
     elif a.config == "cfg5":
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="mellinger", **kw)
+    elif a.config == "drag":      # one feature group each (qs::Feat): the configurations of tools/generic_perf.py
+        env = QuadVecEnv(a.envs, dynamics_params="Crazyflie", controller="raw", dynamics_change={
+            "motor": {"C_drag": 0.0028, "C_roll": 0.003, "linearity": 0.424}, "damp": {"vel": 0.001, "omega_quadratic": 0.015}}, **kw)
+    elif a.config == "noise":
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw",
+                         sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1), **kw)
+    elif a.config == "vertical":
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="vertical", dim_mode="1D", **kw)
+    elif a.config == "info":
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", info=True, **kw)
     else:
         from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", n_agents=8, formation=ring_goals(8),
