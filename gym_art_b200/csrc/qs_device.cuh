@@ -31,6 +31,19 @@ struct Clock {
   unsigned long long step;
 };
 
+// QS_DEBUG_BOUNDS build (tools/build_bounds.sh -> _exp/libquadsim_bounds.so; compute-sanitizer is not available on the GPU
+// pool): every index / pointer the kernels derive - env ranges, optional state rows, the bulk-copy ring, the observation
+// tiles, the tile scheduler, tickets - is checked against its bound BEFORE the access.  A failed check does not trap (the
+// access that follows might): it ORs bit 1 and its code into the handle's status word, which qs_check reports.
+#ifdef QS_DEBUG_BOUNDS
+#define QS_CHECK(p, cond, code) do { if (!(cond)) atomicOr((p).status, 2 | ((code) << 8)); } while (0)
+__device__ __forceinline__ unsigned int dyn_smem_bytes() { unsigned int v; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v)); return v; }
+#else
+#define QS_CHECK(p, cond, code) do { } while (0)
+#endif
+enum BoundsCode { BC_ENV = 1, BC_ROW = 2, BC_MODEL = 4, BC_RING = 8, BC_SRC = 16, BC_OBS_SMEM = 32, BC_OBS_GLOBAL = 64, BC_TILE = 128,
+                  BC_TICKET = 256, BC_INFO = 512, BC_ACTION = 1024, BC_SELFTEST = 2048 };
+
 // ---------------------------------------------------------------------------------------------------------
 // kernel parameter block (passed by value as a __grid_constant__; lives in the constant bank)
 // ---------------------------------------------------------------------------------------------------------
@@ -81,9 +94,11 @@ struct Params {
   long long row_bytes;                // byte stride between state rows = n * 4 * sizeof(real)
   int pdl;                            // step kernel launched with programmatic dependent launch (see env_step_tma_kernel)
   int ow_threads;                     // threads per CTA of a one-wave launch (32, 64 or 128)
+  int obs_stages;                     // pipelined launch: observation tiles in shared memory (2, or 1 when that buys a resident CTA)
   int ow_extra;                       // A/B knob QUADSIM_OW_EXTRA: CTA slots per SM a one-wave launch leaves to its dependent launch
   int prefetch;                       // L2 prefetch of the CTA's first tile ahead of griddepcontrol.wait: 0 off, 1 bulk, 3 lines
   int spec_draw;                      // draw the step's noise ahead of griddepcontrol.wait from a speculative clock read
+  int bounds_selftest;                // QS_DEBUG_BOUNDS builds: raise BC_SELFTEST (proves the reporting path end to end)
   // model
   R dt;
   R thrust_max[4], tz[4], pcx[4], pcy[4], ppx[4], ppy[4], ppz[4], ccw[4];
@@ -114,9 +129,10 @@ enum Feat {
   F_NONE = 0,
   F_DRAG = 1,     // rotor drag / rolling moment block, motor linearity != 1, velocity and omega^2 damping (quadrotor.py:302-349, :403, :431)
   F_NOISEX = 2,   // uniform position / velocity noise, quaternion noise, gyro-bias random walk (sensor_noise.py:116-170)
-  F_MISC = 4,     // dim_mode 1D / 2D, per-env and moving goals, info buffer, swarms outside the common shape, quaternion / t2w /
-                  // t2t observations, pitch-roll-restricted spawn
-  F_ALL = 7
+  F_MISC = 4,     // dim_mode 1D / 2D, per-env and moving goals, swarms outside the common shape, quaternion / t2w / t2t
+                  // observations, pitch-roll-restricted spawn
+  F_INFO = 8,     // diagnostics buffer (qs_bind_info): 48 words per env step, every raw and weighted reward term
+  F_ALL = 15
 };
 template <int CTRL_, int OU_, int SENSE_, bool INJECT_, int FEAT_, int SIM_ = -1, bool PLAIN_ = false, bool SWARM_ = false,
           bool PEM_ = false>
@@ -125,6 +141,7 @@ struct Traits {
   static constexpr bool PEM = PEM_;     // per-env model constants (dynamics randomisation), read from the model buffer
   static constexpr int FEAT = FEAT_;
   static constexpr bool DRAG = (FEAT_ & F_DRAG) != 0, NOISEX = (FEAT_ & F_NOISEX) != 0, MISC = (FEAT_ & F_MISC) != 0;
+  static constexpr bool INFO = (FEAT_ & F_INFO) != 0;
   static constexpr bool SWARM = SWARM_ || MISC;    // n_agents > 1 handled: contact stage, formation goals, log-distance reward
   static constexpr int CTRL = CTRL_;
   static constexpr int SIM = SIM_;      // compile-time sim_steps (substep loop unrolled, OU draws hoisted), -1 = run time
@@ -369,7 +386,7 @@ template <typename R> struct Mdl<R, false> {
 template <typename R> struct Mdl<R, true> {
   const R* base;          // element 0 of this env's vector in row 0
   long long stride;       // elements between rows
-  __device__ __forceinline__ Mdl(const Params<R>& p, long long i) : base(p.models + i * 4), stride(p.n * 4) {}
+  __device__ __forceinline__ Mdl(const Params<R>& p, long long i) : base(p.models + i * 4), stride(p.n * 4) { QS_CHECK(p, i >= 0 && i < p.n, BC_MODEL); }
   __device__ __forceinline__ R at(int row, int c) const { return __ldg(base + row * stride + c); }
   __device__ __forceinline__ R thrust_max(int k) const { return at(0, k); }
   __device__ __forceinline__ R tz(int k) const { return at(1, k); }
@@ -474,6 +491,8 @@ __device__ __forceinline__ void finish_load(St<R>& s) {
 
 template <typename R, class T>
 __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long long i, bool active) {
+  QS_CHECK(p, !active || (i >= p.begin && i < p.end && p.end <= p.n), BC_ENV);
+  QS_CHECK(p, p.row_ou < p.tma_rows && p.row_act < p.tma_rows && p.row_gyro < p.tma_rows && p.row_goal < p.tma_rows && p.tma_rows >= 7, BC_ROW);
   if (active) {
     const char* ptr = reinterpret_cast<const char*>(p.state + i * 4);   // row 0; rows are row_bytes apart
     const long long rb = p.row_bytes;
@@ -516,6 +535,7 @@ __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, 
   st4(p.state, p.n, 5, i, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
   st4(p.state, p.n, 6, i, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
 #else
+  QS_CHECK(p, i >= p.begin && i < p.end && p.end <= p.n && p.row_bytes == p.n * 4 * (long long)sizeof(R), BC_ENV);
   char* ptr = reinterpret_cast<char*>(p.state + i * 4);                 // row 0; rows are row_bytes apart
   const long long rb = p.row_bytes;
   st4p(ptr, rb, s.px, s.py, s.pz, s.vx);
@@ -595,7 +615,7 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
       for (int k = 0; k < 4; ++k) {
         R vrx = vbx + (s.wy * m.ppz(k) - s.wz * m.ppy(k));              // :323 omega x prop_pos
         R vry = vby + (s.wz * m.ppx(k) - s.wx * m.ppz(k));              // z component projected out (:325)
-        R sq = Mth<R>::sqrt(s.cd[k]);
+        R sq = q_sqrt<R, T::FASTM>(s.cd[k]);
         R fx = -m.c_drag() * sq * vrx, fy = -m.c_drag() * sq * vry;         // :328
         fdx += fx; fdy += fy;
         dtx += fy * m.ppz(k);                                           // :331 f x prop_pos (f.z = 0)
@@ -605,14 +625,31 @@ __device__ __forceinline__ void substep(St<R>& s, const R* cmd, const Params<R>&
         rty += -m.c_roll() * p.ccw[k] * sq * vry;
       }
       R vtx = dtx + rtx, vty = dty + rty, vtz = dtz;                    // :336
+      R iwx = s.wx * m.inertia(0), iwy = s.wy * m.inertia(1), iwz = s.wz * m.inertia(2);
+      if (T::FASTM && sizeof(R) == 4) {
+        // fp32: norms by MUFU.RSQ (x * rsqrt(x)), the two rescalings by the reciprocal norm already at hand - no IEEE
+        // square roots or divisions (they were 280 of this kernel's 1,880 instructions per env step)
+        const R hid = R(0.5) / dt;
+        R vel_norm = q_sqrt<R, true>(vbx * vbx + vby * vby + vbz * vbz);  // :339
+        R rdf2 = fdx * fdx + fdy * fdy;                                   // :340
+        R irdf = q_rsqrt<R, true>(Mth<R>::max(rdf2, R(1e-30)));
+        R rdf = rdf2 * irdf;
+        R rdf_clip = clampr(rdf, R(0), vel_norm * m.mass() * hid);        // :341
+        if (rdf > R(1e-6)) { R sc = rdf_clip * irdf; fdx = fdx * sc; fdy = fdy * sc; }   // :342-343
+        R rvt2 = vtx * vtx + vty * vty + vtz * vtz;                       // :346
+        R irvt = q_rsqrt<R, true>(Mth<R>::max(rvt2, R(1e-30)));
+        R rvt = rvt2 * irvt;
+        R rvt_clip = clampr(rvt, R(0), q_sqrt<R, true>(iwx * iwx + iwy * iwy + iwz * iwz) * hid);   // :347
+        if (rvt > R(1e-6)) { R sc = rvt_clip * irvt; vtx = vtx * sc; vty = vty * sc; vtz = vtz * sc; }
+      } else {
       R vel_norm = Mth<R>::sqrt(vbx * vbx + vby * vby + vbz * vbz);     // :339
       R rdf = Mth<R>::sqrt(fdx * fdx + fdy * fdy);                      // :340
       R rdf_clip = clampr(rdf, R(0), vel_norm * m.mass() / (R(2) * dt));  // :341
       if (rdf > R(1e-6)) { R sc = rdf_clip; fdx = (fdx / rdf) * sc; fdy = (fdy / rdf) * sc; }   // :342-343
       R rvt = Mth<R>::sqrt(vtx * vtx + vty * vty + vtz * vtz);          // :346
-      R iwx = s.wx * m.inertia(0), iwy = s.wy * m.inertia(1), iwz = s.wz * m.inertia(2);
       R rvt_clip = clampr(rvt, R(0), Mth<R>::sqrt(iwx * iwx + iwy * iwy + iwz * iwz) / (R(2) * dt));   // :347
       if (rvt > R(1e-6)) { vtx = (vtx / rvt) * rvt_clip; vty = (vty / rvt) * rvt_clip; vtz = (vtz / rvt) * rvt_clip; }
+      }
       tqx += vtx; tqy += vty; tqz += vtz;                               // :361
     }
   }
@@ -920,18 +957,23 @@ __device__ __forceinline__ void rot2quat(const R* r, R* q) {            // senso
 // quad_utils.py:92-99)
 template <typename R, class T>
 __device__ __forceinline__ void noise_quat(const Params<R>& p, const NoiseSrc<R, T>& ns, bool reset_obs, R* q) {
-  R zn[3], zu[3];
-  ns.obs3(reset_obs, 6, false, zn);
-  ns.obs3(reset_obs, 7, true, zu);
+  R zn[3] = {R(0), R(0), R(0)}, zu[3] = {R(0), R(0), R(0)};
+  if (p.sn_quat_std != R(0)) ns.obs3(reset_obs, 6, false, zn);        // a zero scale needs no draw (every slot has its own counter)
+  if (p.sn_quat_unif != R(0)) ns.obs3(reset_obs, 7, true, zu);
   R tx = p.sn_quat_std * zn[0] + p.sn_quat_unif * zu[0], ty = p.sn_quat_std * zn[1] + p.sn_quat_unif * zu[1];
   R tz = p.sn_quat_std * zn[2] + p.sn_quat_unif * zu[2];
   R qs = (tx * tx + ty * ty + tz * tz) / R(4);                          // sensor_noise.py:9-21
   R t0, f;
-  if (qs < R(1)) { t0 = Mth<R>::sqrt(R(1) - qs); f = R(0.5); }
-  else { t0 = R(1) / Mth<R>::sqrt(R(1) + qs); f = R(0.5) * t0; }
+  if (qs < R(1)) { t0 = q_sqrt<R, T::FASTM>(R(1) - qs); f = R(0.5); }
+  else { t0 = q_rsqrt<R, T::FASTM>(R(1) + qs); f = R(0.5) * t0; }
   R t1 = tx * f, t2 = ty * f, t3 = tz * f;
-  R tn = Mth<R>::sqrt(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3);
-  t0 /= tn; t1 /= tn; t2 /= tn; t3 /= tn;
+  if (T::FASTM && sizeof(R) == 4) {                                     // fp32: normalise by MUFU.RSQ (norm^2 is 1 + O(theta^2))
+    R inv = q_rsqrt<R, true>(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3);
+    t0 *= inv; t1 *= inv; t2 *= inv; t3 *= inv;
+  } else {
+    R tn = Mth<R>::sqrt(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3);
+    t0 /= tn; t1 /= tn; t2 /= tn; t3 /= tn;
+  }
   R n0 = q[0] * t0 - q[1] * t1 - q[2] * t2 - q[3] * t3;                 // quad_utils.py:92-99
   R n1 = q[0] * t1 + q[1] * t0 - q[2] * t3 + q[3] * t2;
   R n2 = q[0] * t2 + q[1] * t3 + q[2] * t0 - q[3] * t1;
@@ -1076,6 +1118,7 @@ __device__ __forceinline__ void flush_tile(const Params<R>& p, const R* tile, lo
   long long rows = p.end - block_first;
   if (rows > BLOCK) rows = BLOCK;
   int total = (int)rows * p.obs_dim;
+  QS_CHECK(p, rows >= 0 && block_first >= p.begin && block_first + rows <= p.end, BC_OBS_GLOBAL);
   R* dst = p.obs + block_first * p.obs_dim;
   if (row_valid == nullptr && (total & 3) == 0 && ((p.obs_dim * BLOCK) & 3) == 0) {
     const V4<R>* t4 = reinterpret_cast<const V4<R>*>(tile);
@@ -1319,6 +1362,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     if (a_first != nullptr && ks == 0) {
       a[0] = a_first[0]; a[1] = a_first[1]; a[2] = a_first[2]; a[3] = a_first[3];
     } else if (active && p.actions != nullptr) {
+      QS_CHECK(p, i >= 0 && i < p.n && ks < p.k_steps && p.act_dim >= 1 && p.act_dim <= 4, BC_ACTION);
       const R* ap = p.actions + ((long long)ks * p.n + i) * p.act_dim;
       if (p.act_dim == 4) { V4<R> v = *reinterpret_cast<const V4<R>*>(ap); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
       else {
@@ -1360,7 +1404,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // ---- crash, reward, tick, done (:974-987) ----
     bool crashed = s.pz <= m.arm();                                     // :977
     R costs[20];
-    R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::MISC && p.info) ? costs : nullptr);
+    R rew = compute_reward<R, T>(s, p, a, a_prev, crashed, collided, (T::INFO && p.info) ? costs : nullptr);
     if (!Mth<R>::finite(rew) && active) atomicOr(p.status, 1);          // :633-636
     s.tick += R(1);                                                     // :986
     bool done = s.tick > (R)p.ep_len;                                   // :987
@@ -1370,9 +1414,9 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
 #pragma unroll
     for (int k = 0; k < 4; ++k) s.pa[k] = a[k];                         // becomes actions[1] of the next step
     const bool last = (ks == k_steps - 1);
-    if (T::MISC) {
+    if (T::INFO) {
       if (p.info != nullptr && last && active) {
-        R* inf = p.info + i * INFO_DIM;
+        R inf[INFO_DIM];                   // assembled in registers, stored as twelve 4-wide vectors (a row is 48 reals)
         R am[3];
         accelerometer(s, p, am);
         inf[0] = s.ax; inf[1] = s.ay; inf[2] = s.az; inf[3] = am[0]; inf[4] = am[1]; inf[5] = am[2];
@@ -1384,6 +1428,10 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
         inf[28] = s.ret; inf[29] = s.tick; inf[30] = rew; inf[31] = done ? R(1) : R(0);
 #pragma unroll
         for (int k = 42; k < INFO_DIM; ++k) inf[k] = R(0);
+        QS_CHECK(p, i >= 0 && i < p.n, BC_INFO);
+        V4<R>* dst = reinterpret_cast<V4<R>*>(p.info + i * INFO_DIM);
+#pragma unroll
+        for (int k = 0; k < INFO_DIM / 4; ++k) { V4<R> v; v.x = inf[4 * k]; v.y = inf[4 * k + 1]; v.z = inf[4 * k + 2]; v.w = inf[4 * k + 3]; dst[k] = v; }
       }
     }
     // ---- observation (:988) and episode end: statistics + folded reset (:1059-1144) ----
@@ -1394,6 +1442,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     if (done) {
       if (active && s.tick == (R)(p.ep_len + 1)) { st_ret += (double)s.ret; st_ret2 += (double)s.ret * (double)s.ret; st_n += 1.0; }
       if (resetting) {
+        QS_CHECK(p, !(want_term && last && active) || (i >= 0 && i < p.n), BC_INFO);
         if (want_term && last && active) obs_to_tile<R, T::PLAIN, T::MISC>(p, o, p.term_obs + i * (T::PLAIN ? 18 : p.obs_dim));
         reset_env<R, T>(s, p, ns);
         if (last || walk) build_obs<R, T>(s, p, m, ns, true, s.pa, o);     // :1143 (actions[1] = 0 after reset)
@@ -1490,6 +1539,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
@@ -1534,7 +1586,8 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 
 constexpr int TMA_MIN_CTAS = 4;   // resident CTAs per SM the fast kernel is tuned for (registers <= 128)
 constexpr int TMA_MIN_CTAS_RARE = 3;   // the catch-all configuration (every feature group, everything at run time) needs ~160 registers
-template <class T> constexpr int tma_min_ctas() { return T::FEAT == F_ALL ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS; }
+// (per-env models on top of a feature group: on-demand model loads + the group's code do not fit 128 registers without ~300 B of spills)
+template <class T> constexpr int tma_min_ctas() { return (T::FEAT == F_ALL || (T::PEM && T::RARE)) ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS; }
 constexpr int WARPS = BLOCK / 32;
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -1603,6 +1656,15 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_a) :: "memory");
 #endif
   pdl_launch_dependents();                       // the next launch may start its prologue; it waits below for our completion
+  QS_CHECK(p, !p.bounds_selftest, BC_SELFTEST);
+  QS_CHECK(p, n_tiles > 0 && (ONEWAVE ? (long long)gridDim.x * cta_envs >= p.end - p.begin : G <= n_tiles), BC_TILE);
+#ifdef QS_DEBUG_BOUNDS
+  const size_t dyn_smem = dyn_smem_bytes();
+  QS_CHECK(p, ONEWAVE ? dyn_smem >= (size_t)cta_envs * obs_dim * sizeof(float)
+                      : dyn_smem >= (size_t)2 * stage_vecs * sizeof(float4) + (size_t)p.obs_stages * obs_tile_floats * sizeof(float) +
+                                        ((p.actions != nullptr && p.act_dim < 4) ? (size_t)2 * BLOCK * 2 * sizeof(float) : (size_t)0), BC_RING);
+  QS_CHECK(p, rows_in >= 7 && rows_in <= 12 && p.row_ou < rows_in && p.row_act < rows_in && p.row_gyro < rows_in && p.row_goal < rows_in, BC_ROW);
+#endif
 
   // ---- ahead of the wait: nothing here depends on what the previous grid is still writing ------------------------------
   // (1) L2 prefetch of this CTA's first tile: the CTA is resident well before the previous grid completes (it took the
@@ -1666,6 +1728,8 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     long long rows = p.end - first;
     if (rows > BLOCK) rows = BLOCK;
     const uint32_t bytes = (uint32_t)rows * 16u;
+    QS_CHECK(p, tile >= 0 && tile < n_tiles && (stage == 0 || stage == 1), BC_TILE);
+    QS_CHECK(p, rows > 0 && rows <= BLOCK && first >= p.begin && first + rows <= p.end && p.end <= p.n, BC_SRC);
     mbar_expect_tx(&full_bar[stage], bytes * (uint32_t)(rows_in + (has_act ? 1 : 0)));
     float4* dst = in + (size_t)stage * stage_vecs;
     const char* src = reinterpret_cast<const char*>(p.state + first * 4);
@@ -1692,6 +1756,21 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     __syncthreads();
   }
 
+  // 1- and 2-wide actions (VerticalControl, VertPlaneControl) are not part of the bulk-copy ring: each thread fetches its
+  // own with a 4-byte cp.async into a two-slot shared-memory stage, one tile AHEAD (the index of the CTA's next tile is known a
+  // whole tile early), so the load latency hides behind the compute phase of the current tile and no register is held for it
+  // (a register prefetch was spilled by the compiler straight after the load - i.e. it waited for the load on the spot).
+  const bool act_direct = multi && !has_act && p.actions != nullptr && p.act_dim < 4;
+  float* act_stage = obs_tiles + (size_t)(multi ? p.obs_stages : 0) * obs_tile_floats;      // [2][BLOCK][2], requested by the host
+  auto fetch_narrow_actions = [&](long long t, int slot) {
+    const long long ia = p.begin + t * BLOCK + tid;
+    QS_CHECK(p, t >= -1 && t < n_tiles && (slot == 0 || slot == 1), BC_ACTION);
+    if (t >= 0 && ia < p.end) {
+      float* dst = act_stage + ((size_t)slot * BLOCK + tid) * 2;
+      cp_async4(dst, p.actions + ia * p.act_dim);
+      if (p.act_dim == 2) cp_async4(dst + 1, p.actions + ia * 2 + 1);
+    }
+  };
   uint32_t full_phase = 0;        // bit s: parity to wait for on full_bar[s]
   uint32_t empty_phase = 0;       // (producer only) bit s: parity to wait for on empty_bar[s]
   int j = 0;
@@ -1715,9 +1794,11 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       if (active && has_act) { float4 q = *reinterpret_cast<const float4*>(p.actions + i * 4); a0[0] = q.x; a0[1] = q.y; a0[2] = q.z; a0[3] = q.w; }
     } else if (j == 0) {
       const long long il = active ? i : p.end - 1;                       // lanes beyond the last env: any valid env
+      QS_CHECK(p, il >= p.begin && il < p.end && p.end <= p.n, BC_SRC);
       const char* ptr = reinterpret_cast<const char*>(p.state + il * 4);
       for (int r = 0; r < rows_in; ++r) cp_async16(buf + r * BLOCK, ptr + r * p.row_bytes);
       if (has_act) cp_async16(buf + rows_in * BLOCK, p.actions + il * 4);
+      if (act_direct) fetch_narrow_actions(tile, 0);                       // (same group as the rows of the first tile)
       cp_async_commit();
     }
     if (PREDRAW && !ONEWAVE) predraw<R, T>(p, i, active, step0, pre);
@@ -1728,6 +1809,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       // value, and the end of this grid is its last store rather than an atomic round trip followed by a dependent
       // store.  The ticket comes back while the state loads are in flight; it is looked at after the step is computed.
       // (the increment is made to depend on the two values read, so the reads have completed before it is issued)
+      QS_CHECK(p, !active || (i >= p.begin && i < p.end), BC_ENV);
       const unsigned int one = 1u + (unsigned int)(step0 >> 63) + (unsigned int)((unsigned long long)__double_as_longlong(svd_t0) >> 63);
       __syncwarp();
       if (lane == 0 && atomicAdd(&warps_read, one) == (unsigned)cta_warps - 1u) ticket = atomicAdd(p.launch_ticket, 1u) + 1u;
@@ -1738,6 +1820,12 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       } else {
         mbar_wait(&full_bar[stage], (full_phase >> stage) & 1u);
         full_phase ^= (1u << stage);
+      }
+      if (act_direct) {
+        if (j > 0) cp_async_wait_all();                                  // this tile's actions: issued a whole tile ago
+        if (active) { const float* src = act_stage + ((size_t)stage * BLOCK + tid) * 2; a0[0] = src[0]; if (p.act_dim == 2) a0[1] = src[1]; }
+        fetch_narrow_actions(tile_slot[(j + 1) & 1], (j + 1) & 1);         // (slot of the next tile: written at least one barrier ago)
+        cp_async_commit();
       }
       // lanes beyond the last env of a ragged tile read stale shared memory: harmless, nothing of theirs is stored
       unpack_core(s, buf[0 * BLOCK], buf[1 * BLOCK], buf[2 * BLOCK], buf[3 * BLOCK], buf[4 * BLOCK], buf[5 * BLOCK], buf[6 * BLOCK]);
@@ -1766,7 +1854,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
 #endif
     R o[OBS_SCRATCH];
     StepOut<R> out;
-    run_steps<R, T>(s, p, i, active, has_act ? a0 : nullptr, svd_t0, step0, o, out, &pre);
+    run_steps<R, T>(s, p, i, active, (has_act || act_direct) ? a0 : nullptr, svd_t0, step0, o, out, &pre);
     svd_end = out.svd_t;
 #ifdef QS_PHASE_TIMING
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2) : "f"(o[0] + o[17] + out.rew_sum + s.vz) : "memory");   // computed
@@ -1774,6 +1862,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
 
     if (!multi) {
       // (the clock was read by every warp of every CTA before the last ticket was taken: nobody can see the update)
+      QS_CHECK(p, ticket <= (unsigned)gridDim.x, BC_TICKET);
       if (ticket == (unsigned)gridDim.x) {
         *p.launch_ticket = 0u;
         if (p.clock_advance) { p.clock->svd_timer = out.svd_t; p.clock->step = step0 + (unsigned long long)p.k_steps; }
@@ -1789,11 +1878,15 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       // its own 32 observation rows.  (Same run_steps instance as the pipelined path: results do not depend on which
       // path a batch size selects.)
       float* wtile = obs_tiles + (size_t)warp * 32 * obs_dim;
+#ifdef QS_DEBUG_BOUNDS
+      QS_CHECK(p, (size_t)(warp + 1) * 32 * obs_dim * sizeof(float) <= dyn_smem, BC_OBS_SMEM);
+#endif
       obs_to_tile<R, T::PLAIN, T::MISC>(p, o, wtile + lane * obs_dim);
       __syncwarp();
       const long long warp_first = i - lane;
       long long wrows = p.end - warp_first;
       if (wrows > 32) wrows = 32;
+      QS_CHECK(p, wrows <= 0 || (warp_first >= p.begin && warp_first + wrows <= p.end), BC_OBS_GLOBAL);
       if (wrows > 0) {
         const int total = (int)wrows * obs_dim;
         float* dst = p.obs + warp_first * obs_dim;             // 128 * obs_dim bytes per full warp: 16-byte aligned
@@ -1825,7 +1918,17 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       return;
     }
     // observation rows: registers -> shared tile -> one bulk store per CTA
-    float* tile_obs = obs_tiles + (size_t)stage * obs_tile_floats;
+    // (one observation tile instead of two when the host found that this buys a fourth resident CTA: its previous bulk
+    // store - issued a whole load + compute phase ago - must then have been read out before the tile is overwritten)
+    const bool one_obs_tile = p.obs_stages == 1;
+    float* tile_obs = obs_tiles + (size_t)(one_obs_tile ? 0 : stage) * obs_tile_floats;
+    if (one_obs_tile) {
+      if (tid == 0) bulk_wait_read0();
+      __syncthreads();
+    }
+#ifdef QS_DEBUG_BOUNDS
+    QS_CHECK(p, (size_t)((const unsigned char*)(tile_obs + obs_tile_floats) - smem_raw) <= dyn_smem && (one_obs_tile || p.obs_stages == 2), BC_OBS_SMEM);
+#endif
     obs_to_tile<R, T::PLAIN, T::MISC>(p, o, tile_obs + tid * obs_dim);
     if (multi) {
       fence_proxy_async();                       // generic-proxy tile writes -> async proxy
@@ -1835,6 +1938,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     long long rows = p.end - block_first;
     if (rows > BLOCK) rows = BLOCK;
     const uint32_t obs_bytes = (uint32_t)rows * (uint32_t)obs_dim * 4u;
+    QS_CHECK(p, rows > 0 && rows <= BLOCK && block_first >= p.begin && block_first + rows <= p.end, BC_OBS_GLOBAL);
     if (multi && (obs_bytes & 15u) == 0u) {
       if (tid == 0) { bulk_s2g(p.obs + block_first * obs_dim, tile_obs, obs_bytes); bulk_commit(); }
     } else {
@@ -1843,6 +1947,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
     if (__any_sync(0xffffffffu, out.done_any)) warp_stats(p, out.st_ret, out.st_ret2, out.st_n);
     ++j;
     tile = multi ? tile_slot[j & 1] : -1;        // written at least one barrier ago
+    QS_CHECK(p, tile == -1 || (tile >= G && tile < n_tiles), BC_TILE);
   }
   if (tid == 0) bulk_wait_read0();               // shared memory must outlive the bulk stores
   __syncthreads();                               // every thread of the CTA has read the clock
@@ -2090,6 +2195,8 @@ QS_DECL_FAST(launch_tma_generic_noise_philox);
 QS_DECL_FAST(launch_tma_generic_noise_inject);
 QS_DECL_FAST(launch_tma_generic_misc_philox);
 QS_DECL_FAST(launch_tma_generic_misc_inject);
+QS_DECL_FAST(launch_tma_generic_info_philox);
+QS_DECL_FAST(launch_tma_generic_info_inject);
 #undef QS_DECL_FAST
 
 }  // namespace qs

@@ -35,9 +35,14 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
   // fp32: everything outside the specialised subset still runs through the persistent TMA harness - a kernel that carries
   // just the feature group the configuration needs when it is a single group at the default sim_steps, the catch-all otherwise
   if (p.tma_generic) {
+    if (p.models != nullptr && p.sim_steps == 2) {       // (swarms / the log-distance reward with per-env models carry F_MISC)
+      if (p.feat == F_DRAG) return p.inject ? launch_tma_generic_drag_inject(p, st, name) : launch_tma_generic_drag_philox(p, st, name);
+      if (p.feat == F_MISC) return p.inject ? launch_tma_generic_misc_inject(p, st, name) : launch_tma_generic_misc_philox(p, st, name);
+    }
     if (p.models == nullptr && p.sim_steps == 2) {
       if (p.feat == F_DRAG) return p.inject ? launch_tma_generic_drag_inject(p, st, name) : launch_tma_generic_drag_philox(p, st, name);
       if (p.feat == F_NOISEX) return p.inject ? launch_tma_generic_noise_inject(p, st, name) : launch_tma_generic_noise_philox(p, st, name);
+      if (p.feat == F_INFO) return p.inject ? launch_tma_generic_info_inject(p, st, name) : launch_tma_generic_info_philox(p, st, name);
       if (p.feat == F_MISC || p.feat == F_NONE) return p.inject ? launch_tma_generic_misc_inject(p, st, name) : launch_tma_generic_misc_philox(p, st, name);
     }
     return p.inject ? launch_tma_generic_all_inject(p, st, name) : launch_tma_generic_all_philox(p, st, name);

@@ -47,12 +47,25 @@ static cudaError_t launch_tma_w(const Params<float>& p, cudaStream_t st, unsigne
 }
 
 template <class T>
-static cudaError_t launch_tma_t(const Params<float>& p, cudaStream_t st) {
+static cudaError_t launch_tma_t(const Params<float>& p_in, cudaStream_t st) {
+  Params<float> p = p_in;
   const long long n = p.end - p.begin;
   const long long tiles = (n + BLOCK - 1) / BLOCK;
-  const size_t smem = (size_t)2 * (p.tma_rows + 1) * BLOCK * sizeof(float4) + (size_t)2 * BLOCK * p.obs_dim * sizeof(float);
-  int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_RESERVED));
+  // (+ a two-slot stage for 1- and 2-wide actions, which the threads prefetch themselves: see act_direct in the kernel)
+  const size_t act_stage = (p.actions != nullptr && p.act_dim < 4) ? (size_t)2 * BLOCK * 2 * sizeof(float) : 0;
+  const size_t ring = (size_t)2 * (p.tma_rows + 1) * BLOCK * sizeof(float4) + act_stage, obs_tile = (size_t)BLOCK * p.obs_dim * sizeof(float);
   const int cap = tma_min_ctas<T>();
+  // two observation tiles (the bulk store of one drains while the next is filled) unless dropping to one lets another CTA
+  // fit on the SM: configurations with extra state rows (gyro bias, previous action, goal) are otherwise held to 3 CTAs = 12
+  // warps per SM by shared memory, and these kernels are issue-bound
+  size_t smem = ring + 2 * obs_tile;
+  int per_sm = (int)(SMEM_PER_SM / (smem + SMEM_RESERVED));
+  p.obs_stages = 2;
+  if (per_sm < cap && (int)(SMEM_PER_SM / (ring + obs_tile + SMEM_RESERVED)) > per_sm) {
+    smem = ring + obs_tile;
+    per_sm = (int)(SMEM_PER_SM / (smem + SMEM_RESERVED));
+    p.obs_stages = 1;
+  }
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   const int sms = sm_count();

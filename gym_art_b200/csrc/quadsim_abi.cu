@@ -141,7 +141,8 @@ int feat_of(const QsHandle* h) {
   if (m.linearity != 1.0 || m.C_drag != 0.0 || m.C_roll != 0.0 || m.vel_damp != 0.0 || m.damp_omega_quadratic != 0.0) f |= qs::F_DRAG;
   if (s.enabled && (s.pos_unif_range != 0.0 || s.vel_unif_range != 0.0 || s.quat_norm_std != 0.0 || s.quat_unif_range != 0.0 ||
                     s.gyro_norm_std != 0.0)) f |= qs::F_NOISEX;
-  if (c.dim_mode != 3 || c.per_env_goal || h->info != nullptr) f |= qs::F_MISC;
+  if (c.dim_mode != 3 || c.per_env_goal) f |= qs::F_MISC;
+  if (h->info != nullptr) f |= qs::F_INFO;
   if (c.obs_repr >= QS_OBS_XYZ_VXYZ_QUAT_OMEGA || c.init_random_state == QS_INIT_PITCH_ROLL_RESTRICTED) f |= qs::F_MISC;
   // swarms (and the log-distance reward that comes with them) and per-env models have specialised kernels for the
   // common step shape only
@@ -152,6 +153,9 @@ int feat_of(const QsHandle* h) {
   // the specialised per-env-model kernels compile out linearity / rotor drag / damping (rows 8 and 9 of the model buffer):
   // they are taken only when the caller has asserted that every bound model is plain in that sense
   if (c.per_env_model && !h->models_plain) f |= qs::F_DRAG;
+  // the contact stage, formation goals and the log-distance reward live in the specialised swarm kernels (fast subset) and in
+  // F_MISC: a swarm that needs any other feature group takes F_MISC along
+  if ((c.n_agents > 1 || c.reward.log_pos) && f != qs::F_NONE) f |= qs::F_MISC;
   return f;
 }
 
@@ -211,7 +215,10 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.tma_rows = h->lay.rows;
   p.row_bytes = (long long)c.n_envs * 4 * (long long)sizeof(R);
   p.pdl = h->pdl;
-  p.ow_threads = h->ow_threads; p.ow_extra = h->ow_extra; p.prefetch = 0; p.spec_draw = h->spec_draw;
+  p.ow_threads = h->ow_threads; p.ow_extra = h->ow_extra; p.prefetch = 0;
+#ifdef QS_DEBUG_BOUNDS
+  { const char* e = getenv("QUADSIM_BOUNDS_SELFTEST"); p.bounds_selftest = e ? atoi(e) : 0; }
+#endif p.spec_draw = h->spec_draw;
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
@@ -417,6 +424,7 @@ int qs_bind_terminal_obs(QsHandle* h, void* terminal_obs) {
 
 int qs_bind_info(QsHandle* h, void* info) {
   if (!h) return QS_EINVAL;
+  if (info && !vec_aligned(h, info)) return fail(h, QS_EINVAL, "info must be aligned to 4 reals (16 bytes f32 / 32 bytes f64): vector stores");
   h->info = info;
   return QS_OK;
 }
@@ -638,6 +646,11 @@ int qs_check(QsHandle* h, qs_stream_t stream) {
   QS_CUDA(h, cudaSetDevice(h->cfg.device));
   QS_CUDA(h, cudaMemcpyAsync(&flag, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   QS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag & 2) {            // QS_DEBUG_BOUNDS builds only: a kernel-side index / pointer check failed (qs::BoundsCode mask)
+    char code[32];
+    snprintf(code, sizeof(code), "0x%x", (unsigned)flag >> 8);
+    return fail(h, QS_ECUDA, "QS_DEBUG_BOUNDS: bounds check failed, code mask %s", code);
+  }
   if (flag) return fail(h, QS_ENONFINITE, "QuadEnv: reward is Nan");   // quadrotor.py:636
   return QS_OK;
 }

@@ -268,7 +268,7 @@ int qs_bind_models(QsHandle* h, const void* models, int32_t flags);
  * step (quadrotor.py:988) - is written to this buffer, rows of envs that did not finish are left untouched.
  * NULL to disable. */
 int qs_bind_terminal_obs(QsHandle* h, void* terminal_obs);
-/* optional diagnostics buffer real[n_envs][QS_INFO_DIM] (NULL to disable) */
+/* optional diagnostics buffer real[n_envs][QS_INFO_DIM], aligned to 4 reals (rows leave as vector stores); NULL to disable */
 int qs_bind_info(QsHandle* h, void* info);
 /* QS_NOISE_INJECTED: device buffers of unit draws consumed by the next reset/step calls (any may be NULL = zeros) */
 int qs_set_noise_injection(QsHandle* h, const void* ou_z, const void* obs_z, const void* reset_z);

@@ -60,7 +60,7 @@ def test_fast_and_generic_kernels_agree_on_philox_streams():
     fast = _env(n, sense_noise="default")
     gen = _env(n, sense_noise="default", info=True)
     a, b = _rollout(fast, T, acts), _rollout(gen, T, acts)
-    assert fast.kernel_variant == "tma-raw" and gen.kernel_variant == "tma-generic-misc"
+    assert fast.kernel_variant == "tma-raw" and gen.kernel_variant == "tma-generic-info"
     for t in range(T):
         assert torch.allclose(a[t][0], b[t][0], rtol=0, atol=2e-4), t
         assert torch.allclose(a[t][1], b[t][1], rtol=0, atol=1e-5)
@@ -441,7 +441,7 @@ def test_per_env_models_fast_kernel_fp32(ctrl, oc, with_drag):
         env.set_noise(ou_z=ou_z, obs_z=obs_z)
         o, r, d = env.step(a)
         assert env.models_plain == (not with_drag)
-        assert env.kernel_variant == ("tma-generic-permodel-injected" if with_drag else "tma-%s-injected" % ctrl)
+        assert env.kernel_variant == ("tma-generic-permodel-drag-injected" if with_drag else "tma-%s-injected" % ctrl)
         o, r = o.double().cpu().numpy(), r.double().cpu().numpy()
         for k in range(K):
             s = sel[k]

@@ -227,3 +227,44 @@ def test_mixed_model_swarm_contact_distance_is_the_sum_of_the_arms():
         oe.collide_swarm()
         np.testing.assert_allclose(oe.vel, want[:2], rtol=0, atol=1e-12)
         env.close()
+
+
+def test_swarm_with_rotor_drag_takes_a_kernel_that_has_the_contact_stage():
+    """A swarm whose model needs another feature group (rotor drag here) must not land in that group's single-feature
+    kernel, which has no contact stage: fp32 per step against the oracle, contacts flagged."""
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
+    params = quad_models.crazyflie_params()
+    qr._update_existing(params, {"motor": {"C_drag": 0.0028, "C_roll": 0.003, "linearity": 0.424}, "damp": {"vel": 0.001, "omega_quadratic": 0.015}})
+    E, M, T = 300, 4, 40
+    n = E * M
+    form = ring_goals(M, radius=0.05)
+    kw = dict(ep_time=5, sim_steps=2, collision_k=2.5, box=0.15)
+    env = QuadVecEnv(n, dynamics_params=params, controller="raw", noise_mode="injected", auto_reset=True, n_agents=M, formation=form,
+                     rew_coeff={"collision": 0.7}, **kw)
+    oe = qo.OracleVecEnv(params, n, controller=qo.CTRL_RAW, auto_reset=True, n_agents=M, goals=np.tile(form, (E, 1)), collision_coeff=0.7, **kw)
+    rng = np.random.RandomState(31)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)
+    rz = f32(rng.uniform(-1, 1, (n, qo.RESET_Z)))
+    env.set_noise(reset_z=rz)
+    env.reset()
+    oe.reset(reset_z=rz)
+    fields = (("pos", "pos"), ("vel", "vel"), ("rot", "rot"), ("omega", "omega"), ("thrust_rot_damp", "rot_damp"),
+              ("thrust_cmds_damp", "cmds_damp"), ("ou_state", "ou"))
+    contacts = 0
+    for t in range(T):
+        for f, of in fields:
+            setattr(oe, of, env.get_field(f).double().cpu().numpy())
+        a, ou_z = f32(rng.uniform(-0.2, 0.4, (n, 4))), f32(rng.standard_normal((n, 2, 4)))
+        env.set_noise(ou_z=ou_z)
+        o, r, d = env.step(a)
+        oo, ro, do = oe.step(a, ou_z=ou_z)
+        contacts += int(oe.collided.sum())
+        err = (np.abs(o.double().cpu().numpy() - oo) / np.maximum(np.abs(oo), 1.0)).max(axis=1)
+        bad = (err > 1e-5) | (np.abs(r.double().cpu().numpy() - ro) > 1e-6)   # only pairs within an ulp of the contact distance may differ
+        assert bad.mean() < 2e-3, (t, bad.sum(), err.max())
+    assert contacts > 50
+    assert env.kernel_variant == "tma-generic-injected"                       # drag + the swarm stage: two groups, the catch-all
+    env.close()
