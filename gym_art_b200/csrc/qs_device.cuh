@@ -931,6 +931,21 @@ struct NoiseSrc {
 template <typename R, bool FAST>
 __device__ __forceinline__ void rot2quat(const R* r, R* q) {            // sensor_noise.py:26-55
   R tr = r[0] + r[4] + r[8];
+  if (FAST && sizeof(R) == 4) {
+    // fp32: the four cases differ only in which diagonal combination goes under the root and where the entries land -
+    // one MUFU.RSQ (S = 2 sqrt(t), 1 / S = rsqrt(t) / 2) and selects instead of four divergent branches with a square
+    // root and three divisions each (a warp of 32 random attitudes takes all of them)
+    const int c = tr > R(0) ? 0 : ((r[0] > r[4] && r[0] > r[8]) ? 1 : (r[4] > r[8] ? 2 : 3));
+    const R t = c == 0 ? tr + R(1) : (c == 1 ? R(1) + r[0] - r[4] - r[8] : (c == 2 ? R(1) + r[4] - r[0] - r[8] : R(1) + r[8] - r[0] - r[4]));
+    const R is = q_rsqrt<R, true>(t), h = R(0.5) * is, big = R(0.5) * (t * is);
+    const R d0 = (r[7] - r[5]) * h, d1 = (r[2] - r[6]) * h, d2 = (r[3] - r[1]) * h;
+    const R s01 = (r[1] + r[3]) * h, s02 = (r[2] + r[6]) * h, s12 = (r[5] + r[7]) * h;
+    q[0] = c == 0 ? big : (c == 1 ? d0 : (c == 2 ? d1 : d2));
+    q[1] = c == 0 ? d0 : (c == 1 ? big : (c == 2 ? s01 : s02));
+    q[2] = c == 0 ? d1 : (c == 1 ? s01 : (c == 2 ? big : s12));
+    q[3] = c == 0 ? d2 : (c == 1 ? s02 : (c == 2 ? s12 : big));
+    return;
+  }
   if (tr > R(0)) {
     if (FAST && sizeof(R) == 4) {                                       // the common branch: 1/S by MUFU.RSQ
       R t = tr + R(1);

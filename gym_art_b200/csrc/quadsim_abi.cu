@@ -218,7 +218,8 @@ void fill_params(const QsHandle* h, qs::Params<R>* pp) {
   p.ow_threads = h->ow_threads; p.ow_extra = h->ow_extra; p.prefetch = 0;
 #ifdef QS_DEBUG_BOUNDS
   { const char* e = getenv("QUADSIM_BOUNDS_SELFTEST"); p.bounds_selftest = e ? atoi(e) : 0; }
-#endif p.spec_draw = h->spec_draw;
+#endif
+  p.spec_draw = h->spec_draw;
   // model (quadrotor.py:142-208, :284-288)
   p.dt = (R)c.dt;
   const double eps = 1e-6;
