@@ -199,10 +199,12 @@ def make_env(n, device, seed, env_id_offset=0, cfg="cfg2"):
 
 # (config, envs per GPU, algorithmic bytes per env step): the other BASELINE.json configs, timed briefly for context
 OTHER = (("cfg3", 1 << 20, 349), ("cfg4", 262144 * 8, 349), ("cfg5", 8 << 20, 333))
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/r1_ncu_*.txt)
-NCU_TRAFFIC = {N_BATCH: 9.5e6, N_LARGE: 1406.5e6}
-NCU_TRAFFIC_SOURCE = ("profiles/r1_ncu_cfg2_65536.txt (ncu replays a cold-L2 launch: the 23 MB working set is written back to L2 "
-                      "only, so DRAM sees the reads)")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from committed ncu captures.  The headline size is taken in the regime
+# that is timed - ncu --graph-profiling graph over warm replays of a 64-step graph cycling through the ring (tools/ring_traffic.py):
+# 21.9 MB per launch, 0.96 of the 22.87 MB algorithmic; the large size from the --set full capture of one launch.
+NCU_TRAFFIC = {N_BATCH: 21.89e6, N_LARGE: 1406.5e6}
+NCU_TRAFFIC_SOURCE = ("profiles/r2_ring_traffic.txt (ncu --graph-profiling graph over warm ring replays: read 9.43 MB + write 12.47 MB per "
+                      "65,536-env launch)")
 
 
 def time_graph(torch, fn_steps, n_steps, warmup, device, dist=None, reducer=None, chunk=501, repeats=1, launches_of=None,
@@ -600,7 +602,7 @@ def run_ours(args):
                              "ms_per_step": ms_l / KL,
                              "roofline": {"bound": "hbm", "achieved": big_achieved, "peak": hbm_peak, "unit": "GB/s",
                                           "frac": big_achieved / hbm_peak, "traffic": NCU_TRAFFIC[N_LARGE],
-                                          "traffic_source": "profiles/r1_ncu_cfg2_4194304.txt"}},
+                                          "traffic_source": "profiles/r2_ncu_cfg2_4194304.txt"}},
             "other_workloads": others,
             "l2_resident_same_batch": l2_resident,
             "clocks": clocks,
