@@ -4,4 +4,5 @@
 #define QS_FAST_LABEL "tma-mellinger"
 #define QS_FAST_NAME launch_fast_mellinger_inject
 #define QS_FAST_SUFFIX "-injected"
+#define QS_FAST_MISC 1
 #include "qs_fast.inl"

@@ -4,4 +4,5 @@
 #define QS_FAST_LABEL "tma-mellinger"
 #define QS_FAST_NAME launch_fast_mellinger_philox
 #define QS_FAST_SUFFIX ""
+#define QS_FAST_MISC 1
 #include "qs_fast.inl"

@@ -4,4 +4,5 @@
 #define QS_FAST_LABEL "tma-raw"
 #define QS_FAST_NAME launch_fast_raw_philox
 #define QS_FAST_SUFFIX ""
+#define QS_FAST_MISC 1
 #include "qs_fast.inl"

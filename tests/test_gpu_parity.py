@@ -35,9 +35,10 @@ EXPECTED_VARIANT = {
     # one rarely used feature group at sim_steps = 2: the kernel that carries just that group (qs::Feat)
     "cf_drag_damp": "tma-generic-drag-injected", "cf_fullnoise_accact": "tma-generic-noise-injected",
     "hb_vertical": "tma-generic-misc-injected", "hb_vertical_rnd": "tma-generic-misc-injected",
-    "hb_mellinger_excite": "tma-generic-misc-injected", "cf_raw_resample_goal": "tma-generic-misc-injected",
-    "cf_xyzr_quat_h_rnd": "tma-generic-misc-injected", "hb_t2w_t2t_nonoise": "tma-generic-misc-injected",
-    "hb_xyzr_t2w_mellinger": "tma-generic-misc-injected",
+    # ... F_MISC with the RawControl / Mellinger controllers: the compile-time-controller twins of that group
+    "hb_mellinger_excite": "tma-mellinger-injected", "cf_raw_resample_goal": "tma-raw-injected",
+    "cf_xyzr_quat_h_rnd": "tma-raw-injected", "hb_t2w_t2t_nonoise": "tma-raw-injected",
+    "hb_xyzr_t2w_mellinger": "tma-mellinger-injected",
     "hb_quat_fullnoise": "tma-generic-injected",          # two groups (quaternion builder + full noise): the catch-all
 }
 

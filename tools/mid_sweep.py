@@ -22,7 +22,7 @@ for n in (81920, 98304, 131072, 163840, 196608, 262144, 393216, 524288, 1048576)
         acts.append(a)
     bench.RING_PERIOD[0] = ring
     K = 1600 - 1600 % ring
-    ms = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), K, 4 * ring, dev, chunk=K)
+    ms = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), K, 4 * ring, dev, chunk=K)[0][0]
     print("%s n=%8d tiles/slot %.2f  %8.2f us/step" % (cfg, n, n / 128 / 592, ms * 1e3 / K), flush=True)
     for e in envs:
         e.close()

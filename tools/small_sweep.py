@@ -11,6 +11,6 @@ for n in (1024, 8192, 16384, 32768, 49152, 65536, 75776):
         acts.append(torch.rand((n, 4), device=dev) * 2 - 1)
     bench.RING_PERIOD[0] = ring
     K = 4000
-    ms = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), K, 64, dev, chunk=K)
+    ms = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), K, 64, dev, chunk=K)[0][0]
     print("n=%6d  %.3f us/step" % (n, ms * 1e3 / K), flush=True)
     for e in envs: e.close()

@@ -29,7 +29,7 @@ for cfg in sys.argv[1:] or ["cfg2"]:
         bench.RING_PERIOD[0] = ring
         K = max(32, min(2000, (1 << 28) // n))
         K -= K % ring
-        ms = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), K, 4 * ring, dev, chunk=K)
+        ms = bench.time_graph(torch, lambda i: envs[i % ring].step(acts[i % ring]), K, 4 * ring, dev, chunk=K)[0][0]
         us = ms * 1e3 / K
         print("%s n=%8d ring=%2d  %8.2f us/step  %.3e env-steps/s  frac %.3f" % (cfg, n, ring, us, n / us * 1e6, n * bytes_per / us * 1e-3 / peak), flush=True)
         for e in envs:
