@@ -202,7 +202,7 @@ OTHER = (("cfg3", 1 << 20, 349), ("cfg4", 262144 * 8, 349), ("cfg5", 8 << 20, 33
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from committed ncu captures.  The headline size is taken in the regime
 # that is timed - ncu --graph-profiling graph over warm replays of a 64-step graph cycling through the ring (tools/ring_traffic.py):
 # 21.9 MB per launch, 0.96 of the 22.87 MB algorithmic; the large size from the --set full capture of one launch.
-NCU_TRAFFIC = {N_BATCH: 21.89e6, N_LARGE: 1406.5e6}
+NCU_TRAFFIC = {N_BATCH: 21.89e6, N_LARGE: 1408.0e6}
 NCU_TRAFFIC_SOURCE = ("profiles/r2_ring_traffic.txt (ncu --graph-profiling graph over warm ring replays: read 9.43 MB + write 12.47 MB per "
                       "65,536-env launch)")
 
