@@ -41,6 +41,7 @@ def _stale(lib):
 # (python -m gym_art_b200._build --variant bounds) and loaded through QUADSIM_LIB; the product is the plain library.
 VARIANTS = {
     "bounds": (["-DQS_DEBUG_BOUNDS"], os.path.join(HERE, "_exp", "libquadsim_bounds.so")),     # every derived index checked
+    "timing": (["-DQS_PHASE_TIMING"], os.path.join(HERE, "_exp", "libquadsim_timing.so")),     # %globaltimer stamps per warp (tools/phase_timing.py)
 }
 
 
