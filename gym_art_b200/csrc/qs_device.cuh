@@ -1602,7 +1602,14 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 constexpr int TMA_MIN_CTAS = 4;   // resident CTAs per SM the fast kernel is tuned for (registers <= 128)
 constexpr int TMA_MIN_CTAS_RARE = 3;   // the catch-all configuration (every feature group, everything at run time) needs ~160 registers
 // (per-env models on top of a feature group: on-demand model loads + the group's code do not fit 128 registers without ~300 B of spills)
-template <class T> constexpr int tma_min_ctas() { return (T::FEAT == F_ALL || (T::PEM && T::RARE)) ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS; }
+template <class T> constexpr int tma_min_ctas() {
+  // The F_MISC and F_INFO kernels need 140-150 registers: at 128 they spill 40-90 B, and with four CTAs' rings in shared
+  // memory L1 has next to nothing left to absorb spills.  Three CTAs per SM without spills win (measured: t2w observation +
+  // noise 0.62 -> 0.70, 1D mode 0.63 -> 0.74, info buffer 0.75 -> 0.78 of the byte model).
+  // (F_NOISEX: 0.60 -> 0.62 with three; F_DRAG fits 128 registers and loses with three: 0.77 -> 0.70)
+  if (T::MISC || T::INFO || T::NOISEX) return TMA_MIN_CTAS_RARE;
+  return (T::FEAT == F_ALL || (T::PEM && T::RARE)) ? TMA_MIN_CTAS_RARE : TMA_MIN_CTAS;
+}
 constexpr int WARPS = BLOCK / 32;
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
