@@ -355,6 +355,8 @@ struct Rng {
 // Per-env models (dynamics randomisation, quadrotor_randomization.py): read-only loads from the model buffer, row
 // layout in quadsim.h; nothing is cached in registers (the fp64 build has none to spare), L1 serves the re-reads.
 // ---------------------------------------------------------------------------------------------------------
+template <typename R> struct alignas(4 * sizeof(R)) V4;
+template <typename R> __device__ __forceinline__ V4<R> ldg4(const R* ptr);
 template <typename R, bool PEM> struct Mdl;
 template <typename R> struct Mdl<R, false> {
   const Params<R>& p;
@@ -387,7 +389,12 @@ template <typename R> struct Mdl<R, true> {
   const R* base;          // element 0 of this env's vector in row 0
   long long stride;       // elements between rows
   __device__ __forceinline__ Mdl(const Params<R>& p, long long i) : base(p.models + i * 4), stride(p.n * 4) { QS_CHECK(p, i >= 0 && i < p.n, BC_MODEL); }
-  __device__ __forceinline__ R at(int row, int c) const { return __ldg(base + row * stride + c); }
+  // one 16-byte (fp64: two 16-byte) read-only vector load per row; the component index is a compile-time constant at every
+  // call site, so the select folds away and loads of the same row are merged by the compiler (four scalar loads per row before)
+  __device__ __forceinline__ R at(int row, int c) const {
+    const V4<R> v = ldg4(base + row * stride);
+    return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+  }
   __device__ __forceinline__ R thrust_max(int k) const { return at(0, k); }
   __device__ __forceinline__ R tz(int k) const { return at(1, k); }
   __device__ __forceinline__ R pcx(int k) const { return at(2, k); }
@@ -434,6 +441,16 @@ struct St {
 };
 
 template <typename R> struct alignas(4 * sizeof(R)) V4 { R x, y, z, w; };
+template <> __device__ __forceinline__ V4<float> ldg4<float>(const float* ptr) {
+  const float4 q = __ldg(reinterpret_cast<const float4*>(ptr));
+  V4<float> v; v.x = q.x; v.y = q.y; v.z = q.z; v.w = q.w;
+  return v;
+}
+template <> __device__ __forceinline__ V4<double> ldg4<double>(const double* ptr) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(ptr)), b = __ldg(reinterpret_cast<const double2*>(ptr) + 1);
+  V4<double> v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
+  return v;
+}
 
 template <typename R> __device__ __forceinline__ V4<R> ld4(const R* base, long long n, int row, long long i) {
   return *reinterpret_cast<const V4<R>*>(base + ((long long)row * n + i) * 4);

@@ -41,8 +41,12 @@ static cudaError_t launch_fast_c(const Params<float>& p, cudaStream_t st) {
   const bool plain = p.sim_steps == 2 && p.k_steps == 1 && p.obs_dim == 18 && !p.obs_rel && p.row_act < 0;
   if (p.models != nullptr) {                           // per-env model constants: common shape only (host guarantees it)
     if (!plain || p.n_agents > 1 || p.log_pos) return cudaErrorInvalidValue;
-    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, false, 2, true, false, true> >(p, st);
-    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, false, 2, true, false, true> >(p, st);
+    if (p.feat == F_DRAG) {   // models with linearity != 1 / rotor drag / damping (any RelativeSampler perturbation of the motors)
+      if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, F_DRAG, 2, true, false, true> >(p, st);
+      return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, F_DRAG, 2, true, false, true> >(p, st);
+    }
+    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, F_NONE, 2, true, false, true> >(p, st);
+    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, F_NONE, 2, true, false, true> >(p, st);
   }
   const bool swarm = p.n_agents > 1 || p.log_pos;      // the host only routes these here when k_steps == 1 and plain
   if (swarm) {

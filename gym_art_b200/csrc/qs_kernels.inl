@@ -27,7 +27,11 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
     if (p.controller == CTRL_RAW) return p.inject ? launch_fast_raw_inject(p, st, name) : launch_fast_raw_philox(p, st, name);
     return p.inject ? launch_fast_mellinger_inject(p, st, name) : launch_fast_mellinger_philox(p, st, name);
   }
-  if (p.feat == F_NONE && p.act_dim == 4 &&
+  // per-env models whose drag / linearity / damping rows are in use, in the common step shape: the specialised kernels with
+  // F_DRAG compiled in (qs_fast.inl)
+  const bool pem_drag_plain = p.feat == F_DRAG && p.models != nullptr && p.sim_steps == 2 && p.k_steps == 1 && p.obs_dim == 18 &&
+                              !p.obs_rel && p.row_act < 0;
+  if ((p.feat == F_NONE || pem_drag_plain) && p.act_dim == 4 &&
       (p.controller == CTRL_RAW || p.controller == CTRL_OMEGA_THRUST || p.controller == CTRL_MELLINGER ||
        p.controller == CTRL_SHIFTED || p.controller == CTRL_VELOCITY_YAW)) {
     if (p.controller == CTRL_RAW) return p.inject ? launch_fast_raw_inject(p, st, name) : launch_fast_raw_philox(p, st, name);

@@ -220,7 +220,7 @@ typedef struct QsConfig {
   double spawn_z_min;  /* spawn height floor 0.25 (quadrotor.py:1094) */
   double room_box[2][3];
   double max_init_vel, max_init_omega; /* quadrotor.py:717-718 */
-  double collision_k;  /* swarm: contact when |p_i - p_j| < collision_k * 2 * arm */
+  double collision_k;  /* swarm: contact when |p_i - p_j| < collision_k * 2 * arm (per-env models: collision_k * (arm_i + arm_j)) */
   double pitch_max, roll_max, yaw_max; /* QS_INIT_PITCH_ROLL_RESTRICTED (quadrotor.py:243: 0.5, 0.5, 3.14) */
   double t2w_std, t2t_std; /* t2w / t2t observation noise (quadrotor.py:658: 0.005, 0.0005) */
   int32_t use_formation; /* swarm: drone a of every swarm flies to formation[a] (no goal row in the state buffer) */
@@ -333,7 +333,7 @@ int qs_set_clock(QsHandle* h, double svd_timer, uint64_t step_count, qs_stream_t
 
 /* Number of kernels this handle has launched (bench.py reports it as gpu_launches). */
 int qs_launch_count(const QsHandle* h, uint64_t* out);
-/* Name of the kernel variant the last step launched ("fast-raw", "generic-philox", ...): diagnostics. */
+/* Name of the kernel variant the last step launched ("tma-raw", "tma-generic-drag", "generic-philox", ...): diagnostics. */
 const char* qs_last_variant(const QsHandle* h);
 /* How the last qs_step_host moved its data: "zero-copy" (pinned buffers, read / written by the kernel itself across
  * PCIe) or "staged" (pageable buffers: chunked cudaMemcpyAsync pipeline). */

@@ -409,8 +409,8 @@ def test_per_env_dynamics_sampler_chain_fp32():
 def test_per_env_models_fast_kernel_fp32(ctrl, oc, with_drag):
     """The specialised per-env-model variant of the TMA kernel (multi-tile persistent path), fp32, per step from a
     re-synchronised state against the oracle run model by model: 1e-5 relative.  with_drag: one of the models has
-    linearity != 1 and rotor drag / damping - the specialised kernel compiles those terms out, so the host must route the
-    whole batch to the run-time-parameterised kernel (QS_MODELS_PLAIN not asserted) and the result must still match."""
+    linearity != 1 and rotor drag / damping - the plain specialised kernel compiles those terms out, so the host must route the
+    whole batch to the twin that carries them (QS_MODELS_PLAIN not asserted) and the result must still match."""
     from gym_art_b200 import QuadVecEnv
     from oracle import quadsim_oracle as qo
     zoo = [z for i, z in enumerate(_model_zoo()) if with_drag or i != 4]
@@ -441,7 +441,7 @@ def test_per_env_models_fast_kernel_fp32(ctrl, oc, with_drag):
         env.set_noise(ou_z=ou_z, obs_z=obs_z)
         o, r, d = env.step(a)
         assert env.models_plain == (not with_drag)
-        assert env.kernel_variant == ("tma-generic-permodel-drag-injected" if with_drag else "tma-%s-injected" % ctrl)
+        assert env.kernel_variant == "tma-%s-injected" % ctrl           # (with_drag: the specialised kernel with F_DRAG compiled in)
         o, r = o.double().cpu().numpy(), r.double().cpu().numpy()
         for k in range(K):
             s = sel[k]
