@@ -1383,8 +1383,11 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
     // the dynamics' critical path.
     constexpr int NPRE = T::SIM > 0 ? T::SIM : 1;
     constexpr bool PRE = T::SIM > 0 && T::PLAIN;                        // k_steps == 1: the caller drew everything already
+    // (per-env models + F_MISC run out of registers even at 168: eight more live draws would be spilled, and spills are what
+    // these kernels cannot afford - they draw inside the unrolled substeps instead)
+    constexpr bool HOIST = T::SIM > 0 && !PRE && !(T::PEM && T::MISC);
     Pre<R, T> own;
-    if (T::SIM > 0 && !PRE && ou_on) {
+    if (HOIST && ou_on) {
 #pragma unroll
       for (int sub = 0; sub < NPRE; ++sub) ns.ou(sub, own.zou[sub]);
     }
@@ -1420,6 +1423,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
 #pragma unroll
       for (int sub = 0; sub < NPRE; ++sub) {
         const bool fire = svd_tick(svd_t, p.dt_d, p.svd_period);        // :381-386
+        if (T::SIM > 0 && !PRE && !HOIST && ou_on) ns.ou(sub, own.zou[sub]);
         substep<R, T>(s, cmd, p, m, dr.zou[sub], fire);
       }
     } else {

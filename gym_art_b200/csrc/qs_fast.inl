@@ -21,9 +21,13 @@ static cudaError_t launch_fast_cs(const Params<float>& p, cudaStream_t st) {
 #ifdef QS_FAST_MISC
 // the two controllers the reference env selects itself (raw_control=True / False) also get the F_MISC feature group with
 // compile-time controller / OU / sensor-noise switches: per-env and moving goals, quaternion / t2w / t2t observations, the
-// restricted spawn law, swarms outside the common shape (host: feat == F_MISC, sim_steps == 2, no per-env models)
+// restricted spawn law, swarms outside the common shape, per-env models in any of those (host: feat == F_MISC, sim_steps == 2)
 template <int C>
 static cudaError_t launch_fast_misc(const Params<float>& p, cudaStream_t st) {
+  if (p.models != nullptr) {                           // per-env models (the OU row is always there): t2w observations, swarms ...
+    if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, F_MISC, 2, false, false, true> >(p, st);
+    return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, F_MISC, 2, false, false, true> >(p, st);
+  }
   if (p.ou_on) {
     if (p.sense_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, F_MISC, 2> >(p, st);
     return launch_tma_t<Traits<C, 1, 0, QS_FAST_INJECT != 0, F_MISC, 2> >(p, st);
@@ -36,7 +40,7 @@ static cudaError_t launch_fast_misc(const Params<float>& p, cudaStream_t st) {
 template <int C>
 static cudaError_t launch_fast_c(const Params<float>& p, cudaStream_t st) {
 #ifdef QS_FAST_MISC
-  if (p.feat == F_MISC) return (p.models == nullptr && p.sim_steps == 2) ? launch_fast_misc<C>(p, st) : cudaErrorInvalidValue;
+  if (p.feat == F_MISC) return p.sim_steps == 2 ? launch_fast_misc<C>(p, st) : cudaErrorInvalidValue;
 #endif
   const bool plain = p.sim_steps == 2 && p.k_steps == 1 && p.obs_dim == 18 && !p.obs_rel && p.row_act < 0;
   if (p.models != nullptr) {                           // per-env model constants: common shape only (host guarantees it)

@@ -22,7 +22,7 @@ cases = [
     ("per-env models (RandomQuad x256), raw, plain shape (+112 B model rows)", dict(controller="raw", dynamics_params="RandomQuad", per_env_dynamics=256), 461, "float32"),
     ("per-env models, perturbed motors (RelativeSampler: linearity < 1) (+144 B)", dict(controller="raw", per_env_dynamics=256, dyn_sampler_1={"class": "RelativeSampler", "noise_ratio": 0.1}), 349 + 144, "float32"),
     ("per-env models + t2w observation + default noise (O=19, +128 B)", dict(controller="raw", dynamics_params="RandomQuad", per_env_dynamics=256, obs_repr="xyz_vxyz_R_omega_t2w", sense_noise="default"), 353 + 128, "float32"),
-    ("per-env models in swarms of 8 (catch-all twin)", dict(controller="raw", dynamics_params="RandomQuad", per_env_dynamics=256, n_agents=8, formation="ring8"), 461 + 16, "float32"),
+    ("per-env models in swarms of 8                  ", dict(controller="raw", dynamics_params="RandomQuad", per_env_dynamics=256, n_agents=8, formation="ring8"), 461 + 16, "float32"),
     ("generic fp64 (verification build), raw", dict(controller="raw"), 2 * 349 - 1, "float64"),
 ]
 for name, kw, nbytes, dtype in cases:
