@@ -41,6 +41,11 @@ template <int C>
 static cudaError_t launch_fast_c(const Params<float>& p, cudaStream_t st) {
 #ifdef QS_FAST_MISC
   if (p.feat == F_MISC) return p.sim_steps == 2 ? launch_fast_misc<C>(p, st) : cudaErrorInvalidValue;
+  if (p.feat == F_NOISEX) {                            // uniform / quaternion / gyro-bias noise (sensor noise is on by definition)
+    if (p.sim_steps != 2 || p.models != nullptr || !p.sense_on) return cudaErrorInvalidValue;
+    if (p.ou_on) return launch_tma_t<Traits<C, 1, 1, QS_FAST_INJECT != 0, F_NOISEX, 2> >(p, st);
+    return launch_tma_t<Traits<C, 0, 1, QS_FAST_INJECT != 0, F_NOISEX, 2> >(p, st);
+  }
 #endif
   const bool plain = p.sim_steps == 2 && p.k_steps == 1 && p.obs_dim == 18 && !p.obs_rel && p.row_act < 0;
   if (p.models != nullptr) {                           // per-env model constants: common shape only (host guarantees it)

@@ -22,7 +22,8 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
   typedef QS_REAL R;
 #ifdef QS_FAST_VARIANTS
   // F_MISC with the RawControl / Mellinger controllers at the default sim_steps: compile-time controller twins (qs_fast.inl)
-  if (p.feat == F_MISC && p.act_dim == 4 && p.sim_steps == 2 && p.dim_mode == 3 &&
+  // (a twin of F_DRAG was measured too: 0.77 -> 0.79 for 16 more kernels per translation unit - not kept)
+  if ((p.feat == F_MISC || (p.feat == F_NOISEX && p.models == nullptr)) && p.act_dim == 4 && p.sim_steps == 2 && p.dim_mode == 3 &&
       (p.controller == CTRL_RAW || p.controller == CTRL_MELLINGER)) {
     if (p.controller == CTRL_RAW) return p.inject ? launch_fast_raw_inject(p, st, name) : launch_fast_raw_philox(p, st, name);
     return p.inject ? launch_fast_mellinger_inject(p, st, name) : launch_fast_mellinger_philox(p, st, name);

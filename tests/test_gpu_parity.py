@@ -33,7 +33,7 @@ EXPECTED_VARIANT = {
     "cf_mellinger_rnd": "tma-mellinger-injected", "rq_mellinger": "tma-mellinger-injected",
     "hb_velyaw": "tma-velocity-yaw-injected", "hb_shifted": "tma-shifted-injected", "cf_raw_simplified": "tma-raw-injected",
     # one rarely used feature group at sim_steps = 2: the kernel that carries just that group (qs::Feat)
-    "cf_drag_damp": "tma-generic-drag-injected", "cf_fullnoise_accact": "tma-generic-noise-injected",
+    "cf_drag_damp": "tma-generic-drag-injected", "cf_fullnoise_accact": "tma-raw-injected",       # F_NOISEX with RawControl: compile-time-controller twin
     "hb_vertical": "tma-generic-misc-injected", "hb_vertical_rnd": "tma-generic-misc-injected",
     # ... F_MISC with the RawControl / Mellinger controllers: the compile-time-controller twins of that group
     "hb_mellinger_excite": "tma-mellinger-injected", "cf_raw_resample_goal": "tma-raw-injected",
