@@ -268,3 +268,55 @@ def test_swarm_with_rotor_drag_takes_a_kernel_that_has_the_contact_stage():
     assert contacts > 50
     assert env.kernel_variant == "tma-generic-injected"                       # drag + the swarm stage: two groups, the catch-all
     env.close()
+
+
+def test_swarm_with_per_env_models_specialised_twin_fp32():
+    """The same scenario without the info buffer: per-env goals + per-env models + RawControl take the compile-time-controller
+    twin of the F_MISC group with per-env models (`tma-raw`), whose contact stage reads each partner's arm by shuffle."""
+    from gym_art_b200 import QuadVecEnv
+    from gym_art_b200.quadrotor import quad_models
+    from gym_art_b200.quadrotor import quadrotor_randomization as qr
+    from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
+    np.random.seed(4)
+    zoo = [quad_models.defaultquad_params(), quad_models.crazyflie_params(), qr.RandomQuad().sample()]
+    K, M, T = len(zoo), 4, 40
+    E = (148 * 3 * 128 * 2) // M + 3                              # enough tiles for the pipelined (multi-tile) path
+    n = E * M
+    index = (np.arange(n) // M) % K
+    goals = np.tile(ring_goals(M, radius=0.12), (E, 1))
+    kw = dict(ep_time=5, sim_steps=2, collision_k=2.5, box=0.3, multi_reward=True)
+    env = QuadVecEnv(n, dynamics_params=zoo[0], controller="raw", noise_mode="injected", auto_reset=True, n_agents=M, goals=goals,
+                     rew_coeff={"collision": 0.7}, per_env_dynamics=K, **kw)
+    env.set_models(zoo, index=index)
+    sel = [np.where(index == k)[0] for k in range(K)]
+    oes = [qo.OracleVecEnv(zoo[k], len(sel[k]), controller=qo.CTRL_RAW, auto_reset=True, n_agents=M, goals=goals[sel[k]],
+                           collision_coeff=0.7, **kw) for k in range(K)]
+    rng = np.random.RandomState(22)
+    f32 = lambda x: x.astype(np.float32).astype(np.float64)
+    rz = f32(rng.uniform(-1, 1, (n, qo.RESET_Z)))
+    env.set_noise(reset_z=rz)
+    env.reset()
+    for k in range(K):
+        oes[k].reset(reset_z=rz[sel[k]])
+    fields = (("pos", "pos"), ("vel", "vel"), ("rot", "rot"), ("omega", "omega"), ("thrust_rot_damp", "rot_damp"),
+              ("thrust_cmds_damp", "cmds_damp"), ("ou_state", "ou"))
+    contacts = 0
+    for t in range(T):
+        dev = {f: env.get_field(f).double().cpu().numpy() for f, _ in fields}
+        for k in range(K):
+            for f, of in fields:
+                setattr(oes[k], of, dev[f][sel[k]].copy())
+        a, ou_z = f32(rng.uniform(-0.2, 0.4, (n, 4))), f32(rng.standard_normal((n, 2, 4)))
+        env.set_noise(ou_z=ou_z)
+        o, r, d = env.step(a)
+        o, r = o.double().cpu().numpy(), r.double().cpu().numpy()
+        for k in range(K):
+            s = sel[k]
+            oo, ro, do = oes[k].step(a[s], ou_z=ou_z[s])
+            contacts += int(oes[k].collided.sum())
+            err = (np.abs(o[s] - oo) / np.maximum(np.abs(oo), 1.0)).max(axis=1)
+            bad = (err > 1e-5) | (np.abs(r[s] - ro) > 1e-6)       # only pairs within an ulp of the contact distance may differ
+            assert bad.mean() < 1e-3, (k, t, bad.sum(), err.max())
+    assert contacts > 100
+    assert env.kernel_variant == "tma-raw-injected"
+    env.close()
