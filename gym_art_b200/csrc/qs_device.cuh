@@ -96,6 +96,7 @@ struct Params {
   int ow_threads;                     // threads per CTA of a one-wave launch (32, 64 or 128)
   int obs_stages;                     // pipelined launch: observation tiles in shared memory (2, or 1 when that buys a resident CTA)
   int ow_extra;                       // A/B knob QUADSIM_OW_EXTRA: CTA slots per SM a one-wave launch leaves to its dependent launch
+  int host_ctas;                      // > 0: the launch reads / writes pinned HOST buffers (qs_step_host zero-copy): resident CTAs per SM
   int prefetch;                       // L2 prefetch of the CTA's first tile ahead of griddepcontrol.wait: 0 off, 1 bulk, 3 lines
   int spec_draw;                      // draw the step's noise ahead of griddepcontrol.wait from a speculative clock read
   int bounds_selftest;                // QS_DEBUG_BOUNDS builds: raise BC_SELFTEST (proves the reporting path end to end)

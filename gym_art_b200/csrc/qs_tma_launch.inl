@@ -90,6 +90,10 @@ static cudaError_t launch_tma_t(const Params<float>& p_in, cudaStream_t st) {
     const int extra = p.ow_extra;                      // A/B knob: CTA slots per SM left free for the dependent launch
     want += extra;
     if (want > reg_cap + extra) want = reg_cap + extra;
+    // Host-buffer launches (qs_step_host, zero-copy): the CTAs read their actions and write their results across PCIe.  With
+    // every CTA resident at once all of them read first and then all of them write; fewer resident CTAs = several waves, so the
+    // action reads of later CTAs travel (the link is full duplex) while earlier ones are posting their results.
+    if (p.host_ctas > 0 && p.host_ctas < want) want = p.host_ctas;
     if (want < 1) want = 1;
     size_t dyn = (SMEM_PER_SM / (size_t)want) - SMEM_RESERVED;
     dyn &= ~(size_t)127;
