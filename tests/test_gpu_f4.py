@@ -154,7 +154,8 @@ def test_random_init_in_1d_and_2d_env_matches_oracle(dim_mode, ctrl, adim, dtype
 
 
 @pytest.mark.parametrize("obs_repr,init", [("xyz_vxyz_R_omega_t2w_t2t", "pitch_roll_restricted"), ("xyzr_vxyzr_quat_omega_h", True),
-                                            ("xyzr_vxyzr_R_omega_t2w", False)])
+                                            ("xyzr_vxyzr_R_omega_t2w", False), ("xyzr_vxyzr_quat_omega", False),
+                                            ("xyz_vxyz_R_omega_t2w", True)])
 def test_fp64_philox_rollout_with_the_new_builders_equals_oracle(obs_repr, init):
     """Philox mode, free running, auto-reset: the t2w / t2t draws (slot 11 step, 41 reset), the quaternion builders and the
     restricted spawn law, against the oracle fed by oracle/philox.py with the same (seed, env id, step, slot) draws."""
