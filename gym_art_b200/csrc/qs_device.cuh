@@ -96,7 +96,8 @@ struct Params {
   int ow_threads;                     // threads per CTA of a one-wave launch (32, 64 or 128)
   int obs_stages;                     // pipelined launch: observation tiles in shared memory (2, or 1 when that buys a resident CTA)
   int ow_extra;                       // A/B knob QUADSIM_OW_EXTRA: CTA slots per SM a one-wave launch leaves to its dependent launch
-  int host_ctas;                      // > 0: the launch reads / writes pinned HOST buffers (qs_step_host zero-copy): resident CTAs per SM
+  int host_io;                        // the launch reads / writes pinned HOST buffers across PCIe (qs_step_host zero-copy)
+  int host_ctas;                      // host_io launches: resident CTAs per SM (0 = as many as fit)
   int prefetch;                       // L2 prefetch of the CTA's first tile ahead of griddepcontrol.wait: 0 off, 1 bulk, 3 lines
   int spec_draw;                      // draw the step's noise ahead of griddepcontrol.wait from a speculative clock read
   int bounds_selftest;                // QS_DEBUG_BOUNDS builds: raise BC_SELFTEST (proves the reporting path end to end)
@@ -536,13 +537,15 @@ __device__ __forceinline__ void load_state(St<R>& s, const Params<R>& p, long lo
   finish_load(s);
 }
 
-template <typename R> __device__ __forceinline__ void st4p(char*& ptr, long long stride, R x, R y, R z, R w) {
+// CS: streaming (evict-first) store - one-wave launches only (see env_step_tma_kernel)
+template <typename R, bool CS = false> __device__ __forceinline__ void st4p(char*& ptr, long long stride, R x, R y, R z, R w) {
   V4<R> v; v.x = x; v.y = y; v.z = z; v.w = w;
-  *reinterpret_cast<V4<R>*>(ptr) = v;
+  if (CS && sizeof(R) == 4) __stcs(reinterpret_cast<float4*>(ptr), make_float4((float)x, (float)y, (float)z, (float)w));
+  else *reinterpret_cast<V4<R>*>(ptr) = v;
   ptr += stride;
 }
 
-template <typename R, class T>
+template <typename R, class T, bool CS = false>
 __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, long long i) {
 #ifdef QS_EXP_OLD_ADDR
   st4(p.state, p.n, 0, i, s.px, s.py, s.pz, s.vx);
@@ -556,13 +559,13 @@ __device__ __forceinline__ void store_state(const St<R>& s, const Params<R>& p, 
   QS_CHECK(p, i >= p.begin && i < p.end && p.end <= p.n && p.row_bytes == p.n * 4 * (long long)sizeof(R), BC_ENV);
   char* ptr = reinterpret_cast<char*>(p.state + i * 4);                 // row 0; rows are row_bytes apart
   const long long rb = p.row_bytes;
-  st4p(ptr, rb, s.px, s.py, s.pz, s.vx);
-  st4p(ptr, rb, s.vy, s.vz, s.wx, s.wy);
-  st4p(ptr, rb, s.wz, s.r[0], s.r[1], s.r[2]);
-  st4p(ptr, rb, s.r[3], s.r[4], s.r[5], s.r[6]);
-  st4p(ptr, rb, s.r[7], s.r[8], s.tick, s.ret);
-  st4p(ptr, rb, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
-  st4p(ptr, rb, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
+  st4p<R, CS>(ptr, rb, s.px, s.py, s.pz, s.vx);
+  st4p<R, CS>(ptr, rb, s.vy, s.vz, s.wx, s.wy);
+  st4p<R, CS>(ptr, rb, s.wz, s.r[0], s.r[1], s.r[2]);
+  st4p<R, CS>(ptr, rb, s.r[3], s.r[4], s.r[5], s.r[6]);
+  st4p<R, CS>(ptr, rb, s.r[7], s.r[8], s.tick, s.ret);
+  st4p<R, CS>(ptr, rb, s.rd[0], s.rd[1], s.rd[2], s.rd[3]);
+  st4p<R, CS>(ptr, rb, s.cd[0], s.cd[1], s.cd[2], s.cd[3]);
 #endif
   const bool ou_on = T::OU >= 0 ? (T::OU != 0) : (p.ou_on != 0);
   if (ou_on) st4(p.state, p.n, p.row_ou, i, s.ou[0], s.ou[1], s.ou[2], s.ou[3]);
@@ -1689,6 +1692,7 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
   const long long n_tiles = (p.end - p.begin + cta_envs - 1) / cta_envs;
   const long long G = gridDim.x;
   constexpr bool multi = !ONEWAVE;                                       // more tiles than resident CTAs
+  const bool stream_stores = ONEWAVE && !p.host_io;                // (see the state stores below)
 
   __shared__ unsigned int warps_read;
   if (!multi) {
@@ -1913,7 +1917,12 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
       }
     }
     if (active) {
-      store_state<R, T>(s, p, i);
+      // One-wave launches into DEVICE buffers store with the streaming (evict-first) hint: in the ring regime the lines written
+      // here are evicted long before anybody re-reads them, and marking them so lets L2 drop them first (5.81 -> 5.78 us per
+      // 65,536-env step; the L2-resident single-batch case 5.52 -> 5.49).  Not for the pipelined instantiation (+2 % at the
+      // HBM-resident sizes) and not for pinned host buffers (posted writes across PCIe were 3 % slower with it).
+      if (ONEWAVE && stream_stores) store_state<R, T, ONEWAVE>(s, p, i);
+      else store_state<R, T, false>(s, p, i);
       p.rew[i] = out.rew_sum;
       p.done[i] = out.done_any ? 1 : 0;
     }
@@ -1938,8 +1947,13 @@ env_step_tma_kernel(const __grid_constant__ Params<float> p) {
           const float4* t4 = reinterpret_cast<const float4*>(wtile) + lane;
           float4* d4 = reinterpret_cast<float4*>(dst) + lane;
           const float4 v0 = t4[0], v1 = t4[32], v2 = t4[64], v3 = t4[96];
-          d4[0] = v0; d4[32] = v1; d4[64] = v2; d4[96] = v3;
-          if (lane < 16) d4[128] = t4[128];
+          if (stream_stores) {
+            __stcs(d4, v0); __stcs(d4 + 32, v1); __stcs(d4 + 64, v2); __stcs(d4 + 96, v3);
+            if (lane < 16) __stcs(d4 + 128, t4[128]);
+          } else {
+            d4[0] = v0; d4[32] = v1; d4[64] = v2; d4[96] = v3;
+            if (lane < 16) d4[128] = t4[128];
+          }
         } else if ((total & 3) == 0) {
           const float4* t4 = reinterpret_cast<const float4*>(wtile);
           float4* d4 = reinterpret_cast<float4*>(dst);

@@ -282,7 +282,7 @@ int do_step(QsHandle* h, int k, const void* actions, void* obs, void* rew, uint8
   fill_params<R>(h, &p);
   p.k_steps = k;
   if (device_buffers) p.prefetch = h->prefetch;   // the L2 prefetch hint is for device memory (not for pinned host aliases)
-  else p.host_ctas = h->host_ctas;
+  else { p.host_io = 1; p.host_ctas = h->host_ctas; }
   p.clock_advance = advance;
   if (k > 1 && (h->cfg.n_agents > 1 || h->cfg.reward.log_pos || h->cfg.per_env_model)) p.feat |= qs::F_MISC;   // specialised kernels: k == 1 only
   if (!advance) p.pdl = 0;                       // chunk launches of the host pipeline follow copies on side streams
