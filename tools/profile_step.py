@@ -15,7 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg4", "drag", "noise", "vertical", "info"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg4", "drag", "noise", "vertical", "info", "t2w", "catchall", "pem_t2w"])
     ap.add_argument("--copy", action="store_true")
     a = ap.parse_args()
     kw = dict(device="cuda:0", ep_time=5, seed=1)
@@ -34,6 +34,17 @@ def main():
                          sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1), **kw)
     elif a.config == "vertical":
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="vertical", dim_mode="1D", **kw)
+    elif a.config == "t2w":
+        env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", obs_repr="xyz_vxyz_R_omega_t2w_t2t", sense_noise="default", **kw)
+    elif a.config == "catchall":
+        env = QuadVecEnv(a.envs, dynamics_params="Crazyflie", controller="raw", dynamics_change={
+            "motor": {"C_drag": 0.0028, "C_roll": 0.003, "linearity": 0.424}, "damp": {"vel": 0.001, "omega_quadratic": 0.015}},
+            sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1), **kw)
+    elif a.config == "pem_t2w":
+        import numpy as np
+        np.random.seed(7)
+        env = QuadVecEnv(a.envs, dynamics_params="RandomQuad", per_env_dynamics=256, controller="raw", obs_repr="xyz_vxyz_R_omega_t2w",
+                         sense_noise="default", **kw)
     elif a.config == "info":
         env = QuadVecEnv(a.envs, dynamics_params="DefaultQuad", controller="raw", info=True, **kw)
     else:
