@@ -489,6 +489,16 @@ def run_ours(args):
         others[cfg] = {"n_envs_per_gpu_step": n_o, "value": world * n_o * KO / (ms_o * 1e-3), "unit": "env-steps/s",
                        "ms_per_step": ms_o / KO, "kernel_variant": e.kernel_variant, "bytes_per_env_step": bytes_o,
                        "roofline_frac": n_o * bytes_o / (ms_o * 1e-3 / KO) / 1e9 / hbm_peak}
+        if cfg != "cfg5_64M_job":
+            # the same launch over one WHOLE episode (501 steps, the reset step included): trajectories evolve - under random
+            # actions the drones of a swarm end up in contact on the floor - and the data-dependent branches cost more late in
+            # an episode than in the first steps after a reset (tools/phase_of_episode.py)
+            ms_ep, _ = time_graph(torch, lambda i: e.step(a_o), EP_STEPS, 0, device, pg, chunk=EP_STEPS)
+            ms_ep = reduce_max(torch, pg, device, ms_ep)[0]
+            e.check_finite()
+            others[cfg]["whole_episode"] = {"steps": EP_STEPS, "ms_per_step": ms_ep / EP_STEPS,
+                                            "value": world * n_o * EP_STEPS / (ms_ep * 1e-3),
+                                            "roofline_frac": n_o * bytes_o / (ms_ep * 1e-3 / EP_STEPS) / 1e9 / hbm_peak}
         if cfg == "cfg5_64M_job":
             others[cfg].update(scaling="strong", n_envs_job=total64,
                                note="BASELINE configs[4]: ONE 64 M-env job sharded by env index over the GPUs of the run")

@@ -1302,30 +1302,41 @@ __device__ __forceinline__ R shfl(R v, int src) { return __shfl_sync(0xffffffffu
 // half_thr: this drone's half of the contact distance, collision_k * arm.  One model per handle: every pair touches at
 // collision_k * 2 * arm (p.coll_dist).  Per-env models (PEM): drones of one swarm may have different arms, the pair (i, j)
 // touches at collision_k * (arm_i + arm_j) - the partner's half arrives by shuffle.
-template <typename R, bool PEM>
+// FAST (fp32 throughput kernels): the distance by MUFU.RSQ (d2 * rsqrt(d2), ~2 ulp) and its reciprocal from the same rsqrt -
+// no IEEE square root or division in the pair loop.  Late in an episode under random actions the drones of a swarm lie in contact
+// on the floor and every pair takes the contact branch: the IEEE forms made those steps 28 % slower than the early ones
+// (tools/phase_of_episode.py: 120 -> 153 us per 2,097,152-drone step).
+template <typename R, bool PEM, bool FAST = false>
 __device__ __forceinline__ bool swarm_collide(St<R>& s, const Params<R>& p, R half_thr) {
   const int M = p.n_agents;
   const int lane = threadIdx.x & 31;
   const int base = lane & ~(M - 1);
   R dvx = R(0), dvy = R(0), dvz = R(0);
   bool hit = false;
-#pragma unroll 1
-  for (int j = 1; j < M; ++j) {
+  auto pair = [&](int j) {
     int src = base | ((lane + j) & (M - 1));
     R qx = shfl(s.px, src), qy = shfl(s.py, src), qz = shfl(s.pz, src);
     R dx = s.px - qx, dy = s.py - qy, dz = s.pz - qz;
-    R dist = Mth<R>::sqrt(dx * dx + dy * dy + dz * dz);
+    const R d2 = dx * dx + dy * dy + dz * dz;
+    R dist, is = R(0);
+    if (FAST && sizeof(R) == 4) { is = q_rsqrt<R, true>(Mth<R>::max(d2, R(1e-30))); dist = d2 * is; }
+    else dist = Mth<R>::sqrt(d2);
     bool c = dist < (PEM ? half_thr + shfl(half_thr, src) : p.coll_dist);
     hit = hit || c;
     // contacts are rare: the partner's velocity is fetched (warp-convergent shuffles) only when some lane needs it
     if (__any_sync(0xffffffffu, c)) {
       R ux = shfl(s.vx, src), uy = shfl(s.vy, src), uz = shfl(s.vz, src);
-      R inv = R(1) / Mth<R>::max(dist, R(1e-5));
+      R inv;
+      if (FAST && sizeof(R) == 4) inv = dist > R(1e-5) ? is : R(1e5);     // 1 / max(dist, 1e-5): is = 1 / dist wherever d2 >= 1e-30
+      else inv = R(1) / Mth<R>::max(dist, R(1e-5));
       R nx = dx * inv, ny = dy * inv, nz = dz * inv;
       R delta = (ux - s.vx) * nx + (uy - s.vy) * ny + (uz - s.vz) * nz;
       if (c && delta > R(0)) { dvx += delta * nx; dvy += delta * ny; dvz += delta * nz; }
     }
-  }
+  };
+  // (unrolling the seven partners of the BASELINE swarm size was measured slower: 117 -> 123 us early, 123 -> 133 us late)
+#pragma unroll 1
+  for (int j = 1; j < M; ++j) pair(j);
   s.vx += dvx; s.vy += dvy; s.vz += dvz;
   return hit;
 }
@@ -1440,7 +1451,7 @@ __device__ __forceinline__ void run_steps(St<R>& s, const Params<R>& p, long lon
       }
     }
     bool collided = false;
-    if (T::SWARM) { if (p.n_agents > 1) collided = swarm_collide<R, T::PEM>(s, p, T::PEM ? p.coll_k * m.arm() : R(0)); }
+    if (T::SWARM) { if (p.n_agents > 1) collided = swarm_collide<R, T::PEM, T::FASTM>(s, p, T::PEM ? p.coll_k * m.arm() : R(0)); }
     // ---- crash, reward, tick, done (:974-987) ----
     bool crashed = s.pz <= m.arm();                                     // :977
     R costs[20];
