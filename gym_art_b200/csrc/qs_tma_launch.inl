@@ -70,14 +70,18 @@ static cudaError_t launch_tma_t(const Params<float>& p_in, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   const int sms = sm_count();
   const long long slots = (long long)sms * per_sm;
-  // Up to ~1.8 x slots tiles the one-tile-per-CTA kernel still wins (measured, tools/mid_sweep.py: 9.4 vs 10.6 us at
-  // 81,920 envs, 12.0 vs 12.5 at 131,072, 14.4 vs 13.9 at 163,840): the excess CTAs start as residents retire - a natural
-  // partial second wave - while the persistent pipeline would run 1-2 tiles per CTA with nothing to overlap.
+  // Up to ~2.3 x slots tiles the one-tile-per-CTA kernel still wins (measured, tools/mid_sweep.py + tools/mid_ab.sh with the
+  // equal-depth waves below: 7.2 us at 81,920 envs, 10.6 at 131,072, 12.0 vs 12.7 at 147,456, 13.1 vs 13.5 at 163,840; three
+  // waves at 196,608 lose to the pipeline's 14.9): the CTAs beyond the first wave start as residents retire, while the
+  // persistent pipeline would run 1-2 tiles per CTA with nothing to overlap.
   static double factor = -1.0;
-  if (factor < 0.0) { const char* e = getenv("QUADSIM_ONEWAVE_FACTOR"); factor = e ? atof(e) : 1.8; }
-  // measured on B200 (tools/small_sweep.py): for grids under ~320 CTAs of 128 the dependent-launch hand-over costs more
-  // than the launch ramp it hides (5.1 vs 3.6 us per step at 128 CTAs); above, it wins (6.8 vs 7.5 us at 512 CTAs)
-  const bool pdl = p.pdl && n >= 320 * BLOCK;
+  if (factor < 0.0) { const char* e = getenv("QUADSIM_ONEWAVE_FACTOR"); factor = e ? atof(e) : 2.3; }
+  // Programmatic dependent launch at every size.  (Round 1 measured the hand-over costing more than it hid under ~40,960 envs;
+  // with the L2 prefetch, the speculative draws and the early clock advance ahead of griddepcontrol.wait it now wins
+  // everywhere - tools/small_sweep.py: 1,024 envs 3.79 -> 2.65 us per step, 16,384 envs 4.18 -> 3.03, 32,768 envs 5.28 -> 3.84.)
+  static long long pdl_min = -1;                       // A/B knob QUADSIM_PDL_MIN_ENVS
+  if (pdl_min < 0) { const char* e = getenv("QUADSIM_PDL_MIN_ENVS"); pdl_min = e ? atoll(e) : 0; }
+  const bool pdl = p.pdl && n >= pdl_min;
   if ((double)tiles <= factor * (double)slots) {
     // One wave: one tile per CTA, no ring.  The launch is latency-bound and its time is set by the fullest SM, so the
     // CTAs are made small (p.ow_threads = 64: two warps) and the shared-memory request is sized so that exactly
@@ -86,7 +90,31 @@ static cudaError_t launch_tma_t(const Params<float>& p_in, cudaStream_t st) {
     const unsigned threads = (p.ow_threads == 32 || p.ow_threads == 64) ? (unsigned)p.ow_threads : (unsigned)BLOCK;
     const long long ctas = (n + threads - 1) / threads;
     long long want = (ctas + sms - 1) / sms;
-    const long long reg_cap = (long long)cap * (BLOCK / threads);
+    // resident CTAs per SM the register file allows for THIS instantiation at this CTA size (asked of the runtime once per
+    // device; the one-wave instantiations need 80 - 100 registers, well under the 128 the launch bound promises: ten 64-thread
+    // CTAs instead of eight -> up to 94,720 envs in one evenly spread wave: 81,920 envs 9.5 -> 7.1 us)
+    static int occ_cache[64][3] = {};
+    const int ti = threads == 32 ? 0 : (threads == 64 ? 1 : 2);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = (dev >= 0 && dev < 64) ? occ_cache[dev][ti] : 0;
+    if (occ == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_step_tma_kernel<T, true>, (int)threads,
+                                                        (size_t)threads * p.obs_dim * sizeof(float)) != cudaSuccess || occ <= 0) {
+        cudaGetLastError();
+        occ = cap * (BLOCK / (int)threads);
+      }
+      if (dev >= 0 && dev < 64) occ_cache[dev][ti] = occ;
+    }
+    static int reg_cap_knob = -1;                      // A/B knob QUADSIM_OW_REGCAP: 0 = the launch-bound formula (round 2: 8)
+    if (reg_cap_knob < 0) { const char* e = getenv("QUADSIM_OW_REGCAP"); reg_cap_knob = e ? atoi(e) : 1; }
+    const long long reg_cap = reg_cap_knob ? (long long)occ : (long long)cap * (BLOCK / threads);
+    // More CTAs than fit at once: waves of EQUAL depth rather than one full wave and a remainder (131,072 envs = 2,048 CTAs: two
+    // waves of 7 per SM take 11.1 us, 10 + 4 per SM 12.1 us - a wave costs its latency chain however thin it is).
+    if (reg_cap_knob && want > reg_cap) {
+      const long long waves = (want + reg_cap - 1) / reg_cap;
+      want = (want + waves - 1) / waves;
+    }
     const int extra = p.ow_extra;                      // A/B knob: CTA slots per SM left free for the dependent launch
     want += extra;
     if (want > reg_cap + extra) want = reg_cap + extra;

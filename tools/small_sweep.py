@@ -2,7 +2,7 @@ import sys
 sys.path.insert(0, "/root/repo")
 import torch, bench
 dev = torch.device("cuda", 0)
-for n in (1024, 8192, 16384, 32768, 49152, 65536, 75776):
+for n in (1024, 4096, 8192, 12288, 16384, 24576, 32768, 40960, 49152, 65536, 75776):
     ring = 16
     envs, acts = [], []
     for b in range(ring):
