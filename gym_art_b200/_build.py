@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libquadsim.so")
 FAST = ["qs_fast_%s_%s.cu" % (c, n) for c in ("raw", "omega", "mellinger", "shifted", "velyaw") for n in ("philox", "inject")]
-GENERIC = ["qs_tma_generic_%s_%s.cu" % (f, n) for f in ("all", "drag", "noise", "misc", "info") for n in ("philox", "inject")]
+GENERIC = ["qs_tma_generic_%s_%s.cu" % (f, n) for f in ("all", "drag", "noise", "misc", "info", "dragnoise") for n in ("philox", "inject")]
 SOURCES = ["qs_kernels_f32.cu", "qs_kernels_f64.cu", "quadsim_abi.cu"] + GENERIC + FAST
 DEPS = ["qs_device.cuh", "qs_kernels.inl", "qs_fast.inl", "qs_tma_launch.inl", "qs_tma_generic.inl", os.path.join("..", "..", "include", "quadsim.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -2266,6 +2266,8 @@ QS_DECL_FAST(launch_tma_generic_misc_philox);
 QS_DECL_FAST(launch_tma_generic_misc_inject);
 QS_DECL_FAST(launch_tma_generic_info_philox);
 QS_DECL_FAST(launch_tma_generic_info_inject);
+QS_DECL_FAST(launch_tma_generic_dragnoise_philox);   // ... and the one two-group pairing with a kernel of its own: F_DRAG | F_NOISEX
+QS_DECL_FAST(launch_tma_generic_dragnoise_inject);
 #undef QS_DECL_FAST
 
 }  // namespace qs

@@ -54,6 +54,8 @@ cudaError_t launch_step<QS_REAL>(const Params<QS_REAL>& p, cudaStream_t st, cons
       if (p.feat == F_DRAG) return p.inject ? launch_tma_generic_drag_inject(p, st, name) : launch_tma_generic_drag_philox(p, st, name);
       if (p.feat == F_NOISEX) return p.inject ? launch_tma_generic_noise_inject(p, st, name) : launch_tma_generic_noise_philox(p, st, name);
       if (p.feat == F_INFO) return p.inject ? launch_tma_generic_info_inject(p, st, name) : launch_tma_generic_info_philox(p, st, name);
+      // drag model + full sensor noise (the sim-to-real pairing): 0.49 of its byte model through the catch-all
+      if (p.feat == (F_DRAG | F_NOISEX)) return p.inject ? launch_tma_generic_dragnoise_inject(p, st, name) : launch_tma_generic_dragnoise_philox(p, st, name);
       if (p.feat == F_MISC || p.feat == F_NONE) return p.inject ? launch_tma_generic_misc_inject(p, st, name) : launch_tma_generic_misc_philox(p, st, name);
     }
     return p.inject ? launch_tma_generic_all_inject(p, st, name) : launch_tma_generic_all_philox(p, st, name);

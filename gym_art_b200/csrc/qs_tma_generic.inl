@@ -5,6 +5,7 @@
 //   F_NOISEX  uniform / quaternion / gyro-bias noise only   }  sim_steps = 2 (substeps unrolled, OU draws hoisted)
 //   F_MISC    1D / 2D, goals, quaternion / t2w layouts      }
 //   F_INFO    diagnostics buffer only                       }
+//   F_DRAG | F_NOISEX   the one two-group pairing with its own kernel (drag model + full sensor noise), sim_steps = 2
 // One translation unit per family and noise source, so that they compile in parallel.
 #include "qs_device.cuh"
 #include "qs_tma_launch.inl"

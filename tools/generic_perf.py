@@ -18,7 +18,8 @@ cases = [
     ("misc: info buffer bound (+192 B)", dict(controller="raw", info=True), 349 + 192, "float32"),
     ("misc: quaternion observation xyz_vxyz_quat_omega (O=13: 329 B)", dict(controller="raw", obs_repr="xyz_vxyz_quat_omega"), 329, "float32"),
     ("misc: xyz_vxyz_R_omega_t2w_t2t + default noise (O=20: 357 B)", dict(controller="raw", obs_repr="xyz_vxyz_R_omega_t2w_t2t", sense_noise="default"), 357, "float32"),
-    ("catch-all: drag + full sensor noise", dict(controller="raw", dynamics_change=DRAG, sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1)), 349 + 24, "float32"),
+    ("pair family: drag + full sensor noise", dict(controller="raw", dynamics_change=DRAG, sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1)), 349 + 24, "float32"),
+    ("catch-all: quaternion observation + full sensor noise (O=13)", dict(controller="raw", obs_repr="xyz_vxyz_quat_omega", sense_noise=dict(pos_unif_range=0.01, quat_norm_std=0.01, gyro_norm_std=0.1)), 329 + 24, "float32"),
     ("per-env models (RandomQuad x256), raw, plain shape (+112 B model rows)", dict(controller="raw", dynamics_params="RandomQuad", per_env_dynamics=256), 461, "float32"),
     ("per-env models, perturbed motors (RelativeSampler: linearity < 1) (+144 B)", dict(controller="raw", per_env_dynamics=256, dyn_sampler_1={"class": "RelativeSampler", "noise_ratio": 0.1}), 349 + 144, "float32"),
     ("per-env models + t2w observation + default noise (O=19, +128 B)", dict(controller="raw", dynamics_params="RandomQuad", per_env_dynamics=256, obs_repr="xyz_vxyz_R_omega_t2w", sense_noise="default"), 353 + 128, "float32"),
@@ -28,7 +29,7 @@ cases = [
 for name, kw, nbytes, dtype in cases:
     m = n if dtype == "float32" else n // 4
     kw = dict(kw)
-    kw.setdefault("dynamics_params", "Crazyflie" if "drag" in name else "DefaultQuad")
+    kw.setdefault("dynamics_params", "Crazyflie" if "drag" in name else "DefaultQuad")   # (the drag model is the CrazyFlie's)
     if kw.get("formation") == "ring8":
         from gym_art_b200.quadrotor_multi.quadrotor_multi import ring_goals
         kw["formation"] = ring_goals(8)
