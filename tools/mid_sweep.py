@@ -9,7 +9,7 @@ import bench  # noqa: E402
 
 dev = torch.device("cuda", 0)
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-for n in (73728, 81920, 90112, 98304, 114688, 131072, 147456, 163840, 196608, 262144):
+for n in [int(x) for x in os.environ.get("MID_SIZES", "73728,81920,90112,98304,114688,131072,147456,163840,196608,262144").split(",")]:
     ring = max(1, min(16, (300 << 20) // (n * 349) + 1))
     envs, acts = [], []
     for b in range(ring):
