@@ -1,5 +1,6 @@
-"""GPU, needs 2+ devices (skipped on a single-GPU box): one process per GPU over NCCL with env-index sharding and
-the per-episode statistics all-reduce; and two handles on two devices inside one process."""
+"""GPU: one process per rank with env-index sharding and the per-episode statistics all-reduce - over NCCL on two devices (needs
+2+ GPUs, skipped on a single-GPU box), and over gloo with both ranks sharing cuda:0 (runs anywhere); two handles on two devices
+inside one process (needs 2+ GPUs)."""
 import os
 import socket
 
@@ -28,12 +29,16 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_total, T, out):
+def _worker(rank, world, port, n_total, T, out, share_gpu=False):
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    local = 0 if share_gpu else rank
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(local))
+    torch.cuda.set_device(local)
+    if share_gpu:       # both ranks on cuda:0 (NCCL refuses two ranks on one device): gloo carries the 24-byte all-reduce
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from gym_art_b200.sharding import episode_stats, make_sharded_env
     env = make_sharded_env(n_total, dynamics_params="Crazyflie", controller="mellinger", sense_noise="default",
                            init_random_state=True, ep_time=0.1, seed=21)
@@ -51,15 +56,14 @@ def _worker(rank, world, port, n_total, T, out):
     dist.destroy_process_group()
 
 
-@needs2
-def test_two_rank_nccl_job_equals_single_gpu_job(tmp_path):
+def _two_rank_job_equals_single_gpu_job(tmp_path, share_gpu):
     import torch
     import torch.multiprocessing as mp
     from gym_art_b200 import QuadVecEnv
     from gym_art_b200.stats import all_reduce_stats
     n_total, T = 100000 + 37, 45
     out = str(tmp_path / "w2.npz")
-    mp.spawn(_worker, args=(2, _free_port(), n_total, T, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n_total, T, out, share_gpu), nprocs=2, join=True)
     env = QuadVecEnv(n_total, dynamics_params="Crazyflie", controller="mellinger", sense_noise="default",
                      init_random_state=True, ep_time=0.1, seed=21)
     env.reset()
@@ -70,6 +74,18 @@ def test_two_rank_nccl_job_equals_single_gpu_job(tmp_path):
     assert np.array_equal(two["obs"], o.cpu().numpy())          # Philox is keyed by the global env id
     assert float(two["n"]) == one["episodes"] == 4 * n_total
     assert abs(float(two["mean"]) - one["mean"]) < 1e-9 and abs(float(two["std"]) - one["std"]) < 1e-7
+
+
+@needs2
+def test_two_rank_nccl_job_equals_single_gpu_job(tmp_path):
+    _two_rank_job_equals_single_gpu_job(tmp_path, share_gpu=False)
+
+
+def test_two_rank_job_sharing_one_gpu_equals_single_gpu_job(tmp_path):
+    """The same two-process sharded job on a single-GPU box: both ranks step their env-index block on cuda:0 (two processes,
+    two handles, kernels of both interleaving on one device) and all-reduce their episode statistics over gloo - trajectories
+    and job statistics equal the one-process job bit for bit.  (Runs where the NCCL variant above has to be skipped.)"""
+    _two_rank_job_equals_single_gpu_job(tmp_path, share_gpu=True)
 
 
 @needs2
