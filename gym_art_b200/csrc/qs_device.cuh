@@ -1031,9 +1031,15 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Md
   if (obs_acc) accelerometer(s, p, acc);
   R qo[4] = {R(1), R(0), R(0), R(0)};
   if (obs_quat) {                                                       // R2quat, quad_utils.py:101-109 (single branch)
-    R w = Mth<R>::sqrt(R(1) + s.r[0] + s.r[4] + s.r[8]) / R(2);
-    R w4 = R(4) * w;
-    qo[0] = w; qo[1] = (s.r[7] - s.r[5]) / w4; qo[2] = (s.r[2] - s.r[6]) / w4; qo[3] = (s.r[3] - s.r[1]) / w4;
+    const R t = R(1) + s.r[0] + s.r[4] + s.r[8];
+    if (T::FASTM && sizeof(R) == 4 && t > R(1e-12)) {                   // fp32: w = sqrt(t) / 2 and 1 / (4 w) from one MUFU.RSQ
+      const R is = q_rsqrt<R, true>(t), i4 = R(0.5) * is;
+      qo[0] = R(0.5) * (t * is); qo[1] = (s.r[7] - s.r[5]) * i4; qo[2] = (s.r[2] - s.r[6]) * i4; qo[3] = (s.r[3] - s.r[1]) * i4;
+    } else {                                                            // (t <= 0: the reference's own 0 / 0 and NaN cases)
+      R w = Mth<R>::sqrt(t) / R(2);
+      R w4 = R(4) * w;
+      qo[0] = w; qo[1] = (s.r[7] - s.r[5]) / w4; qo[2] = (s.r[2] - s.r[6]) / w4; qo[3] = (s.r[3] - s.r[1]) / w4;
+    }
   }
   if (sense) {
     R z[3];
@@ -1112,11 +1118,11 @@ __device__ __forceinline__ void build_obs(St<R>& s, const Params<R>& p, const Md
       ns.obs3(reset_obs, 10, false, z);
       R w = m.t2w(), sc = p.t2w_half_std * w;
       R nw = clampr(w + (sc < R(0) ? -sc : sc) * z[0], R(1.5), R(10));              // quadrotor.py:707-708
-      o[30] = (nw - R(1.5)) / (R(10) - R(1.5));
+      o[30] = (T::FASTM && sizeof(R) == 4) ? (nw - R(1.5)) * R(1.0 / 8.5) : (nw - R(1.5)) / (R(10) - R(1.5));
       if (p.obs_t2t) {
         w = m.t2t(); sc = p.t2t_half_std * w;
         nw = clampr(w + (sc < R(0) ? -sc : sc) * z[1], R(0.005), R(1));             // quadrotor.py:711-712
-        o[31] = (nw - R(0.005)) / (R(1) - R(0.005));
+        o[31] = (T::FASTM && sizeof(R) == 4) ? (nw - R(0.005)) * R(1.0 / 0.995) : (nw - R(0.005)) / (R(1) - R(0.005));
       }
     }
   }
