@@ -116,3 +116,21 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_every_translation_unit_is_in_the_build_list_and_every_family_launcher_is_defined():
+    """A .cu file under csrc/ that the build script does not list would silently drop its kernels (and every launcher the device
+    header declares must be defined by exactly one translation unit, or the library would not load)."""
+    import glob
+    import re
+    from gym_art_b200 import _build
+    csrc = os.path.join(ROOT, "gym_art_b200", "csrc")
+    on_disk = sorted(os.path.basename(p) for p in glob.glob(os.path.join(csrc, "*.cu")))
+    assert on_disk == sorted(_build.SOURCES)
+    declared = re.findall(r"QS_DECL_FAST\((launch_\w+)\);", open(os.path.join(csrc, "qs_device.cuh")).read())
+    defined = []
+    for f in on_disk:
+        m = re.search(r"#define QS_(?:FAST|GEN)_NAME (launch_\w+)", open(os.path.join(csrc, f)).read())
+        if m:
+            defined.append(m.group(1))
+    assert sorted(declared) == sorted(defined) and len(set(defined)) == len(defined)
